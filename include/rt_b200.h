@@ -1,0 +1,274 @@
+/*
+ * rt_b200.h — C ABI of the B200-native path-tracing core for rs-pathtracing.
+ *
+ * This is the drop-in boundary: everything the Rust crate's FFI (`-sys` crate whose
+ * build.rs runs nvcc) would bind for the hot path.  Plain C, plain pointers and sizes,
+ * no C++ / torch types.  All `path:line` citations are into the reference repository
+ * (dkarpushkin/rs-pathtracing).
+ *
+ * The reference has no FFI layer of its own; the seam that this ABI sits under is
+ *   pub trait Renderer { start_rendering, render_step, stop_rendering }   src/renderer/mod.rs:47-56
+ *   ThreadPoolRenderer::new(scene, thread_number, depth)                  src/renderer/step_by_step.rs:37
+ *   Scene::closest_hit(&Ray, min_t, max_t)                                src/world/mod.rs:42-44
+ *   renderer::trace_pixel_samples(&(idx, rays), &Scene, depth)            src/renderer/mod.rs:151-155
+ *
+ * Conventions
+ *   - every entry point returns 0 (RT_OK) or a negative rt_status; nothing unwinds or aborts
+ *     across the boundary; rt_last_error() gives the message of the calling thread's last failure.
+ *   - the caller owns every host buffer; the library owns every device buffer unless a
+ *     function is documented as taking a caller-supplied DEVICE pointer.
+ *   - handles are not thread-safe (the reference calls the Renderer from one UI thread).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
+ *     RT_ERR_NO_DEVICE.
+ */
+#ifndef RT_B200_H
+#define RT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_B200_ABI_VERSION 1
+
+typedef enum rt_status {
+    RT_OK = 0,
+    RT_ERR_INVALID = -1,    /* bad argument / malformed scene description            */
+    RT_ERR_NO_DEVICE = -2,  /* no CUDA device (the product path never falls back)     */
+    RT_ERR_CUDA = -3,       /* a CUDA runtime call failed; see rt_last_error()        */
+    RT_ERR_STATE = -4,      /* call out of order (poll without start, ...)            */
+    RT_ERR_NOMEM = -5
+} rt_status;
+
+/* ---- POD mirrors of the reference's algebra / camera types ------------------------- */
+
+/* algebra::Vector3d, src/algebra/mod.rs:23-28 (needs a #[repr(C)] mirror on the Rust side) */
+typedef struct rt_vec3 { double x, y, z; } rt_vec3;
+
+/* world::ray::Ray, src/world/ray.rs:5-9.  `direction` is what Ray::new produced (unit length,
+ * ray.rs:12-17); the library never renormalises a caller-supplied ray. */
+typedef struct rt_ray { rt_vec3 origin, direction; } rt_ray;
+
+/* camera::Camera after Camera::new, src/camera/mod.rs:36-46,71-88:
+ * direction/up/right are the derived unit vectors, fov in RADIANS. */
+typedef struct rt_camera {
+    rt_vec3 position, direction, up, right;
+    double fov_rad, focal_length;
+} rt_camera;
+
+/* camera::ray_caster::ImageParams, src/camera/ray_caster.rs:10-14 */
+typedef struct rt_image_params { uint32_t width, height; } rt_image_params;
+
+/* ---- flat scene description (structure of arrays) ---------------------------------- */
+
+/* Shape::ray_intersect implementations on the hot path, src/world/shapes/mod.rs:181,250,330 and
+ * src/world/shapes/ray_marching.rs:20 */
+enum {
+    RT_SHAPE_SPHERE = 0,     /* unit sphere, flag bit0 = inverse_normal                         */
+    RT_SHAPE_CUBE = 1,       /* unit box [-1,1]^3                                               */
+    RT_SHAPE_RECTANGLE = 2,  /* z = 0 plane clipped to [x0,x1]x[y0,y1]; params = x0,y0,x1,y1    */
+    RT_SHAPE_MARCH = 3       /* RayMarchingShape; params below                                  */
+};
+#define RT_SHAPE_FLAG_INVERSE_NORMAL 1u
+
+/* ShapeFunction implementations, src/world/shapes/ray_marching.rs:121-520 */
+enum {
+    RT_SURF_HEART = 0,   /* bound: ellipsoid radii (1.45, 1.45/2.05, 1.45)                      */
+    RT_SURF_SINE = 1,    /* params a, sphere_radius                                              */
+    RT_SURF_STAR = 2,    /* params a, sphere_radius                                              */
+    RT_SURF_DUPIN = 3,   /* params a, b, c, d, sphere_radius                                     */
+    RT_SURF_HUNTS = 4,   /* params sphere_radius                                                 */
+    RT_SURF_CUSHION = 5  /* params sphere_radius                                                 */
+};
+
+/* params[i][8] layout
+ *   RECTANGLE: [0]=x0 [1]=y0 [2]=x1 [3]=y1
+ *   MARCH:     [0]=surface kind (as double) [1]=step [2]=depth (as double, u8 in the reference)
+ *              [3]=a [4]=b [5]=c [6]=d [7]=sphere_radius
+ *   SPHERE/CUBE: unused (zero)
+ */
+#define RT_SHAPE_PARAMS 8
+
+/* Material implementations, src/world/material.rs:36-134 */
+enum {
+    RT_MAT_LAMBERTIAN = 0,   /* texture = albedo                       */
+    RT_MAT_METAL = 1,        /* texture = albedo, scalar = fuzz        */
+    RT_MAT_DIELECTRIC = 2,   /* scalar = index_of_refraction           */
+    RT_MAT_DIFFUSE_LIGHT = 3,/* texture = emit                         */
+    RT_MAT_EMPTY = 4
+};
+typedef struct rt_material {
+    uint32_t kind;
+    uint32_t texture;   /* index into textures[] (ignored for DIELECTRIC / EMPTY) */
+    double scalar;
+} rt_material;
+
+/* Texture implementations, src/world/texture.rs:10-117 (NoiseTexture is out of scope) */
+enum {
+    RT_TEX_SOLID = 0,      /* color                                                   */
+    RT_TEX_CHECKER = 1,    /* color = multipliers (x,y,z); odd/even texture indices   */
+    RT_TEX_UV_CHECKER = 2, /* color.x/.y = multipliers .0/.1; odd/even                */
+    RT_TEX_IMAGE = 3       /* image = index into images[]                             */
+};
+typedef struct rt_texture {
+    uint32_t kind;
+    uint32_t odd, even;   /* child texture indices; children always precede nothing in particular,
+                             but the graph must be acyclic and at most RT_TEX_MAX_DEPTH deep */
+    uint32_t image;
+    rt_vec3 color;
+} rt_texture;
+#define RT_TEX_MAX_DEPTH 8
+
+/* image::RgbaImage, row-major, 4 bytes per texel, row 0 = top (src/world/texture.rs:98-117) */
+typedef struct rt_image {
+    uint32_t width, height;
+    const uint8_t* rgba;
+} rt_image;
+
+typedef struct rt_scene_desc {
+    uint32_t n_shapes;
+    const uint8_t* kind;        /* [n_shapes]                                                   */
+    const uint8_t* flags;       /* [n_shapes]                                                   */
+    const double* inverse;      /* [n_shapes][12]: rows 0..2 of InversableTransform.inverse     */
+    const double* direct;       /* [n_shapes][12]: rows 0..2 of InversableTransform.direct      */
+    const double* params;       /* [n_shapes][RT_SHAPE_PARAMS]                                  */
+    const uint32_t* material;   /* [n_shapes] index into materials[]                            */
+    uint32_t n_materials;
+    const rt_material* materials;
+    uint32_t n_textures;
+    const rt_texture* textures;
+    uint32_t n_images;
+    const rt_image* images;
+} rt_scene_desc;
+
+typedef struct rt_scene rt_scene;   /* opaque: the device-resident scene + renderer state */
+
+/* ---- library ------------------------------------------------------------------------ */
+
+int rt_abi_version(void);
+const char* rt_last_error(void);
+/* number of visible CUDA devices (0 on a CPU-only host; never fails) */
+int rt_device_count(void);
+
+/* ---- scene -------------------------------------------------------------------------- */
+
+/* Upload a flattened Scene to `device` (replaces Arc<RwLock<Scene>> handed to
+ * ThreadPoolRenderer::new, src/renderer/step_by_step.rs:37).  The description is copied;
+ * the caller may free it afterwards. */
+int rt_scene_create(const rt_scene_desc* desc, int device, rt_scene** out);
+void rt_scene_destroy(rt_scene* scene);
+
+/* ---- batched nearest hit (replaces Scene::closest_hit, src/world/mod.rs:42-44, with the
+ *      ShapeCollection semantics of src/world/shapes/mod.rs:573-597) -------------------- */
+
+/* mode for rt_intersect_batch */
+enum {
+    RT_ISECT_BRUTE = 0,   /* one thread per ray walks the whole shape list in index order: the
+                             literal restatement of ShapeCollection::ray_intersect             */
+    RT_ISECT_FAST = 1     /* conservative culling + exact FP64 test on the survivors; provably the
+                             same result as RT_ISECT_BRUTE (degenerate rays fall back to it)     */
+};
+
+/* Host buffers in, host buffers out.  Any output pointer may be NULL.
+ *   shape_index[i] = winning shape, -1 = miss
+ *   t[i]           = RayHit.distance
+ *   normal[i]      = RayHit.normal() after set_normal (unit, facing the ray), world space
+ *   point[i]       = RayHit.point (direct transform of the object-space hit point)
+ *   uv[2i..2i+1]   = RayHit.u, RayHit.v
+ *   front_face[i]  = RayHit.is_front_face
+ */
+int rt_intersect_batch(rt_scene* scene, const rt_ray* rays, uint64_t n, double t_min, double t_max,
+                       int mode, int32_t* shape_index, double* t, rt_vec3* normal, rt_vec3* point,
+                       double* uv, uint8_t* front_face);
+
+/* Same, with every pointer a DEVICE pointer on the scene's device and no copies; runs on
+ * `stream` (a cudaStream_t passed as void*, NULL = the library's stream) and does not
+ * synchronise.  Used for kernel-only timing and by callers that keep rays resident. */
+int rt_intersect_batch_device(rt_scene* scene, const rt_ray* d_rays, uint64_t n, double t_min,
+                              double t_max, int mode, int32_t* d_shape_index, double* d_t,
+                              rt_vec3* d_normal, rt_vec3* d_point, double* d_uv,
+                              uint8_t* d_front_face, void* stream);
+
+/* ---- frame rendering (replaces the Renderer trait, src/renderer/mod.rs:47-56) -------- */
+
+typedef struct rt_render_params {
+    rt_image_params image;
+    uint32_t samples_number;   /* start_rendering's samples_number                               */
+    uint32_t max_depth;        /* ThreadPoolRenderer::new's depth (ray_color's depth argument)   */
+    uint64_t seed;             /* counter-based RNG key                                          */
+    /* image sharding (one process per GPU): this handle renders the tiles t with
+     * t % shard_count == shard_index, tiles numbered row-major.  1 / 0 = whole image. */
+    uint32_t shard_count, shard_index;
+    uint32_t tile_width, tile_height;   /* 0 = default (32 x 32)                                 */
+} rt_render_params;
+
+/* Renderer::start_rendering: returns immediately, work proceeds on the library's stream. */
+int rt_render_start(rt_scene* scene, const rt_camera* camera, const rt_render_params* params);
+
+/* Renderer::render_step: non-blocking.  Writes the pixels finished so far into
+ * buffer[x + y*width] (linear per-pixel mean radiance, src/renderer/mod.rs:151-155; pixels of
+ * other shards are left untouched) and sets *done to 1 when the frame (this shard) is
+ * complete, exactly like render_step's bool. */
+int rt_render_poll(rt_scene* scene, rt_vec3* buffer, int* done);
+
+/* Blocking convenience: waits for completion, then behaves like a final rt_render_poll. */
+int rt_render_wait(rt_scene* scene, rt_vec3* buffer);
+
+/* Renderer::stop_rendering: abandons the frame in flight (no-op when idle). */
+int rt_render_stop(rt_scene* scene);
+
+/* Device-side result of the last started frame, for callers that gather shards over NCCL:
+ * a float4 (r,g,b sums; w = samples) per owned pixel, tile-packed in this shard's tile order
+ * (tile-major, row-major inside a tile, tiles clipped at the image border are still padded to
+ * tile_width*tile_height).  *d_accum is a device pointer owned by the library, valid until the
+ * next rt_render_start / rt_scene_destroy; *n_float4 its length.  The frame must be complete. */
+int rt_render_device_result(rt_scene* scene, const void** d_accum, uint64_t* n_float4);
+
+/* number of float4 slots a shard owns (so every rank can size the gather) */
+uint64_t rt_shard_float4_count(const rt_render_params* params, uint32_t shard_index);
+
+/* Assemble a full frame from the gathered shard buffers (all DEVICE pointers on the scene's
+ * device): d_shards[s] = shard s's tile-packed float4 buffer; d_frame = w*h rt_vec3 (x + y*w,
+ * linear mean).  Runs on `stream` (NULL = library stream), does not synchronise. */
+int rt_assemble_frame(rt_scene* scene, const rt_render_params* params, const void* const* d_shards,
+                      rt_vec3* d_frame, void* stream);
+
+/* Frame post-process of the bins (src/bin/main_raylib.rs:239-247): sqrt, clamp(0,0.999)*256 ->
+ * RGBA8, alpha 255.  Host in / host out convenience running on the device. */
+int rt_tonemap_rgba8(rt_scene* scene, const rt_vec3* frame, uint64_t n_pixels, uint8_t* rgba);
+
+/* ---- pixel probe (replaces renderer::trace_pixel_samples, src/renderer/mod.rs:151-155) */
+
+/* Traces caller-supplied primary rays (host buffer) as samples of ONE pixel and returns their
+ * mean radiance; RNG keyed by (seed, pixel_index, sample = ray number). */
+int rt_trace_pixel_samples(rt_scene* scene, const rt_ray* rays, uint32_t n_rays, uint32_t max_depth,
+                           uint64_t seed, uint32_t pixel_index, rt_vec3* mean_out);
+
+/* ---- instrumentation ---------------------------------------------------------------- */
+
+typedef struct rt_stats {
+    uint64_t kernel_launches;   /* kernels launched by the library since the last reset         */
+    uint64_t paths;             /* primary paths started                                        */
+    uint64_t segments;          /* ray segments traced (nearest-hit queries)                    */
+    uint64_t shape_tests;       /* exact FP64 shape tests executed                              */
+    uint64_t cull_tests;        /* conservative pre-tests executed                              */
+    uint64_t march_steps;       /* implicit-surface function evaluations                        */
+    uint64_t march_rays;        /* (ray, marching shape) pairs marched                          */
+    double last_frame_ms;       /* device time of the last completed frame (CUDA events)        */
+    double last_intersect_ms;   /* device time of the last rt_intersect_batch kernel            */
+} rt_stats;
+int rt_get_stats(rt_scene* scene, rt_stats* out);
+int rt_reset_stats(rt_scene* scene);
+/* enable (1) / disable (0) the per-kernel work counters above (segments..march_rays); counting
+ * costs a few atomics per block and is off by default.  kernel_launches / *_ms are always on. */
+int rt_set_counters(rt_scene* scene, int enabled);
+
+/* FP64 / FP32 FMA micro-benchmarks used as roofline denominators (TFLOP/s, FMA = 2 flop). */
+int rt_measure_peaks(int device, double* fp64_tflops, double* fp32_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_B200_H */

@@ -1,0 +1,1036 @@
+// rt_core.cu — the CUDA core behind include/rt_b200.h (sm_100a).
+//
+// Kernels
+//   k_intersect_batch   batched nearest hit (Scene::closest_hit with ShapeCollection semantics)
+//   k_raygen            MultisamplerRayCaster::next for a batch of pixels x samples
+//   k_bounce            one segment of ray_color for every live path: nearest hit, scatter / emit /
+//                       sky, survivors compacted into the next queue (ballot + popc + one atomic per warp)
+//   k_resolve           per-pixel mean (trace_pixel_samples) -> float4 accumulator + f64 frame
+//   k_assemble          multi-GPU: gathered tile-packed shards -> frame
+//   k_tonemap           the bins' sqrt / clamp / *256 -> RGBA8
+// Compile with -fmad=false (see rt_math.cuh).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "rt_scene.cuh"
+
+using namespace rt;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// path state: structure of arrays in HBM, two queues (ping-pong per bounce)
+// ------------------------------------------------------------------------------------------------
+struct PathQueue {
+    double *ox, *oy, *oz, *dx, *dy, *dz;  // ray
+    double *bx, *by, *bz;                 // throughput (product of attenuations so far)
+    uint32_t* pid;                        // path id inside the batch = pixel_local * spp + sample
+};
+
+struct ShardMap {  // which pixels this handle owns, in "owned order" (tile-major)
+    uint32_t width, height, tile_w, tile_h, tiles_x, tiles_y, shard_count, shard_index;
+    __host__ __device__ uint32_t tile_pixels() const { return tile_w * tile_h; }
+    // owned pixel index -> (x, y); false for the padding of clipped border tiles
+    __host__ __device__ bool pixel_of(uint64_t q, uint32_t& x, uint32_t& y) const {
+        uint32_t tp = tile_w * tile_h;
+        uint32_t j = (uint32_t)(q / tp), r = (uint32_t)(q % tp);
+        uint32_t k = shard_index + j * shard_count;
+        uint32_t ty = k / tiles_x, tx = k % tiles_x;
+        x = tx * tile_w + r % tile_w;
+        y = ty * tile_h + r / tile_w;
+        return x < width && y < height;
+    }
+};
+
+static ShardMap make_shard_map(const rt_render_params& p, uint32_t shard_index) {
+    ShardMap m;
+    m.width = p.image.width;
+    m.height = p.image.height;
+    m.shard_count = p.shard_count ? p.shard_count : 1;
+    m.shard_index = shard_index;
+    if (m.shard_count == 1) {  // whole image: rows, so owned order == x + y*width
+        m.tile_w = m.width;
+        m.tile_h = 1;
+    } else {
+        m.tile_w = p.tile_width ? p.tile_width : 32;
+        m.tile_h = p.tile_height ? p.tile_height : 32;
+    }
+    m.tiles_x = (m.width + m.tile_w - 1) / m.tile_w;
+    m.tiles_y = (m.height + m.tile_h - 1) / m.tile_h;
+    return m;
+}
+static uint64_t owned_tiles(const ShardMap& m) {
+    uint64_t total = (uint64_t)m.tiles_x * m.tiles_y;
+    if (m.shard_index >= total) return 0;
+    return (total - m.shard_index + m.shard_count - 1) / m.shard_count;
+}
+
+struct RayCasterDev {  // MultisamplerRayCaster, src/camera/ray_caster.rs:17-48
+    D3 camera_position, camera_right, camera_up, left_top;
+    double pixel_resolution;
+};
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory staging of the shape list (inverse rows + kind): every lane of a warp reads the
+// same shape at the same time, so each read is a conflict-free broadcast
+// ------------------------------------------------------------------------------------------------
+struct Staged {
+    const double* inv;
+    const uint8_t* kind;
+};
+__device__ __forceinline__ Staged stage_scene(const DevScene& S, bool use_smem) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    if (!use_smem) return Staged{S.inv, S.kind};
+    double* s_inv = reinterpret_cast<double*>(smem_raw);
+    uint8_t* s_kind = reinterpret_cast<uint8_t*>(s_inv + (size_t)12 * S.n_shapes);
+    const int n12 = 12 * S.n_shapes;
+    // 16-byte vector copies: rows are 96 B, cudaMalloc aligns the base
+    const double2* src = reinterpret_cast<const double2*>(S.inv);
+    double2* dst = reinterpret_cast<double2*>(s_inv);
+    for (int k = threadIdx.x; k < n12 / 2; k += blockDim.x) dst[k] = src[k];
+    for (int k = threadIdx.x; k < S.n_shapes; k += blockDim.x) s_kind[k] = S.kind[k];
+    __syncthreads();
+    return Staged{s_inv, s_kind};
+}
+
+__device__ __forceinline__ void flush_counters(const DevCounters& c, DevCounters* g) {
+    // warp-reduce, one atomic per warp and counter
+    unsigned long long v[5] = {c.segments, c.shape_tests, c.cull_tests, c.march_steps, c.march_rays};
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        unsigned long long x = v[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        v[k] = x;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&g->segments, v[0]);
+        atomicAdd(&g->shape_tests, v[1]);
+        atomicAdd(&g->cull_tests, v[2]);
+        atomicAdd(&g->march_steps, v[3]);
+        atomicAdd(&g->march_rays, v[4]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2/K3: batched nearest hit
+// ------------------------------------------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(256)
+k_intersect_batch(DevScene S, bool use_smem, const rt_ray* __restrict__ rays, unsigned long long n, double t_min,
+                  double t_max, int32_t* __restrict__ shape_index, double* __restrict__ t_out,
+                  rt_vec3* __restrict__ normal, rt_vec3* __restrict__ point, double* __restrict__ uv,
+                  uint8_t* __restrict__ front_face, DevCounters* g_counters) {
+    Staged st = stage_scene(S, use_smem);
+    DevCounters c = {0, 0, 0, 0, 0};
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        rt_ray r = rays[i];
+        D3 ro = mk(r.origin.x, r.origin.y, r.origin.z), rd = mk(r.direction.x, r.direction.y, r.direction.z);
+        double bt;
+        int bi;
+        nearest_hit_brute<COUNT>(S, st.inv, st.kind, ro, rd, t_min, t_max, bt, bi, c);
+        if (shape_index) shape_index[i] = bi;
+        if (bi < 0) {
+            if (t_out) t_out[i] = 0.0;
+            if (normal) normal[i] = rt_vec3{0.0, 0.0, 0.0};
+            if (point) point[i] = rt_vec3{0.0, 0.0, 0.0};
+            if (uv) { uv[2 * i] = 0.0; uv[2 * i + 1] = 0.0; }
+            if (front_face) front_face[i] = 0;
+            continue;
+        }
+        if (t_out) t_out[i] = bt;
+        if (normal || point || uv || front_face) {
+            HitRec h;
+            finalize_hit(S, bi, bt, ro, rd, h);
+            if (normal) normal[i] = rt_vec3{h.normal.x, h.normal.y, h.normal.z};
+            if (point) point[i] = rt_vec3{h.point.x, h.point.y, h.point.z};
+            if (uv) { uv[2 * i] = h.u; uv[2 * i + 1] = h.v; }
+            if (front_face) front_face[i] = h.front ? 1 : 0;
+        }
+    }
+    if (COUNT) flush_counters(c, g_counters);
+}
+
+// ------------------------------------------------------------------------------------------------
+// wavefront path tracer
+// ------------------------------------------------------------------------------------------------
+// warp-aggregated append: returns this lane's slot in the destination queue (valid when `alive`)
+__device__ __forceinline__ uint32_t queue_append(bool alive, uint32_t* counter) {
+    unsigned mask = __ballot_sync(0xffffffffu, alive);
+    if (mask == 0) return 0;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
+
+// K1: primary rays.  Batch = pixels [first_owned, first_owned + n_pixels) of this shard x spp samples,
+// path id = pixel_local * spp + sample.  Padding pixels of clipped tiles produce no path.
+__global__ void __launch_bounds__(256)
+k_raygen(RayCasterDev rc, ShardMap map, unsigned long long first_owned, uint32_t n_pixels, uint32_t spp,
+         uint32_t k0, uint32_t k1, PathQueue q, uint32_t* count_out, float4* __restrict__ radiance) {
+    const unsigned long long n = (unsigned long long)n_pixels * spp;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    // round the trip count up so that whole warps stay converged for the ballot in queue_append
+    const unsigned long long n_round = (n + 31ull) & ~31ull;
+    for (unsigned long long id = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; id < n_round; id += stride) {
+        bool alive = false;
+        D3 dir = mk(0.0, 0.0, 0.0);
+        if (id < n) {
+            uint32_t pl = (uint32_t)(id / spp), s = (uint32_t)(id % spp);
+            uint32_t x, y;
+            if (map.pixel_of(first_owned + pl, x, y)) {
+                PathRng rng;
+                rng.k0 = k0; rng.k1 = k1;
+                rng.pixel = x + y * map.width;
+                rng.sample = s;
+                rng.begin_event(0);
+                double u = rng.next();   // ray_caster.rs:106-107
+                double v = rng.next();
+                // :109-112
+                D3 d = rc.left_top + (rc.pixel_resolution * ((double)x + u)) * rc.camera_right -
+                       (rc.pixel_resolution * ((double)y + v)) * rc.camera_up;
+                dir = normalize(d - rc.camera_position);  // Ray::new
+                alive = true;
+            } else {
+                radiance[id] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        uint32_t slot = queue_append(alive, count_out);
+        if (alive) {
+            q.ox[slot] = rc.camera_position.x; q.oy[slot] = rc.camera_position.y; q.oz[slot] = rc.camera_position.z;
+            q.dx[slot] = dir.x; q.dy[slot] = dir.y; q.dz[slot] = dir.z;
+            q.bx[slot] = 1.0; q.by[slot] = 1.0; q.bz[slot] = 1.0;
+            q.pid[slot] = (uint32_t)id;
+        }
+    }
+}
+
+// One segment of ray_color (src/renderer/mod.rs:23-45), iteratively: `level` = number of hits so
+// far, the reference's `depth` argument at this call is max_depth - level.
+template <bool COUNT>
+__global__ void __launch_bounds__(256)
+k_bounce(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ count_in, PathQueue out,
+         uint32_t* count_out, uint32_t level, uint32_t max_depth, ShardMap map, unsigned long long first_owned,
+         uint32_t spp, uint32_t k0, uint32_t k1, float4* __restrict__ radiance, DevCounters* g_counters) {
+    Staged st = stage_scene(S, use_smem);
+    DevCounters c = {0, 0, 0, 0, 0};
+    const uint32_t n = *count_in;
+    const uint32_t n_round = (n + 31u) & ~31u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool alive = false;
+        D3 no = mk(0, 0, 0), nd = mk(0, 0, 0), nb = mk(0, 0, 0);
+        uint32_t pid = 0;
+        if (i < n) {
+            D3 ro = mk(in.ox[i], in.oy[i], in.oz[i]);
+            D3 rd = mk(in.dx[i], in.dy[i], in.dz[i]);
+            D3 beta = mk(in.bx[i], in.by[i], in.bz[i]);
+            pid = in.pid[i];
+            double bt;
+            int bi;
+            nearest_hit_brute<COUNT>(S, st.inv, st.kind, ro, rd, 0.001, INFINITY, bt, bi, c);  // mod.rs:24
+            D3 L = mk(0.0, 0.0, 0.0);
+            if (bi < 0) {
+                L = hadamard(beta, sky(rd));  // :41-43
+            } else if (level == max_depth) {
+                // depth == 0: black (:26-27)
+            } else {
+                HitRec h;
+                finalize_hit(S, bi, bt, ro, rd, h);
+                uint32_t pl = pid / spp, s = pid % spp, x, y;
+                map.pixel_of(first_owned + pl, x, y);
+                PathRng rng;
+                rng.k0 = k0; rng.k1 = k1;
+                rng.pixel = x + y * map.width;
+                rng.sample = s;
+                rng.begin_event(level + 1);
+                D3 ndir, atten;
+                if (scatter_or_emit(S, h, rd, rng, ndir, atten)) {  // :29-32
+                    alive = true;
+                    no = h.point;
+                    nd = ndir;
+                    nb = hadamard(beta, atten);
+                } else {
+                    L = hadamard(beta, atten);  // :34-36
+                }
+            }
+            if (!alive) radiance[pid] = make_float4((float)L.x, (float)L.y, (float)L.z, 1.0f);
+        }
+        uint32_t slot = queue_append(alive, count_out);
+        if (alive) {
+            out.ox[slot] = no.x; out.oy[slot] = no.y; out.oz[slot] = no.z;
+            out.dx[slot] = nd.x; out.dy[slot] = nd.y; out.dz[slot] = nd.z;
+            out.bx[slot] = nb.x; out.by[slot] = nb.y; out.bz[slot] = nb.z;
+            out.pid[slot] = pid;
+        }
+    }
+    if (COUNT) flush_counters(c, g_counters);
+}
+
+// K5: per-pixel mean of the batch (trace_pixel_samples, src/renderer/mod.rs:151-155).  One thread
+// per owned pixel; the float4 accumulator keeps (sum rgb, samples) for the NCCL path, the frame
+// buffer the f64 mean for the host path.
+__global__ void __launch_bounds__(256)
+k_resolve(const float4* __restrict__ radiance, uint32_t n_pixels, uint32_t spp, unsigned long long first_owned,
+          float4* __restrict__ accum, rt_vec3* __restrict__ frame_owned) {
+    uint32_t pl = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pl >= n_pixels) return;
+    const float4* r = radiance + (size_t)pl * spp;
+    double sx = 0.0, sy = 0.0, sz = 0.0;
+    for (uint32_t s = 0; s < spp; s++) {
+        float4 v = r[s];
+        sx += (double)v.x; sy += (double)v.y; sz += (double)v.z;
+    }
+    accum[first_owned + pl] = make_float4((float)sx, (float)sy, (float)sz, (float)spp);
+    double ln = (double)spp;
+    frame_owned[first_owned + pl] = rt_vec3{sx / ln, sy / ln, sz / ln};
+}
+
+// K7: de-interleave gathered shards into the frame (x + y*w, f64 linear mean)
+struct ShardPtrs {
+    const float4* p[16];
+};
+__global__ void __launch_bounds__(256)
+k_assemble(ShardPtrs shards, ShardMap map0, rt_vec3* __restrict__ frame) {
+    uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= map0.width || y >= map0.height) return;
+    uint32_t tx = x / map0.tile_w, ty = y / map0.tile_h;
+    uint32_t k = ty * map0.tiles_x + tx;
+    uint32_t s = k % map0.shard_count, j = k / map0.shard_count;
+    size_t q = (size_t)j * map0.tile_pixels() + (size_t)(y % map0.tile_h) * map0.tile_w + (x % map0.tile_w);
+    float4 v = shards.p[s][q];
+    double w = (double)v.w;
+    frame[(size_t)y * map0.width + x] = rt_vec3{(double)v.x / w, (double)v.y / w, (double)v.z / w};
+}
+
+// src/bin/main_raylib.rs:239-247
+__global__ void __launch_bounds__(256)
+k_tonemap(const rt_vec3* __restrict__ frame, unsigned long long n, uchar4* __restrict__ rgba) {
+    unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rt_vec3 c = frame[i];
+    double r = sqrt(c.x), g = sqrt(c.y), b = sqrt(c.z);
+    // f64::clamp keeps NaN, and `NaN as u8` is 0
+    auto q = [](double v) -> unsigned char {
+        if (isnan(v)) return 0;
+        double cl = fmin(fmax(v, 0.0), 0.999);
+        return (unsigned char)(cl * 256.0);
+    };
+    rgba[i] = make_uchar4(q(r), q(g), q(b), 255);
+}
+
+// scatter owned-order pixels into a full frame (host path of a sharded render keeps it simple and
+// does this on the host; this kernel serves rt_trace_pixel_samples' ray upload)
+__global__ void __launch_bounds__(256)
+k_load_rays(const rt_ray* __restrict__ rays, uint32_t n, PathQueue q, uint32_t* count_out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *count_out = n;
+    if (i >= n) return;
+    rt_ray r = rays[i];
+    q.ox[i] = r.origin.x; q.oy[i] = r.origin.y; q.oz[i] = r.origin.z;
+    q.dx[i] = r.direction.x; q.dy[i] = r.direction.y; q.dz[i] = r.direction.z;
+    q.bx[i] = 1.0; q.by[i] = 1.0; q.bz[i] = 1.0;
+    q.pid[i] = i;
+}
+
+// FMA micro-benchmarks: 8 independent chains per thread, FMA counted as 2 flop
+template <typename T>
+__global__ void __launch_bounds__(256) k_fma_peak(T* out, int iters, T a, T b) {
+    T x0 = (T)threadIdx.x, x1 = x0 + (T)1, x2 = x0 + (T)2, x3 = x0 + (T)3, x4 = x0 + (T)4, x5 = x0 + (T)5,
+      x6 = x0 + (T)6, x7 = x0 + (T)7;
+    for (int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct Batch {
+    uint64_t first_owned;
+    uint32_t n_pixels;
+    cudaEvent_t done;
+};
+
+struct rt_scene {
+    int device = 0;
+    int n_sm = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    DevScene ds{};
+    std::vector<void*> allocs;  // scene arrays
+    bool use_smem = false;
+    size_t smem_bytes = 0;
+    int grid = 0;
+
+    // instrumentation
+    bool counters_on = false;
+    DevCounters* d_counters = nullptr;
+    uint64_t launches = 0, paths = 0;
+    double last_frame_ms = 0.0, last_intersect_ms = 0.0;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+
+    // render state
+    bool rendering = false, frame_complete = false;
+    rt_render_params rp{};
+    ShardMap map{};
+    uint64_t owned_pixels = 0;   // incl. tile padding
+    uint64_t path_capacity = 0;  // allocated queue capacity (paths)
+    PathQueue q[2]{};
+    std::vector<void*> qallocs;
+    float4* d_radiance = nullptr;
+    uint32_t* d_counts = nullptr;  // one counter per level, per batch slot (reset per batch)
+    float4* d_accum = nullptr;
+    rt_vec3* d_frame = nullptr;    // owned order
+    uint64_t frame_capacity = 0;
+    std::vector<Batch> batches;
+    size_t delivered = 0;          // batches already copied to the caller
+    cudaEvent_t ev_frame_start = nullptr, ev_frame_stop = nullptr;
+    std::vector<rt_vec3> host_stage;  // sharded poll: owned-order staging
+};
+
+template <class T>
+static int upload(rt_scene* sc, const T* src, size_t count, const T** out) {
+    void* d = nullptr;
+    size_t bytes = std::max<size_t>(count * sizeof(T), 16);
+    CU(cudaMalloc(&d, bytes));
+    sc->allocs.push_back(d);
+    if (count) CU(cudaMemcpy(d, src, count * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (const T*)d;
+    return RT_OK;
+}
+
+static size_t env_size(const char* name, size_t dflt) {
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    return (size_t)strtoull(v, nullptr, 10);
+}
+
+extern "C" {
+
+int rt_abi_version(void) { return RT_B200_ABI_VERSION; }
+const char* rt_last_error(void) { return g_err.c_str(); }
+
+int rt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+static int validate_desc(const rt_scene_desc* d) {
+    if (!d) return fail(RT_ERR_INVALID, "null scene description");
+    if (d->n_shapes && (!d->kind || !d->flags || !d->inverse || !d->direct || !d->params || !d->material))
+        return fail(RT_ERR_INVALID, "scene description: null shape array");
+    if ((d->n_materials && !d->materials) || (d->n_textures && !d->textures) || (d->n_images && !d->images))
+        return fail(RT_ERR_INVALID, "scene description: null table");
+    for (uint32_t i = 0; i < d->n_shapes; i++) {
+        if (d->kind[i] > RT_SHAPE_MARCH) return fail(RT_ERR_INVALID, "scene description: unknown shape kind");
+        if (d->material[i] >= d->n_materials) return fail(RT_ERR_INVALID, "scene description: material index out of range");
+        if (d->kind[i] == RT_SHAPE_MARCH) {
+            double sk = d->params[(size_t)i * RT_SHAPE_PARAMS];
+            if (!(sk >= 0 && sk <= RT_SURF_CUSHION)) return fail(RT_ERR_INVALID, "scene description: unknown surface kind");
+        }
+    }
+    for (uint32_t i = 0; i < d->n_materials; i++) {
+        const rt_material& m = d->materials[i];
+        if (m.kind > RT_MAT_EMPTY) return fail(RT_ERR_INVALID, "scene description: unknown material kind");
+        bool needs_tex = m.kind == RT_MAT_LAMBERTIAN || m.kind == RT_MAT_METAL || m.kind == RT_MAT_DIFFUSE_LIGHT;
+        if (needs_tex && m.texture >= d->n_textures) return fail(RT_ERR_INVALID, "scene description: texture index out of range");
+    }
+    for (uint32_t i = 0; i < d->n_textures; i++) {
+        const rt_texture& t = d->textures[i];
+        if (t.kind > RT_TEX_IMAGE) return fail(RT_ERR_INVALID, "scene description: unknown texture kind");
+        if ((t.kind == RT_TEX_CHECKER || t.kind == RT_TEX_UV_CHECKER) && (t.odd >= d->n_textures || t.even >= d->n_textures))
+            return fail(RT_ERR_INVALID, "scene description: child texture index out of range");
+        if (t.kind == RT_TEX_IMAGE && t.image >= d->n_images) return fail(RT_ERR_INVALID, "scene description: image index out of range");
+    }
+    for (uint32_t i = 0; i < d->n_images; i++)
+        if (!d->images[i].rgba || !d->images[i].width || !d->images[i].height)
+            return fail(RT_ERR_INVALID, "scene description: empty image");
+    return RT_OK;
+}
+
+int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
+    if (!out) return fail(RT_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    int rc = validate_desc(d);
+    if (rc != RT_OK) return rc;
+    int ndev = rt_device_count();
+    if (ndev == 0) return fail(RT_ERR_NO_DEVICE, "no CUDA device: the path-tracing core has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(RT_ERR_INVALID, "device index out of range");
+    CU(cudaSetDevice(device));
+    rt_scene* sc = new rt_scene();
+    sc->device = device;
+    auto bail = [&](int code) {
+        rt_scene_destroy(sc);
+        return code;
+    };
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return bail(fail(RT_ERR_CUDA, "cudaGetDeviceProperties failed"));
+    sc->n_sm = prop.multiProcessorCount;
+    sc->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&sc->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(fail(RT_ERR_CUDA, "cudaStreamCreate failed"));
+    cudaEventCreate(&sc->ev_a);
+    cudaEventCreate(&sc->ev_b);
+    cudaEventCreate(&sc->ev_frame_start);
+    cudaEventCreate(&sc->ev_frame_stop);
+
+    const uint32_t n = d->n_shapes;
+    sc->ds.n_shapes = (int)n;
+    if ((rc = upload(sc, d->inverse, (size_t)n * 12, &sc->ds.inv)) != RT_OK) return bail(rc);
+    if ((rc = upload(sc, d->direct, (size_t)n * 12, &sc->ds.dir)) != RT_OK) return bail(rc);
+    if ((rc = upload(sc, d->params, (size_t)n * RT_SHAPE_PARAMS, &sc->ds.params)) != RT_OK) return bail(rc);
+    if ((rc = upload(sc, d->kind, (size_t)n, &sc->ds.kind)) != RT_OK) return bail(rc);
+    if ((rc = upload(sc, d->flags, (size_t)n, &sc->ds.flags)) != RT_OK) return bail(rc);
+    if ((rc = upload(sc, d->material, (size_t)n, &sc->ds.material)) != RT_OK) return bail(rc);
+    if ((rc = upload(sc, d->materials, (size_t)d->n_materials, &sc->ds.materials)) != RT_OK) return bail(rc);
+    if ((rc = upload(sc, d->textures, (size_t)d->n_textures, &sc->ds.textures)) != RT_OK) return bail(rc);
+    std::vector<DevImage> imgs(d->n_images);
+    for (uint32_t i = 0; i < d->n_images; i++) {
+        imgs[i].width = d->images[i].width;
+        imgs[i].height = d->images[i].height;
+        if ((rc = upload(sc, d->images[i].rgba, (size_t)4 * imgs[i].width * imgs[i].height, &imgs[i].rgba)) != RT_OK) return bail(rc);
+    }
+    if ((rc = upload(sc, imgs.data(), imgs.size(), &sc->ds.images)) != RT_OK) return bail(rc);
+    std::vector<int> march;
+    for (uint32_t i = 0; i < n; i++)
+        if (d->kind[i] == RT_SHAPE_MARCH) march.push_back((int)i);
+    sc->ds.n_march = (int)march.size();
+    if ((rc = upload(sc, march.data(), march.size(), &sc->ds.march_index)) != RT_OK) return bail(rc);
+
+    // shared-memory staging: 96 B of inverse rows + 1 B kind per shape
+    sc->smem_bytes = (size_t)n * 12 * sizeof(double) + ((n + 15) & ~15u);
+    sc->use_smem = n > 0 && sc->smem_bytes <= sc->smem_optin;
+    if (!sc->use_smem) sc->smem_bytes = 0;
+    if (sc->smem_bytes > 48 * 1024) {
+        cudaFuncSetAttribute(k_intersect_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+        cudaFuncSetAttribute(k_intersect_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+        cudaFuncSetAttribute(k_bounce<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+        cudaFuncSetAttribute(k_bounce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+    }
+    // persistent grid: a whole number of CTAs per SM
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce<false>, 256, sc->smem_bytes);
+    if (per_sm < 1) per_sm = 1;
+    sc->grid = sc->n_sm * per_sm;
+
+    if (cudaMalloc(&sc->d_counters, sizeof(DevCounters)) != cudaSuccess) return bail(fail(RT_ERR_NOMEM, "cudaMalloc failed"));
+    cudaMemset(sc->d_counters, 0, sizeof(DevCounters));
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return bail(fail(RT_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e)));
+    *out = sc;
+    return RT_OK;
+}
+
+static void free_render_buffers(rt_scene* sc) {
+    for (void* p : sc->qallocs) cudaFree(p);
+    sc->qallocs.clear();
+    cudaFree(sc->d_radiance); sc->d_radiance = nullptr;
+    cudaFree(sc->d_counts); sc->d_counts = nullptr;
+    cudaFree(sc->d_accum); sc->d_accum = nullptr;
+    cudaFree(sc->d_frame); sc->d_frame = nullptr;
+    sc->path_capacity = 0;
+    sc->frame_capacity = 0;
+    for (Batch& b : sc->batches) cudaEventDestroy(b.done);
+    sc->batches.clear();
+}
+
+void rt_scene_destroy(rt_scene* sc) {
+    if (!sc) return;
+    cudaSetDevice(sc->device);
+    if (sc->stream) cudaStreamSynchronize(sc->stream);
+    free_render_buffers(sc);
+    for (void* p : sc->allocs) cudaFree(p);
+    cudaFree(sc->d_counters);
+    if (sc->ev_a) cudaEventDestroy(sc->ev_a);
+    if (sc->ev_b) cudaEventDestroy(sc->ev_b);
+    if (sc->ev_frame_start) cudaEventDestroy(sc->ev_frame_start);
+    if (sc->ev_frame_stop) cudaEventDestroy(sc->ev_frame_stop);
+    if (sc->stream) cudaStreamDestroy(sc->stream);
+    if (sc->copy_stream) cudaStreamDestroy(sc->copy_stream);
+    delete sc;
+}
+
+// ---- batched nearest hit -----------------------------------------------------------------------
+int rt_intersect_batch_device(rt_scene* sc, const rt_ray* d_rays, uint64_t n, double t_min, double t_max, int mode,
+                              int32_t* d_idx, double* d_t, rt_vec3* d_normal, rt_vec3* d_point, double* d_uv,
+                              uint8_t* d_ff, void* stream) {
+    if (!sc) return fail(RT_ERR_INVALID, "null scene");
+    if (mode != RT_ISECT_BRUTE && mode != RT_ISECT_FAST) return fail(RT_ERR_INVALID, "unknown intersect mode");
+    if (n == 0) return RT_OK;
+    if (!d_rays) return fail(RT_ERR_INVALID, "null rays");
+    CU(cudaSetDevice(sc->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : sc->stream;
+    uint64_t want = (n + 255) / 256;
+    int grid = (int)std::min<uint64_t>(want, (uint64_t)sc->grid);
+    if (sc->counters_on)
+        k_intersect_batch<true><<<grid, 256, sc->smem_bytes, st>>>(sc->ds, sc->use_smem, d_rays, n, t_min, t_max, d_idx,
+                                                                   d_t, d_normal, d_point, d_uv, d_ff, sc->d_counters);
+    else
+        k_intersect_batch<false><<<grid, 256, sc->smem_bytes, st>>>(sc->ds, sc->use_smem, d_rays, n, t_min, t_max, d_idx,
+                                                                    d_t, d_normal, d_point, d_uv, d_ff, sc->d_counters);
+    sc->launches++;
+    CU(cudaGetLastError());
+    return RT_OK;
+}
+
+int rt_intersect_batch(rt_scene* sc, const rt_ray* rays, uint64_t n, double t_min, double t_max, int mode,
+                       int32_t* idx, double* t, rt_vec3* normal, rt_vec3* point, double* uv, uint8_t* ff) {
+    if (!sc) return fail(RT_ERR_INVALID, "null scene");
+    if (n == 0) return RT_OK;
+    if (!rays) return fail(RT_ERR_INVALID, "null rays");
+    CU(cudaSetDevice(sc->device));
+    rt_ray* d_rays = nullptr;
+    int32_t* d_idx = nullptr;
+    double *d_t = nullptr, *d_uv = nullptr;
+    rt_vec3 *d_n = nullptr, *d_p = nullptr;
+    uint8_t* d_ff = nullptr;
+    int rc = RT_OK;
+    auto cleanup = [&]() {
+        cudaFree(d_rays); cudaFree(d_idx); cudaFree(d_t); cudaFree(d_uv); cudaFree(d_n); cudaFree(d_p); cudaFree(d_ff);
+    };
+#define CUX(call)                                                                             \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            cleanup();                                                                        \
+            return fail(RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+        }                                                                                     \
+    } while (0)
+    CUX(cudaMalloc(&d_rays, n * sizeof(rt_ray)));
+    if (idx) CUX(cudaMalloc(&d_idx, n * sizeof(int32_t)));
+    if (t) CUX(cudaMalloc(&d_t, n * sizeof(double)));
+    if (uv) CUX(cudaMalloc(&d_uv, 2 * n * sizeof(double)));
+    if (normal) CUX(cudaMalloc(&d_n, n * sizeof(rt_vec3)));
+    if (point) CUX(cudaMalloc(&d_p, n * sizeof(rt_vec3)));
+    if (ff) CUX(cudaMalloc(&d_ff, n));
+    CUX(cudaMemcpyAsync(d_rays, rays, n * sizeof(rt_ray), cudaMemcpyHostToDevice, sc->stream));
+    CUX(cudaEventRecord(sc->ev_a, sc->stream));
+    rc = rt_intersect_batch_device(sc, d_rays, n, t_min, t_max, mode, d_idx, d_t, d_n, d_p, d_uv, d_ff, sc->stream);
+    if (rc != RT_OK) {
+        cleanup();
+        return rc;
+    }
+    CUX(cudaEventRecord(sc->ev_b, sc->stream));
+    if (idx) CUX(cudaMemcpyAsync(idx, d_idx, n * sizeof(int32_t), cudaMemcpyDeviceToHost, sc->stream));
+    if (t) CUX(cudaMemcpyAsync(t, d_t, n * sizeof(double), cudaMemcpyDeviceToHost, sc->stream));
+    if (uv) CUX(cudaMemcpyAsync(uv, d_uv, 2 * n * sizeof(double), cudaMemcpyDeviceToHost, sc->stream));
+    if (normal) CUX(cudaMemcpyAsync(normal, d_n, n * sizeof(rt_vec3), cudaMemcpyDeviceToHost, sc->stream));
+    if (point) CUX(cudaMemcpyAsync(point, d_p, n * sizeof(rt_vec3), cudaMemcpyDeviceToHost, sc->stream));
+    if (ff) CUX(cudaMemcpyAsync(ff, d_ff, n, cudaMemcpyDeviceToHost, sc->stream));
+    CUX(cudaStreamSynchronize(sc->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, sc->ev_a, sc->ev_b);
+    sc->last_intersect_ms = ms;
+    cleanup();
+#undef CUX
+    return RT_OK;
+}
+
+// ---- rendering ---------------------------------------------------------------------------------
+static RayCasterDev make_raycaster(const rt_camera& cam, rt_image_params img) {
+    // MultisamplerRayCaster::new, src/camera/ray_caster.rs:30-48 (host FP64: needs libm tan).
+    // This file is compiled with -fmad=false, which also governs host code generated by nvcc's
+    // host compiler pass?  No: host code goes to g++, so -ffp-contract=off is passed via -Xcompiler.
+    auto V = [](rt_vec3 a) { return D3{a.x, a.y, a.z}; };
+    D3 pos = V(cam.position), dir = V(cam.direction), right = V(cam.right), up = V(cam.up);
+    D3 center = {pos.x + dir.x * cam.focal_length, pos.y + dir.y * cam.focal_length, pos.z + dir.z * cam.focal_length};
+    double aspect_ratio = (double)img.width / (double)img.height;
+    double viewport_width = tan(cam.fov_rad / 2.0) * cam.focal_length * 2.0;
+    double viewport_height = viewport_width / aspect_ratio;
+    double hw = viewport_width / 2.0, hh = viewport_height / 2.0;
+    RayCasterDev rc;
+    rc.left_top = D3{(center.x - hw * right.x) + hh * up.x, (center.y - hw * right.y) + hh * up.y,
+                     (center.z - hw * right.z) + hh * up.z};
+    rc.pixel_resolution = viewport_width / (double)img.width;
+    rc.camera_position = pos;
+    rc.camera_right = right;
+    rc.camera_up = up;
+    return rc;
+}
+
+static int alloc_queue(rt_scene* sc, PathQueue& q, uint64_t cap) {
+    double** d[9] = {&q.ox, &q.oy, &q.oz, &q.dx, &q.dy, &q.dz, &q.bx, &q.by, &q.bz};
+    for (int k = 0; k < 9; k++) {
+        void* p = nullptr;
+        CU(cudaMalloc(&p, cap * sizeof(double)));
+        sc->qallocs.push_back(p);
+        *d[k] = (double*)p;
+    }
+    void* p = nullptr;
+    CU(cudaMalloc(&p, cap * sizeof(uint32_t)));
+    sc->qallocs.push_back(p);
+    q.pid = (uint32_t*)p;
+    return RT_OK;
+}
+
+#define RT_MAX_LEVELS 64  // counters per batch: level 0 .. max_depth + 1
+
+// enqueue the bounce loop for paths already in q[0] (count in d_counts[0]); no host sync
+static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long first_owned, uint32_t spp, uint64_t seed) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (uint32_t level = 0; level <= max_depth; level++) {
+        PathQueue& in = sc->q[level & 1];
+        PathQueue& out = sc->q[(level + 1) & 1];
+        if (sc->counters_on)
+            k_bounce<true><<<sc->grid, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, sc->d_counts + level, out,
+                                                                          sc->d_counts + level + 1, level, max_depth, sc->map,
+                                                                          first_owned, spp, k0, k1, sc->d_radiance, sc->d_counters);
+        else
+            k_bounce<false><<<sc->grid, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, sc->d_counts + level, out,
+                                                                           sc->d_counts + level + 1, level, max_depth, sc->map,
+                                                                           first_owned, spp, k0, k1, sc->d_radiance, sc->d_counters);
+        sc->launches++;
+    }
+}
+
+static int ensure_path_buffers(rt_scene* sc, uint64_t need_paths) {
+    if (sc->path_capacity >= need_paths) return RT_OK;
+    for (void* p : sc->qallocs) cudaFree(p);
+    sc->qallocs.clear();
+    cudaFree(sc->d_radiance); sc->d_radiance = nullptr;
+    sc->path_capacity = 0;
+    int rc;
+    if ((rc = alloc_queue(sc, sc->q[0], need_paths)) != RT_OK) return rc;
+    if ((rc = alloc_queue(sc, sc->q[1], need_paths)) != RT_OK) return rc;
+    CU(cudaMalloc(&sc->d_radiance, need_paths * sizeof(float4)));
+    if (!sc->d_counts) CU(cudaMalloc(&sc->d_counts, RT_MAX_LEVELS * sizeof(uint32_t)));
+    sc->path_capacity = need_paths;
+    return RT_OK;
+}
+
+int rt_render_start(rt_scene* sc, const rt_camera* cam, const rt_render_params* p) {
+    if (!sc || !cam || !p) return fail(RT_ERR_INVALID, "null argument");
+    if (p->image.width == 0 || p->image.height == 0 || p->samples_number == 0)
+        return fail(RT_ERR_INVALID, "empty image or zero samples");
+    if (p->max_depth + 2 > RT_MAX_LEVELS) return fail(RT_ERR_INVALID, "max_depth too large (limit 62)");
+    uint32_t shard_count = p->shard_count ? p->shard_count : 1;
+    if (p->shard_index >= shard_count) return fail(RT_ERR_INVALID, "shard_index >= shard_count");
+    if (shard_count > 16) return fail(RT_ERR_INVALID, "at most 16 shards");
+    if ((uint64_t)p->image.width * p->image.height > 0xFFFFFFFFull) return fail(RT_ERR_INVALID, "image too large");
+    CU(cudaSetDevice(sc->device));
+    if (sc->rendering) rt_render_stop(sc);
+
+    sc->rp = *p;
+    sc->rp.shard_count = shard_count;
+    sc->map = make_shard_map(sc->rp, p->shard_index);
+    sc->owned_pixels = owned_tiles(sc->map) * sc->map.tile_pixels();
+
+    const uint32_t spp = p->samples_number;
+    uint64_t cap_paths = env_size("RT_B200_BATCH_PATHS", (size_t)1 << 22);
+    uint64_t px_per_batch = std::max<uint64_t>(1, cap_paths / spp);
+    px_per_batch = std::min<uint64_t>(px_per_batch, std::max<uint64_t>(sc->owned_pixels, 1));
+    if (px_per_batch * spp > 0xFFFFFFF0ull) return fail(RT_ERR_INVALID, "samples_number too large for one batch");
+    int rc = ensure_path_buffers(sc, px_per_batch * spp);
+    if (rc != RT_OK) return rc;
+    if (sc->frame_capacity < sc->owned_pixels) {
+        cudaFree(sc->d_accum); cudaFree(sc->d_frame);
+        sc->d_accum = nullptr; sc->d_frame = nullptr; sc->frame_capacity = 0;
+        CU(cudaMalloc(&sc->d_accum, std::max<uint64_t>(sc->owned_pixels, 1) * sizeof(float4)));
+        CU(cudaMalloc(&sc->d_frame, std::max<uint64_t>(sc->owned_pixels, 1) * sizeof(rt_vec3)));
+        sc->frame_capacity = sc->owned_pixels;
+    }
+    for (Batch& b : sc->batches) cudaEventDestroy(b.done);
+    sc->batches.clear();
+    sc->delivered = 0;
+
+    RayCasterDev rcd = make_raycaster(*cam, p->image);
+    uint32_t k0 = (uint32_t)p->seed, k1 = (uint32_t)(p->seed >> 32);
+    CU(cudaEventRecord(sc->ev_frame_start, sc->stream));
+    for (uint64_t first = 0; first < sc->owned_pixels; first += px_per_batch) {
+        uint32_t npx = (uint32_t)std::min<uint64_t>(px_per_batch, sc->owned_pixels - first);
+        CU(cudaMemsetAsync(sc->d_counts, 0, RT_MAX_LEVELS * sizeof(uint32_t), sc->stream));
+        k_raygen<<<sc->grid, 256, 0, sc->stream>>>(rcd, sc->map, first, npx, spp, k0, k1, sc->q[0], sc->d_counts, sc->d_radiance);
+        sc->launches++;
+        launch_bounces(sc, p->max_depth, first, spp, p->seed);
+        k_resolve<<<(npx + 255) / 256, 256, 0, sc->stream>>>(sc->d_radiance, npx, spp, first, sc->d_accum, sc->d_frame);
+        sc->launches++;
+        Batch b;
+        b.first_owned = first;
+        b.n_pixels = npx;
+        CU(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+        CU(cudaEventRecord(b.done, sc->stream));
+        sc->batches.push_back(b);
+        sc->paths += (uint64_t)npx * spp;
+    }
+    CU(cudaEventRecord(sc->ev_frame_stop, sc->stream));
+    CU(cudaGetLastError());
+    sc->rendering = true;
+    sc->frame_complete = false;
+    return RT_OK;
+}
+
+// copy the owned-order range [q0, q1) of the f64 frame to the caller's x + y*w buffer
+static int deliver(rt_scene* sc, uint64_t q0, uint64_t q1, rt_vec3* buffer) {
+    if (q1 <= q0) return RT_OK;
+    if (sc->map.shard_count == 1) {  // owned order is row-major: one contiguous copy
+        CU(cudaMemcpyAsync(buffer + q0, sc->d_frame + q0, (q1 - q0) * sizeof(rt_vec3), cudaMemcpyDeviceToHost, sc->copy_stream));
+        CU(cudaStreamSynchronize(sc->copy_stream));
+        return RT_OK;
+    }
+    sc->host_stage.resize(q1 - q0);
+    CU(cudaMemcpyAsync(sc->host_stage.data(), sc->d_frame + q0, (q1 - q0) * sizeof(rt_vec3), cudaMemcpyDeviceToHost, sc->copy_stream));
+    CU(cudaStreamSynchronize(sc->copy_stream));
+    for (uint64_t q = q0; q < q1; q++) {
+        uint32_t x, y;
+        if (sc->map.pixel_of(q, x, y)) buffer[(size_t)y * sc->map.width + x] = sc->host_stage[q - q0];
+    }
+    return RT_OK;
+}
+
+int rt_render_poll(rt_scene* sc, rt_vec3* buffer, int* done) {
+    if (!sc || !done) return fail(RT_ERR_INVALID, "null argument");
+    if (!sc->rendering) return fail(RT_ERR_STATE, "rt_render_poll without rt_render_start");
+    CU(cudaSetDevice(sc->device));
+    size_t ready = sc->delivered;
+    while (ready < sc->batches.size()) {
+        cudaError_t e = cudaEventQuery(sc->batches[ready].done);
+        if (e == cudaSuccess) ready++;
+        else if (e == cudaErrorNotReady) break;
+        else return fail(RT_ERR_CUDA, std::string("render: ") + cudaGetErrorString(e));
+    }
+    if (ready > sc->delivered && buffer) {
+        uint64_t q0 = sc->batches[sc->delivered].first_owned;
+        uint64_t q1 = sc->batches[ready - 1].first_owned + sc->batches[ready - 1].n_pixels;
+        int rc = deliver(sc, q0, q1, buffer);
+        if (rc != RT_OK) return rc;
+    }
+    sc->delivered = ready;
+    if (ready == sc->batches.size()) {
+        cudaError_t e = cudaEventQuery(sc->ev_frame_stop);
+        if (e == cudaErrorNotReady) {
+            *done = 0;
+            return RT_OK;
+        }
+        if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("render: ") + cudaGetErrorString(e));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, sc->ev_frame_start, sc->ev_frame_stop);
+        sc->last_frame_ms = ms;
+        sc->rendering = false;
+        sc->frame_complete = true;
+        *done = 1;
+        return RT_OK;
+    }
+    *done = 0;
+    return RT_OK;
+}
+
+int rt_render_wait(rt_scene* sc, rt_vec3* buffer) {
+    if (!sc) return fail(RT_ERR_INVALID, "null scene");
+    if (!sc->rendering) return fail(RT_ERR_STATE, "rt_render_wait without rt_render_start");
+    CU(cudaSetDevice(sc->device));
+    CU(cudaStreamSynchronize(sc->stream));
+    int done = 0;
+    int rc = rt_render_poll(sc, buffer, &done);
+    if (rc != RT_OK) return rc;
+    if (!done) return fail(RT_ERR_STATE, "frame did not complete");
+    return RT_OK;
+}
+
+int rt_render_stop(rt_scene* sc) {
+    if (!sc) return fail(RT_ERR_INVALID, "null scene");
+    if (!sc->rendering) return RT_OK;
+    cudaSetDevice(sc->device);
+    // work already enqueued cannot be recalled; drain it so the buffers can be reused
+    cudaStreamSynchronize(sc->stream);
+    sc->rendering = false;
+    sc->frame_complete = false;
+    return RT_OK;
+}
+
+int rt_render_device_result(rt_scene* sc, const void** d_accum, uint64_t* n_float4) {
+    if (!sc || !d_accum || !n_float4) return fail(RT_ERR_INVALID, "null argument");
+    if (sc->rendering) {
+        CU(cudaSetDevice(sc->device));
+        CU(cudaStreamSynchronize(sc->stream));
+        int done = 0;
+        int rc = rt_render_poll(sc, nullptr, &done);
+        if (rc != RT_OK) return rc;
+    }
+    if (!sc->frame_complete) return fail(RT_ERR_STATE, "no completed frame");
+    *d_accum = sc->d_accum;
+    *n_float4 = sc->owned_pixels;
+    return RT_OK;
+}
+
+uint64_t rt_shard_float4_count(const rt_render_params* p, uint32_t shard_index) {
+    if (!p || p->image.width == 0 || p->image.height == 0) return 0;
+    ShardMap m = make_shard_map(*p, shard_index);
+    return owned_tiles(m) * m.tile_pixels();
+}
+
+int rt_assemble_frame(rt_scene* sc, const rt_render_params* p, const void* const* d_shards, rt_vec3* d_frame, void* stream) {
+    if (!sc || !p || !d_shards || !d_frame) return fail(RT_ERR_INVALID, "null argument");
+    uint32_t shard_count = p->shard_count ? p->shard_count : 1;
+    if (shard_count > 16) return fail(RT_ERR_INVALID, "at most 16 shards");
+    CU(cudaSetDevice(sc->device));
+    rt_render_params pp = *p;
+    pp.shard_count = shard_count;
+    ShardMap m = make_shard_map(pp, 0);
+    ShardPtrs sp;
+    for (uint32_t s = 0; s < 16; s++) sp.p[s] = s < shard_count ? (const float4*)d_shards[s] : nullptr;
+    cudaStream_t st = stream ? (cudaStream_t)stream : sc->stream;
+    dim3 grid((m.width + 255) / 256, m.height);
+    k_assemble<<<grid, 256, 0, st>>>(sp, m, d_frame);
+    sc->launches++;
+    CU(cudaGetLastError());
+    return RT_OK;
+}
+
+int rt_tonemap_rgba8(rt_scene* sc, const rt_vec3* frame, uint64_t n, uint8_t* rgba) {
+    if (!sc || !frame || !rgba) return fail(RT_ERR_INVALID, "null argument");
+    if (n == 0) return RT_OK;
+    CU(cudaSetDevice(sc->device));
+    rt_vec3* d_in = nullptr;
+    uchar4* d_out = nullptr;
+    CU(cudaMalloc(&d_in, n * sizeof(rt_vec3)));
+    cudaError_t e = cudaMalloc(&d_out, n * sizeof(uchar4));
+    if (e != cudaSuccess) { cudaFree(d_in); return fail(RT_ERR_NOMEM, "cudaMalloc failed"); }
+    cudaMemcpyAsync(d_in, frame, n * sizeof(rt_vec3), cudaMemcpyHostToDevice, sc->stream);
+    k_tonemap<<<(unsigned)((n + 255) / 256), 256, 0, sc->stream>>>(d_in, n, d_out);
+    sc->launches++;
+    cudaMemcpyAsync(rgba, d_out, n * sizeof(uchar4), cudaMemcpyDeviceToHost, sc->stream);
+    e = cudaStreamSynchronize(sc->stream);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("tonemap: ") + cudaGetErrorString(e));
+    return RT_OK;
+}
+
+int rt_trace_pixel_samples(rt_scene* sc, const rt_ray* rays, uint32_t n_rays, uint32_t max_depth, uint64_t seed,
+                           uint32_t pixel_index, rt_vec3* mean_out) {
+    if (!sc || !rays || !mean_out) return fail(RT_ERR_INVALID, "null argument");
+    if (n_rays == 0) return fail(RT_ERR_INVALID, "no rays");
+    if (max_depth + 2 > RT_MAX_LEVELS) return fail(RT_ERR_INVALID, "max_depth too large (limit 62)");
+    if (sc->rendering) return fail(RT_ERR_STATE, "a frame is in flight");
+    CU(cudaSetDevice(sc->device));
+    int rc = ensure_path_buffers(sc, std::max<uint64_t>(n_rays, 1024));
+    if (rc != RT_OK) return rc;
+    rt_ray* d_rays = nullptr;
+    float4* d_acc = nullptr;
+    rt_vec3* d_mean = nullptr;
+    CU(cudaMalloc(&d_rays, n_rays * sizeof(rt_ray)));
+    cudaMalloc(&d_acc, sizeof(float4));
+    cudaMalloc(&d_mean, sizeof(rt_vec3));
+    cudaMemcpyAsync(d_rays, rays, n_rays * sizeof(rt_ray), cudaMemcpyHostToDevice, sc->stream);
+    cudaMemsetAsync(sc->d_counts, 0, RT_MAX_LEVELS * sizeof(uint32_t), sc->stream);
+    k_load_rays<<<(n_rays + 255) / 256, 256, 0, sc->stream>>>(d_rays, n_rays, sc->q[0], sc->d_counts);
+    sc->launches++;
+    // a 1-pixel-wide "image" whose only pixel is pixel_index: owned pixel 0 -> (x = pixel_index, y = 0)
+    ShardMap saved = sc->map;
+    ShardMap m;
+    m.width = 0xFFFFFFFFu; m.height = 1; m.tile_w = 0xFFFFFFFFu; m.tile_h = 1; m.tiles_x = 1; m.tiles_y = 1;
+    m.shard_count = 1; m.shard_index = 0;
+    sc->map = m;
+    // pixel_of(first_owned + 0) must give x = pixel_index: use first_owned = pixel_index
+    launch_bounces(sc, max_depth, pixel_index, n_rays, seed);
+    sc->map = saved;
+    k_resolve<<<1, 256, 0, sc->stream>>>(sc->d_radiance, 1, n_rays, 0, d_acc, d_mean);
+    sc->launches++;
+    cudaMemcpyAsync(mean_out, d_mean, sizeof(rt_vec3), cudaMemcpyDeviceToHost, sc->stream);
+    cudaError_t e = cudaStreamSynchronize(sc->stream);
+    cudaFree(d_rays); cudaFree(d_acc); cudaFree(d_mean);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("trace_pixel_samples: ") + cudaGetErrorString(e));
+    sc->paths += n_rays;
+    return RT_OK;
+}
+
+// ---- instrumentation ---------------------------------------------------------------------------
+int rt_get_stats(rt_scene* sc, rt_stats* out) {
+    if (!sc || !out) return fail(RT_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(sc->device));
+    DevCounters c;
+    CU(cudaMemcpy(&c, sc->d_counters, sizeof c, cudaMemcpyDeviceToHost));
+    out->kernel_launches = sc->launches;
+    out->paths = sc->paths;
+    out->segments = c.segments;
+    out->shape_tests = c.shape_tests;
+    out->cull_tests = c.cull_tests;
+    out->march_steps = c.march_steps;
+    out->march_rays = c.march_rays;
+    out->last_frame_ms = sc->last_frame_ms;
+    out->last_intersect_ms = sc->last_intersect_ms;
+    return RT_OK;
+}
+int rt_reset_stats(rt_scene* sc) {
+    if (!sc) return fail(RT_ERR_INVALID, "null scene");
+    CU(cudaSetDevice(sc->device));
+    CU(cudaMemset(sc->d_counters, 0, sizeof(DevCounters)));
+    sc->launches = 0;
+    sc->paths = 0;
+    return RT_OK;
+}
+int rt_set_counters(rt_scene* sc, int enabled) {
+    if (!sc) return fail(RT_ERR_INVALID, "null scene");
+    sc->counters_on = enabled != 0;
+    return RT_OK;
+}
+
+int rt_measure_peaks(int device, double* fp64_tflops, double* fp32_tflops) {
+    int ndev = rt_device_count();
+    if (ndev == 0) return fail(RT_ERR_NO_DEVICE, "no CUDA device");
+    if (device < 0 || device >= ndev) return fail(RT_ERR_INVALID, "device index out of range");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    void* buf = nullptr;
+    CU(cudaMalloc(&buf, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    auto run = [&](bool dbl, int iters) -> double {
+        float best = 1e30f;
+        for (int rep = 0; rep < 4; rep++) {
+            cudaEventRecord(a);
+            if (dbl) k_fma_peak<double><<<blocks, threads>>>((double*)buf, iters, 1.0000001, 1e-9);
+            else k_fma_peak<float><<<blocks, threads>>>((float*)buf, iters, 1.0000001f, 1e-9f);
+            cudaEventRecord(b);
+            cudaEventSynchronize(b);
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, a, b);
+            if (rep > 0 && ms < best) best = ms;
+        }
+        double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+        return flops / (best * 1e-3) / 1e12;
+    };
+    if (fp64_tflops) *fp64_tflops = run(true, 1 << 14);
+    if (fp32_tflops) *fp32_tflops = run(false, 1 << 15);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(buf);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("measure_peaks: ") + cudaGetErrorString(e));
+    return RT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,364 @@
+// Device-side FP64 arithmetic of the path-tracing core.
+//
+// The parity contract (bit-exact nearest-hit index, t and normal identical to the reference's f64
+// code) holds only if every expression is evaluated with the reference's operand order and WITHOUT
+// fused multiply-add: this translation unit must be compiled with -fmad=false.  Where an FMA is
+// wanted (conservative culling, never the exact tests) it is written explicitly as fma()/__fmaf_rn.
+// Citations are file:line into dkarpushkin/rs-pathtracing.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rt_b200.h"
+
+namespace rt {
+
+// algebra::Vector3d, src/algebra/mod.rs:23-28
+struct D3 {
+    double x, y, z;
+};
+__device__ __forceinline__ D3 mk(double x, double y, double z) { return D3{x, y, z}; }
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ D3 operator-(D3 a) { return {-a.x, -a.y, -a.z}; }
+__device__ __forceinline__ D3 operator*(D3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ D3 operator*(double s, D3 a) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ D3 operator/(D3 a, double s) { return {a.x / s, a.y / s, a.z / s}; }
+// `*` between vectors is the dot product: (x*x' + y*y') + z*z'   (mod.rs:319-349)
+__device__ __forceinline__ double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ D3 hadamard(D3 a, D3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }  // product, :135-141
+__device__ __forceinline__ D3 divide(D3 a, D3 b) { return {a.x / b.x, a.y / b.y, a.z / b.z}; }    // :143-150
+__device__ __forceinline__ double length(D3 a) { return sqrt(dot(a, a)); }                       // :117-120
+__device__ __forceinline__ D3 normalize(D3 a) { return a / length(a); }                          // :107-110
+__device__ __forceinline__ bool approx_zero(double a) { return fabs(a - 0.0) < 1e-15; }          // approx_equal(a, 0.0), :14-17
+// f64::min/max ignore a NaN operand; so do fmin/fmax (:168-198)
+__device__ __forceinline__ double max3(double a, double b, double c) { return fmax(fmax(a, b), c); }
+__device__ __forceinline__ double min3(double a, double b, double c) { return fmin(fmin(a, b), c); }
+
+__device__ __forceinline__ D3 reflect(D3 v, D3 n) {  // :122-125
+    D3 b = dot(v, n) * n;
+    return v - (2.0 * b);
+}
+__device__ __forceinline__ D3 refract(D3 v, D3 n, double ratio) {  // :127-133
+    double cos_theta = dot(-v, n);
+    D3 r_out_perp = ratio * (v + cos_theta * n);
+    D3 r_out_parallel = -(sqrt(fabs(1.0 - dot(r_out_perp, r_out_perp)))) * n;
+    return r_out_perp + r_out_parallel;
+}
+
+// Transform::transform_point / transform_vector / transform_normal on rows 0..2 of the 4x4
+// (src/algebra/transform.rs:394-425).  `m` is 12 doubles, row-major 3x4.
+__device__ __forceinline__ D3 xf_point(const double* m, D3 p) {
+    return {p.x * m[0] + p.y * m[1] + p.z * m[2] + m[3], p.x * m[4] + p.y * m[5] + p.z * m[6] + m[7],
+            p.x * m[8] + p.y * m[9] + p.z * m[10] + m[11]};
+}
+__device__ __forceinline__ D3 xf_vector(const double* m, D3 v) {
+    return {v.x * m[0] + v.y * m[1] + v.z * m[2], v.x * m[4] + v.y * m[5] + v.z * m[6],
+            v.x * m[8] + v.y * m[9] + v.z * m[10]};
+}
+__device__ __forceinline__ D3 xf_normal(const double* m, D3 n) {  // transpose of the 3x3
+    return {n.x * m[0] + n.y * m[4] + n.z * m[8], n.x * m[1] + n.y * m[5] + n.z * m[9],
+            n.x * m[2] + n.y * m[6] + n.z * m[10]};
+}
+
+// ------------------------------------------------------------------------------------------------
+// implicit surfaces — src/world/shapes/ray_marching.rs:134-520.  KIND is a compile-time constant so
+// that the marching loop contains exactly one polynomial; q = params[8] of the shape.
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ double surface_func(const double* q, D3 p) {
+    if (KIND == RT_SURF_HEART) {  // :147-155
+        double x2 = p.x * p.x;
+        double y2 = p.y * p.y;
+        double z2 = p.z * p.z;
+        double z3 = z2 * p.z;
+        double a = x2 + (9.0 / 4.0) * y2 + z2 - 1.0;
+        return a * a * a - x2 * z3 - (9.0 / 80.0) * y2 * z3;
+    } else if (KIND == RT_SURF_SINE) {  // :203-211
+        double a_ = q[3];
+        return a_ * a_ * (p.x - p.y - p.z) * (p.x + p.y - p.z) * (p.x - p.y + p.z) * (p.x + p.y + p.z) +
+               4.0 * p.x * p.x * p.y * p.y * p.z * p.z;
+    } else if (KIND == RT_SURF_STAR) {  // :268-274
+        double a_ = q[3];
+        double x2 = p.x * p.x;
+        double y2 = p.y * p.y;
+        double z2 = p.z * p.z;
+        double c = x2 + y2 + z2 - 1.0;
+        return a_ * (x2 * y2 + x2 * z2 + y2 * z2) + (c * c * c);
+    } else if (KIND == RT_SURF_DUPIN) {  // :340-345
+        double a_ = q[3], b_ = q[4], c_ = q[5], d_ = q[6];
+        double b2 = b_ * b_;
+        double e = p.x * p.x + p.y * p.y + p.z * p.z + b2 - d_ * d_;
+        double f = a_ * p.x - c_ * d_;
+        return e * e - 4.0 * (f * f + b2 * p.y * p.y);
+    } else if (KIND == RT_SURF_HUNTS) {  // :399-406
+        double x2 = p.x * p.x;
+        double y2 = p.y * p.y;
+        double z2 = p.z * p.z;
+        double a = x2 + y2 + z2 - 13.0;
+        double b = 3.0 * x2 + y2 - 4.0 * z2 - 12.0;
+        return 4.0 * a * a * a + 27.0 * b * b;
+    } else {  // RT_SURF_CUSHION, :464-478
+        double x2 = p.x * p.x;
+        double y2 = p.y * p.y;
+        double z2 = p.z * p.z;
+        double a = x2 - p.z;
+        return z2 * x2 - z2 * z2 - 2.0 * p.z * x2 + 2.0 * p.z * z2 + x2 - z2 - a * a - y2 * y2 - 2.0 * x2 * y2 -
+               y2 * z2 + 2.0 * y2 * p.z + y2;
+    }
+}
+
+__device__ inline D3 surface_gradient(const double* q, D3 p) {
+    switch ((int)q[0]) {
+        case RT_SURF_HEART: {  // :157-168
+            double a = p.x * p.x + (9.0 / 4.0) * p.y * p.y + p.z * p.z - 1.0;
+            a = 3.0 * a * a;
+            double z2 = p.z * p.z;
+            double z3 = z2 * p.z;
+            return mk(2.0 * p.x * (a - z3), (9.0 / 2.0) * p.y * (a - 0.05 * z3),
+                      2.0 * p.z * (a - p.z * (1.5 * p.x * p.x + (27.0 / 40.0) * p.y * p.y)));
+        }
+        case RT_SURF_SINE: {  // :227-237
+            double a_ = q[3];
+            double x2 = p.x * p.x;
+            double y2 = p.y * p.y;
+            double z2 = p.z * p.z;
+            double a2 = a_ * a_;
+            return mk(4.0 * p.x * (a2 * (x2 - y2 - z2) + 2.0 * y2 * z2),
+                      8.0 * x2 * p.y * z2 - 4.0 * a2 * p.y * (x2 - y2 + z2),
+                      8.0 * x2 * y2 * p.z - 4.0 * a2 * p.z * (x2 + y2 - z2));
+        }
+        case RT_SURF_STAR: {  // :290-300
+            double a_ = q[3];
+            double x2 = p.x * p.x;
+            double y2 = p.y * p.y;
+            double z2 = p.z * p.z;
+            double c = x2 + y2 + z2 - 1.0;
+            return mk(2.0 * a_ * p.x * (y2 + z2) + 6.0 * p.x * c * c, 2.0 * a_ * p.y * (x2 + z2) + 6.0 * p.y * c * c,
+                      2.0 * a_ * p.z * (x2 + y2) + 6.0 * p.z * c * c);
+        }
+        case RT_SURF_DUPIN: {  // :361-369
+            double a_ = q[3], b_ = q[4], c_ = q[5], d_ = q[6];
+            double b2 = b_ * b_;
+            double e = 4.0 * (p.x * p.x + p.y * p.y + p.z * p.z + b2 - d_ * d_);
+            return mk(e * p.x - 8.0 * a_ * (a_ * p.x - c_ * d_), e * p.y - 8.0 * b2 * p.y, e * p.z);
+        }
+        case RT_SURF_HUNTS: {  // :422-434
+            double x2 = p.x * p.x;
+            double y2 = p.y * p.y;
+            double z2 = p.z * p.z;
+            double a = x2 + y2 + z2 - 13.0;
+            double b = 3.0 * x2 + y2 - 4.0 * (z2 + 3.0);
+            return mk(24.0 * p.x * a * a + 324.0 * p.x * b, 12.0 * p.y * (2.0 * a * a + 9.0 * b),
+                      24.0 * p.z * (a * a - 18.0 * b));
+        }
+        default: {  // RT_SURF_CUSHION, :494-504
+            double x2 = p.x * p.x;
+            double y2 = p.y * p.y;
+            double z2 = p.z * p.z;
+            return mk(2.0 * p.x * (-2.0 * x2 - 2.0 * y2 + z2 + 1.0),
+                      -2.0 * p.y * (2.0 * x2 + 2.0 * y2 + z2 - 2.0 * p.z - 1.0),
+                      2.0 * p.z * (x2 - 2.0 * z2 + 3.0 * p.z - 2.0) - 2.0 * p.y * (p.z - 1.0));
+        }
+    }
+}
+
+// solve_quadratic_equation, src/algebra/equation.rs:5-15
+__device__ __forceinline__ bool solve_quadratic(double a, double half_b, double c, double& x1, double& x2) {
+    double d = half_b * half_b - a * c;
+    if (d < 0.0) return false;
+    if (d == 0.0) {
+        x1 = -half_b;
+        x2 = -half_b;
+        return true;
+    }
+    double d_sqrt = sqrt(d);  // NaN d falls through to here, exactly like the reference
+    x1 = (-half_b - d_sqrt) / a;
+    x2 = (-half_b + d_sqrt) / a;
+    return true;
+}
+
+// ShapeFunction::intersect_bound — ray_marching.rs:135-145 (Heart: ellipsoid), :213-225 (sphere)
+__device__ __forceinline__ bool march_bound(const double* q, D3 o, D3 d, double& start, double& end) {
+    double x1, x2;
+    if ((int)q[0] == RT_SURF_HEART) {
+        const double sr = 1.45;  // Heart::new, :126-131
+        D3 radius = mk(sr, sr / 2.05, sr);
+        D3 os = divide(o, radius);
+        D3 ds = divide(d, radius);
+        if (!solve_quadratic(dot(ds, ds), dot(ds, os), dot(os, os) - 1.0, x1, x2)) return false;
+    } else {
+        double R = q[7];
+        if (!solve_quadratic(dot(d, d), dot(d, o), dot(o, o) - R * R, x1, x2)) return false;
+    }
+    if (x1 < 0.0 && x2 < 0.0) return false;
+    start = fmax(x1, 0.0);
+    end = fmax(x2, 0.0);
+    return true;
+}
+
+// RayMarchingShape::ray_intersect's loops, ray_marching.rs:27-57.  Returns the candidate t or
+// false; `evals` counts shape_func evaluations (statistics only).
+template <int KIND>
+__device__ __forceinline__ bool march_loop(const double* q, D3 o, D3 d, double start, double end, double min_t,
+                                           double max_t, double& t_out, unsigned long long& evals) {
+    double step = q[1];
+    int depth = (int)q[2];
+    double t = start;
+    D3 p = o + t * d;
+    double r = surface_func<KIND>(q, p);
+    unsigned long long n = 0;
+    for (int it = 0; it < depth; it++) {
+        bool finished = false;
+        D3 sd = step * d;  // `step * dir` is loop-invariant until the step changes
+        for (;;) {
+            if (t > end || t < start) {
+                evals += n;
+                return false;
+            }
+            t += step;
+            p.x += sd.x;
+            p.y += sd.y;
+            p.z += sd.z;
+            double next = surface_func<KIND>(q, p);
+            n++;
+            if (approx_zero(next)) {
+                finished = true;
+                break;
+            }
+            if ((r < 0.0 && next > 0.0) || (r > 0.0 && next < 0.0)) {
+                step *= -0.01;
+                r = next;
+                break;
+            }
+            r = next;
+        }
+        if (finished) break;
+    }
+    evals += n;
+    if (t < min_t || t > max_t) return false;
+    t_out = t;
+    return true;
+}
+
+__device__ inline bool march_candidate(const double* q, D3 o, D3 d, double min_t, double max_t, double& t,
+                                       unsigned long long& evals) {
+    double start, end;
+    if (!march_bound(q, o, d, start, end)) return false;
+    switch ((int)q[0]) {
+        case RT_SURF_HEART: return march_loop<RT_SURF_HEART>(q, o, d, start, end, min_t, max_t, t, evals);
+        case RT_SURF_SINE: return march_loop<RT_SURF_SINE>(q, o, d, start, end, min_t, max_t, t, evals);
+        case RT_SURF_STAR: return march_loop<RT_SURF_STAR>(q, o, d, start, end, min_t, max_t, t, evals);
+        case RT_SURF_DUPIN: return march_loop<RT_SURF_DUPIN>(q, o, d, start, end, min_t, max_t, t, evals);
+        case RT_SURF_HUNTS: return march_loop<RT_SURF_HUNTS>(q, o, d, start, end, min_t, max_t, t, evals);
+        default: return march_loop<RT_SURF_CUSHION>(q, o, d, start, end, min_t, max_t, t, evals);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// analytic shapes, object space.  Each returns the candidate t (the rest of the RayHit is a pure
+// function of (shape, t, ray) and is rebuilt for the winner only by finalize_hit()).
+// ------------------------------------------------------------------------------------------------
+
+// Sphere::ray_intersect, src/world/shapes/mod.rs:330-356
+__device__ __forceinline__ bool sphere_candidate(D3 o, D3 d, double min_t, double max_t, double& t) {
+    double a = dot(d, d);
+    double half_b = dot(d, o);
+    double c = dot(o, o) - 1.0;
+    double disc = half_b * half_b - a * c;
+    if (disc < 0.0) return false;
+    if (disc == 0.0) {
+        t = -half_b * a;  // sic (:343-344): multiplied, and accepted with no range check
+        return true;
+    }
+    double sq = sqrt(disc);
+    double x = (-half_b - sq) / a;
+    if (x < min_t || x > max_t) {
+        x = (-half_b + sq) / a;
+        if (x < min_t || x > max_t) return false;
+    }
+    t = x;
+    return true;
+}
+
+// Cube::ray_intersect, :250-263
+__device__ __forceinline__ bool cube_candidate(D3 o, D3 d, double min_t, double max_t, double& t) {
+    D3 t_lower = divide(mk(-1.0, -1.0, -1.0) - o, d);
+    D3 t_upper = divide(mk(1.0, 1.0, 1.0) - o, d);
+    double t_box_min = fmax(max3(fmin(t_lower.x, t_upper.x), fmin(t_lower.y, t_upper.y), fmin(t_lower.z, t_upper.z)), min_t);
+    double t_box_max = fmin(min3(fmax(t_lower.x, t_upper.x), fmax(t_lower.y, t_upper.y), fmax(t_lower.z, t_upper.z)), max_t);
+    if (t_box_min > t_box_max || t_box_min > max_t) return false;
+    // the reference panics when the hit point's largest |component| is NaN (:279-281); that can only
+    // happen for a NaN ray, which the core reports as a miss
+    D3 p = o + t_box_min * d;
+    double m = max3(fabs(p.x), fabs(p.y), fabs(p.z));
+    if (!(m == fabs(p.x) || m == fabs(p.y) || m == fabs(p.z))) return false;
+    t = t_box_min;
+    return true;
+}
+
+// Rectangle::ray_intersect, :181-190
+__device__ __forceinline__ bool rect_candidate(const double* q, D3 o, D3 d, double min_t, double max_t, double& t) {
+    double x = -o.z / d.z;
+    if (x < min_t || x > max_t) return false;
+    D3 p = o + d * x;
+    if (p.x < q[0] || p.x > q[2] || p.y < q[1] || p.y > q[3]) return false;
+    t = x;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG (Salmon et al., SC'11).  One stream of doubles per
+// (seed; pixel, sample, event): event 0 = pixel jitter, event k+1 = scatter at the k-th hit.
+// Double i of a stream is half (i & 1) of block (i >> 1); 53 bits each.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct PathRng {
+    uint32_t k0, k1, pixel, sample, event, next_index;
+    double cache1;
+    __device__ __forceinline__ void begin_event(uint32_t ev) {
+        event = ev;
+        next_index = 0;
+    }
+    __device__ __forceinline__ double next() {
+        uint32_t i = next_index++;
+        if (i & 1u) return cache1;
+        uint32_t o[4];
+        philox4x32_10(pixel, sample, event, i >> 1, k0, k1, o);
+        unsigned long long a = ((unsigned long long)o[1] << 32) | o[0];
+        unsigned long long b = ((unsigned long long)o[3] << 32) | o[2];
+        cache1 = (double)(b >> 11) * (1.0 / 9007199254740992.0);
+        return (double)(a >> 11) * (1.0 / 9007199254740992.0);
+    }
+};
+
+// Vector3d::random(min, max), src/algebra/mod.rs:59-66 (x, y, z drawn in that order)
+__device__ __forceinline__ D3 random_range(PathRng& r, double mn, double mx) {
+    double x = mn + (mx - mn) * r.next();
+    double y = mn + (mx - mn) * r.next();
+    double z = mn + (mx - mn) * r.next();
+    return mk(x, y, z);
+}
+// random_in_unit_sphere, :77-84 (rejection, accepts |v|^2 <= 1)
+__device__ __forceinline__ D3 random_in_unit_sphere(PathRng& r) {
+    for (;;) {
+        D3 v = random_range(r, -1.0, 1.0);
+        if (dot(v, v) <= 1.0) return v;
+    }
+}
+__device__ __forceinline__ D3 random_unit(PathRng& r) { return normalize(random_in_unit_sphere(r)); }  // :86-88
+
+}  // namespace rt

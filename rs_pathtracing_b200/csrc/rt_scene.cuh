@@ -1,0 +1,232 @@
+// Device-resident scene (structure of arrays), winner finalisation, textures, materials and the
+// one-step integrator shared by every kernel of the core.  FP64, no FMA contraction (see rt_math.cuh).
+#pragma once
+#include "rt_math.cuh"
+
+namespace rt {
+
+struct DevImage {
+    uint32_t width, height;
+    const uint8_t* rgba;
+};
+
+// Flat scene in HBM.  inv/dir: [n][12] rows 0..2 of InversableTransform.inverse/.direct;
+// params: [n][8]; everything is read-only for the lifetime of the rt_scene.
+struct DevScene {
+    int n_shapes;
+    const double* inv;
+    const double* dir;
+    const double* params;
+    const uint8_t* kind;
+    const uint8_t* flags;
+    const uint32_t* material;
+    const rt_material* materials;
+    const rt_texture* textures;
+    const DevImage* images;
+    // indices of the RT_SHAPE_MARCH shapes (they are few; kernels that split marching out of the
+    // analytic loop walk this list)
+    int n_march;
+    const int* march_index;
+};
+
+// optional work counters (rt_stats); enabled per launch by a template flag
+struct DevCounters {
+    unsigned long long segments, shape_tests, cull_tests, march_steps, march_rays;
+};
+
+struct HitRec {  // RayHit, src/world/ray.rs:21-29
+    D3 point, normal;
+    double t, u, v;
+    bool front;
+    int shape;
+};
+
+// Rebuild the winner's RayHit from (shape, t, ray): Shape::ray_hit_transformed
+// (src/world/shapes/mod.rs:112-124) around the tail of each ray_intersect and RayHit::new /
+// set_normal (src/world/ray.rs:32-64).
+__device__ inline void finalize_hit(const DevScene& S, int i, double t, D3 ro, D3 rd, HitRec& h) {
+    const double* inv = S.inv + 12 * i;
+    const double* q = S.params + RT_SHAPE_PARAMS * i;
+    const double PI = 3.14159265358979323846264338327950288;
+    D3 o = xf_point(inv, ro);   // inverse_transform_ray, src/algebra/transform.rs:32-37
+    D3 d = xf_vector(inv, rd);
+    D3 p = o + d * t;
+    D3 n;
+    double u = 0.0, v = 0.0;
+    switch (S.kind[i]) {
+        case RT_SHAPE_SPHERE: {  // shapes/mod.rs:358-373
+            n = (S.flags[i] & RT_SHAPE_FLAG_INVERSE_NORMAL) ? -p : p;
+            double theta = acos(-p.y);
+            double phi = atan2(-p.z, p.x) + PI;
+            u = phi / (2.0 * PI);
+            v = theta / PI;
+            break;
+        }
+        case RT_SHAPE_CUBE: {  // :263-283
+            double ax = fabs(p.x), ay = fabs(p.y), az = fabs(p.z);
+            double max_c = max3(ax, ay, az);
+            if (max_c == ax) { n = mk(p.x, 0.0, 0.0); u = p.y; v = p.z; }
+            else if (max_c == ay) { n = mk(0.0, p.y, 0.0); u = p.x; v = p.z; }
+            else { n = mk(0.0, 0.0, p.z); u = p.x; v = p.y; }
+            break;
+        }
+        case RT_SHAPE_RECTANGLE: {  // :191-201
+            n = mk(0.0, 0.0, 1.0);
+            u = (p.x - q[0]) / (q[2] - q[0]);
+            v = (p.y - q[1]) / (q[3] - q[1]);
+            break;
+        }
+        default: {  // RT_SHAPE_MARCH, ray_marching.rs:59-61
+            n = surface_gradient(q, p);
+            int sk = (int)q[0];
+            if (sk == RT_SURF_DUPIN || sk == RT_SURF_HUNTS || sk == RT_SURF_CUSHION) { u = p.x; v = p.y; }
+            break;
+        }
+    }
+    D3 n_obj = normalize(n);                           // RayHit::new, ray.rs:42-45
+    h.point = xf_point(S.dir + 12 * i, p);             // shapes/mod.rs:117
+    D3 n_w = xf_normal(inv, n_obj);                    // shapes/mod.rs:118
+    bool front = dot(n_w, rd) < 0.0;                   // set_normal, ray.rs:60-64
+    h.normal = normalize(front ? n_w : -n_w);
+    h.front = front;
+    h.t = t;
+    h.u = u;
+    h.v = v;
+    h.shape = i;
+}
+
+// One candidate test: Shape::ray_hit for shape i with the current max_t (shapes/mod.rs:126-137).
+// `m` points at the shape's inverse rows (shared or global memory).
+template <bool COUNT>
+__device__ __forceinline__ bool shape_candidate(const DevScene& S, int i, int kind, const double* m, D3 ro, D3 rd,
+                                                double min_t, double max_t, double& t, DevCounters& c) {
+    D3 o = xf_point(m, ro);
+    D3 d = xf_vector(m, rd);
+    if (COUNT) c.shape_tests++;
+    if (kind == RT_SHAPE_SPHERE) return sphere_candidate(o, d, min_t, max_t, t);
+    if (kind == RT_SHAPE_CUBE) return cube_candidate(o, d, min_t, max_t, t);
+    if (kind == RT_SHAPE_RECTANGLE) return rect_candidate(S.params + RT_SHAPE_PARAMS * i, o, d, min_t, max_t, t);
+    unsigned long long ev = 0;
+    bool ok = march_candidate(S.params + RT_SHAPE_PARAMS * i, o, d, min_t, max_t, t, ev);
+    if (COUNT) {
+        c.march_steps += ev;
+        c.march_rays += 1;  // counts bound hits + misses alike; refined by the split kernels
+    }
+    return ok;
+}
+
+// ShapeCollection::ray_intersect (src/world/shapes/mod.rs:573-597): index order, shrinking max_t.
+// s_inv / s_kind: the shape list staged in shared memory (or the global arrays when it does not fit).
+template <bool COUNT>
+__device__ __forceinline__ void nearest_hit_brute(const DevScene& S, const double* s_inv, const uint8_t* s_kind,
+                                                  D3 ro, D3 rd, double min_t, double max_t, double& best_t,
+                                                  int& best_i, DevCounters& c) {
+    double min_distance = max_t;
+    int winner = -1;
+    const int n = S.n_shapes;
+    for (int i = 0; i < n; i++) {
+        double t;
+        if (shape_candidate<COUNT>(S, i, s_kind[i], s_inv + 12 * i, ro, rd, min_t, min_distance, t, c)) {
+            min_distance = t;
+            winner = i;
+        }
+    }
+    if (COUNT) c.segments++;
+    best_t = min_distance;
+    best_i = winner;
+}
+
+// ------------------------------------------------------------------------------------------------
+// textures — src/world/texture.rs:17-116
+// ------------------------------------------------------------------------------------------------
+__device__ inline D3 texture_value(const DevScene& S, uint32_t tex, double u, double v, D3 p) {
+    const double PI = 3.14159265358979323846264338327950288;
+    for (int depth = 0; depth <= RT_TEX_MAX_DEPTH; depth++) {
+        const rt_texture& t = S.textures[tex];
+        if (t.kind == RT_TEX_SOLID) return mk(t.color.x, t.color.y, t.color.z);
+        if (t.kind == RT_TEX_CHECKER) {  // :40-51
+            double sines = sin(t.color.x * p.x) * sin(t.color.y * p.y) * sin(t.color.z * p.z);
+            tex = sines < 0.0 ? t.odd : t.even;
+        } else if (t.kind == RT_TEX_UV_CHECKER) {  // :78-88 (v pairs with multipliers.0)
+            double sines = sin(v * t.color.x * PI) * sin(u * t.color.y * PI);
+            tex = sines < 0.0 ? t.odd : t.even;
+        } else if (t.kind == RT_TEX_IMAGE) {  // :98-117
+            const DevImage& im = S.images[t.image];
+            double uu = isnan(u) ? u : fmin(fmax(u, 0.0), 1.0);
+            double vc = isnan(v) ? v : fmin(fmax(v, 0.0), 1.0);
+            double vv = 1.0 - vc;
+            double fx = uu * (double)im.width, fy = vv * (double)im.height;
+            // `as u32`: saturating, NaN -> 0.  get_pixel panics at x == width; clamp instead
+            uint32_t x = isnan(fx) ? 0u : (fx <= 0.0 ? 0u : (fx >= 4294967295.0 ? 4294967295u : (uint32_t)fx));
+            uint32_t y = isnan(fy) ? 0u : (fy <= 0.0 ? 0u : (fy >= 4294967295.0 ? 4294967295u : (uint32_t)fy));
+            if (x >= im.width) x = im.width - 1;
+            if (y >= im.height) y = im.height - 1;
+            const uint8_t* px = im.rgba + ((size_t)y * im.width + x) * 4;
+            double color_scale = 1.0 / 255.0;
+            return mk((double)px[0] * color_scale, (double)px[1] * color_scale, (double)px[2] * color_scale);
+        } else {
+            return mk(0.0, 0.0, 0.0);
+        }
+    }
+    return mk(0.0, 0.0, 0.0);
+}
+
+// Dielectric::reflectance, src/world/material.rs:84-88; powi(5) = x * ((x*x)*(x*x))
+__device__ __forceinline__ double reflectance(double cosine, double ref_index) {
+    double r0 = (1.0 - ref_index) / (1.0 + ref_index);
+    r0 = r0 * r0;
+    double x = 1.0 - cosine;
+    double x2 = x * x;
+    double x5 = x * (x2 * x2);
+    return r0 + (1.0 - r0) * x5;
+}
+
+// Material::scatter (src/world/material.rs:42-115).  Returns false when the material does not
+// scatter (DiffuseLight, EmptyMaterial); then `atten` holds Material::emitted (:123-127).
+__device__ inline bool scatter_or_emit(const DevScene& S, const HitRec& h, D3 rd, PathRng& rng, D3& new_dir,
+                                       D3& atten) {
+    const rt_material m = S.materials[S.material[h.shape]];
+    switch (m.kind) {
+        case RT_MAT_LAMBERTIAN: {  // :42-53
+            D3 direction = h.normal + random_unit(rng);
+            if (approx_zero(direction.x) && approx_zero(direction.y) && approx_zero(direction.z)) direction = h.normal;
+            new_dir = normalize(direction);  // Ray::new, ray.rs:12-17
+            atten = texture_value(S, m.texture, h.u, h.v, h.point);
+            return true;
+        }
+        case RT_MAT_METAL: {  // :64-75
+            D3 reflected = reflect(rd, h.normal);
+            D3 direction = (m.scalar == 0.0) ? reflected : reflected + m.scalar * random_in_unit_sphere(rng);
+            new_dir = normalize(direction);
+            atten = texture_value(S, m.texture, h.u, h.v, h.point);
+            return true;
+        }
+        case RT_MAT_DIELECTRIC: {  // :93-115
+            double refract_ratio = h.front ? 1.0 / m.scalar : m.scalar;
+            double cos_theta = dot(-rd, h.normal);
+            double sin_theta = sqrt(1.0 - cos_theta * cos_theta);
+            D3 direction;
+            if (refract_ratio * sin_theta > 1.0 || reflectance(cos_theta, refract_ratio) > rng.next())
+                direction = reflect(rd, h.normal);
+            else
+                direction = refract(rd, h.normal, refract_ratio);
+            new_dir = normalize(direction);
+            atten = mk(1.0, 1.0, 1.0);
+            return true;
+        }
+        case RT_MAT_DIFFUSE_LIGHT:
+            atten = texture_value(S, m.texture, h.u, h.v, h.point);
+            return false;
+        default:
+            atten = mk(0.0, 0.0, 0.0);
+            return false;
+    }
+}
+
+// Scene::background, src/world/mod.rs:199-202
+__device__ __forceinline__ D3 sky(D3 rd) {
+    double t = 0.5 * (rd.y + 1.0);
+    return (1.0 - t) * mk(1.0, 1.0, 1.0) + t * mk(0.5, 0.7, 1.0);
+}
+
+}  // namespace rt

@@ -1,0 +1,198 @@
+"""Host-side logic on CPU: the C-ABI libraries load and export every declared symbol, the JSON loader
+mirrors the reference's schema and error behaviour, and the flattened transforms equal the oracle's
+restatement bit for bit."""
+import ctypes as C
+import json
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+
+import rs_pathtracing_b200 as rt
+from rs_pathtracing_b200 import _ffi
+from oracle import pyoracle as po
+
+from conftest import ROOT, scene_path
+
+
+def _declared(header):
+    text = open(os.path.join(ROOT, "include", header)).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return set(re.findall(r"\b(rth?_[a-z0-9_]+)\s*\(", text))
+
+
+def test_core_exports_every_declared_symbol():
+    lib = _ffi.core()
+    names = _declared("rt_b200.h")
+    assert names == set(_ffi.CORE_SYMBOLS), names ^ set(_ffi.CORE_SYMBOLS)
+    for n in names:
+        assert hasattr(lib, n)
+    assert lib.rt_abi_version() == 1
+
+
+def test_host_exports_every_declared_symbol():
+    lib = _ffi.host()
+    names = _declared("rt_b200_host.h") - {"rth_image_loader"}
+    assert names == set(_ffi.HOST_SYMBOLS), names ^ set(_ffi.HOST_SYMBOLS)
+    for n in names:
+        assert hasattr(lib, n)
+
+
+def test_pod_layouts():
+    assert C.sizeof(_ffi.Vec3) == 24 and C.sizeof(_ffi.Ray) == 48 and C.sizeof(_ffi.Camera) == 112
+    assert C.sizeof(_ffi.Material) == 16 and C.sizeof(_ffi.Texture) == 40 and C.sizeof(_ffi.RenderParams) == 40
+
+
+@pytest.mark.parametrize("name,json_shapes", [("spheres.json", 5), ("cornell_box.json", 9),
+                                               ("detached_materials.json", 5), ("dupin.json", 3),
+                                               ("cube_test.json", 3), ("empty.json", 0)])
+def test_scene_loads_and_adds_random_spheres(name, json_shapes):
+    bare = rt.Scene.from_file(scene_path(name), add_random_spheres=False)
+    assert bare.shape_count == json_shapes
+    full = rt.Scene.from_file(scene_path(name), random_spheres_seed=1)
+    extra = full.shape_count - json_shapes
+    assert 470 <= extra <= 484          # 22*22 grid minus those within 0.9 of (4, 0.2, 0); SURVEY §0.1
+    d = full.desc()
+    kinds = np.ctypeslib.as_array(d.kind, shape=(d.n_shapes,))
+    assert (kinds[json_shapes:] == _ffi.RT_SHAPE_SPHERE).all()
+    inv = np.ctypeslib.as_array(d.inverse, shape=(d.n_shapes, 12))
+    dirm = np.ctypeslib.as_array(d.direct, shape=(d.n_shapes, 12))
+    # radius 0.2, centre (a + 0.9u, 0.2, b + 0.9u) appended in grid order, a outer / b inner
+    assert np.allclose(dirm[json_shapes:, [0, 5, 10]], 0.2)
+    assert (inv[json_shapes:, [0, 5, 10]] == 5.0).all()
+    cx, cy, cz = dirm[json_shapes:, 3], dirm[json_shapes:, 7], dirm[json_shapes:, 11]
+    assert (cy == 0.2).all() and (cx >= -11).all() and (cx < 11).all() and (cz >= -11).all() and (cz < 11).all()
+    assert (np.sqrt((cx - 4) ** 2 + cz ** 2) > 0.9).all()
+    assert (np.diff(np.floor(cx)) >= 0).all()
+    # reproducible for a seed, different across seeds
+    again = rt.Scene.from_file(scene_path(name), random_spheres_seed=1).desc()
+    assert np.array_equal(np.ctypeslib.as_array(again.direct, shape=(d.n_shapes, 12)), dirm)
+    other = rt.Scene.from_file(scene_path(name), random_spheres_seed=2)
+    od = other.desc()
+    assert not np.array_equal(np.ctypeslib.as_array(od.direct, shape=(od.n_shapes, 12))[json_shapes:json_shapes + 5],
+                              dirm[json_shapes:json_shapes + 5])
+
+
+def test_random_sphere_material_mix():
+    """80 % Lambertian / 15 % Metal / 5 % Dielectric (json_models.rs:86-112)"""
+    counts = np.zeros(3)
+    for seed in range(1, 9):
+        sc = rt.Scene.from_file(scene_path("empty.json"), random_spheres_seed=seed)
+        d = sc.desc()
+        mats = [d.materials[d.material[i]] for i in range(d.n_shapes)]
+        for m in mats:
+            counts[m.kind] += 1
+            if m.kind == _ffi.RT_MAT_METAL:
+                assert 0.0 <= m.scalar < 0.5
+                c = d.textures[m.texture].color
+                assert all(0.0 <= v <= 0.5 for v in c.tuple())
+            elif m.kind == _ffi.RT_MAT_DIELECTRIC:
+                assert m.scalar == 1.5
+    frac = counts / counts.sum()
+    assert abs(frac[0] - 0.8) < 0.03 and abs(frac[1] - 0.15) < 0.03 and abs(frac[2] - 0.05) < 0.02
+
+
+def test_flat_transforms_equal_oracle_bitwise():
+    """InversableTransform::new in the host mirror vs the oracle's independent restatement"""
+    text = json.load(open(scene_path("cornell_box.json")))
+    sc = rt.Scene.from_file(scene_path("cornell_box.json"), add_random_spheres=False)
+    d = sc.desc()
+    inv = np.ctypeslib.as_array(d.inverse, shape=(d.n_shapes, 12))
+    dirm = np.ctypeslib.as_array(d.direct, shape=(d.n_shapes, 12))
+    for i, s in enumerate(text["shapes"]):
+        t = s["transform"]
+        od, oi = po.transform_new(t["translate"], t["rotate"], t["scale"])
+        assert np.array_equal(od[:3].reshape(12), dirm[i])
+        assert np.array_equal(oi[:3].reshape(12), inv[i])
+    rng = np.random.default_rng(0)
+    lib = _ffi.host()
+    for _ in range(50):
+        tr, ro, scl = rng.uniform(-100, 100, 3), rng.uniform(-180, 180, 3), rng.uniform(0.1, 50, 3)
+        hd, hi = np.empty(16), np.empty(16)
+        lib.rth_transform_new(_ffi.Vec3(*tr), _ffi.Vec3(*ro), _ffi.Vec3(*scl), hd.ctypes.data_as(C.POINTER(C.c_double)),
+                              hi.ctypes.data_as(C.POINTER(C.c_double)))
+        od, oi = po.transform_new(tr, ro, scl)
+        assert np.array_equal(hd.reshape(4, 4), od) and np.array_equal(hi.reshape(4, 4), oi)
+
+
+def test_camera_matches_oracle_and_reference_kat():
+    cam = rt.camera_new((0, 0, 0), (0, 0, -1), (0, 1, 0), 1.0, math.radians(90.0))
+    assert cam.right.tuple() == (1.0, 0.0, 0.0)   # src/camera/mod.rs:333
+    rng = np.random.default_rng(2)
+    for _ in range(20):
+        p, dvec, up = rng.normal(size=3), rng.normal(size=3), rng.normal(size=3)
+        a = rt.camera_new(p, dvec, up, 1.3, 0.7)
+        b = po.camera_new(p, dvec, up, 1.3, 0.7)
+        assert bytes(a) == bytes(b)
+    sc = rt.Scene.from_file(scene_path("cornell_box.json"), add_random_spheres=False)
+    c = sc.camera()
+    assert c.fov_rad == 40.0 * (math.pi / 180.0) and c.position.tuple() == (278.0, 278.0, -800.0)
+
+
+def test_loader_error_behaviour():
+    base = json.load(open(scene_path("cube_test.json")))
+    def load(d):
+        return rt.Scene.from_json(json.dumps(d), add_random_spheres=False)
+    for key in ("camera", "shapes", "materials", "background"):   # SceneJson: all four required
+        d = dict(base); del d[key]
+        with pytest.raises(rt.RtError, match="missing field"):
+            load(d)
+    d = json.loads(json.dumps(base)); d["shapes"][0]["material"] = "Nope"
+    with pytest.raises(rt.RtError, match="not found"):
+        load(d)
+    d = json.loads(json.dumps(base)); d["shapes"][0]["type"] = "TransformedSphere"   # dupin.json's old tag
+    with pytest.raises(rt.RtError, match="unknown variant"):
+        load(d)
+    with pytest.raises(rt.RtError):
+        rt.Scene.from_json("{ not json", add_random_spheres=False)
+    # both Vector3d spellings, unknown keys ignored, depth defaults to 4
+    d = json.loads(json.dumps(base))
+    d["shapes"][0]["transform"]["translate"] = {"x": 5, "y": 6, "z": 0}
+    d["shapes"][0]["bogus"] = 1
+    d["shapes"].append({"type": "BruteForsableShape", "shape": {"type": "Heart"}, "step": 0.01,
+                        "transform": {"translate": [0, 0, 0], "rotate": [0, 0, 0], "scale": [1, 1, 1]}, "material": "Red"})
+    sc = load(d)
+    dd = sc.desc()
+    params = np.ctypeslib.as_array(dd.params, shape=(dd.n_shapes, 8))
+    assert params[-1][0] == _ffi.RT_SURF_HEART and params[-1][1] == 0.01 and params[-1][2] == 4.0
+    ref = load(base).desc()
+    assert np.array_equal(np.ctypeslib.as_array(ref.direct, shape=(ref.n_shapes, 12))[0],
+                          np.ctypeslib.as_array(dd.direct, shape=(dd.n_shapes, 12))[0])
+
+
+def test_image_texture_loaded_and_material_reassign():
+    sc = rt.Scene.from_file(scene_path("detached_materials.json"), add_random_spheres=False)
+    d = sc.desc()
+    assert d.n_images == 1 and d.images[0].width == 1024 and d.images[0].height == 512
+    names = [_ffi.host().rth_scene_material_name(sc._h, i).decode() for i in range(d.n_materials)]
+    assert "EarthMap" in names
+    sc.assign_material(1, "EarthMap")
+    assert sc.desc().material[1] == names.index("EarthMap")
+    with pytest.raises(rt.RtError):
+        sc.assign_material(1, "Nope")
+
+
+def test_compute_entry_points_fail_loudly_without_gpu():
+    if rt.device_count() > 0:
+        pytest.skip("GPU present")
+    sc = rt.Scene.from_file(scene_path("cube_test.json"), add_random_spheres=False)
+    with pytest.raises(rt.RtError, match="no CUDA device"):
+        sc.closest_hit(np.zeros((1, 6)))
+    with pytest.raises(rt.RtError, match="no CUDA device"):
+        rt.GpuRenderer(sc, 12, 8)
+    with pytest.raises(rt.RtError, match="no CUDA device"):
+        rt.measure_peaks()
+
+
+def test_shard_float4_count():
+    lib = _ffi.core()
+    p = _ffi.RenderParams()
+    p.image = _ffi.ImageParams(100, 70)
+    p.shard_count = 1
+    assert lib.rt_shard_float4_count(C.byref(p), 0) == 7000
+    p.shard_count, p.tile_width, p.tile_height = 4, 32, 32      # 4 x 3 = 12 tiles -> 3 per shard
+    assert [lib.rt_shard_float4_count(C.byref(p), s) for s in range(4)] == [3 * 1024] * 4
+    p.shard_count = 5                                            # 12 tiles over 5 shards: 3,3,2,2,2
+    assert [lib.rt_shard_float4_count(C.byref(p), s) for s in range(5)] == [3072, 3072, 2048, 2048, 2048]
