@@ -868,7 +868,10 @@ double render(const Scene& sc, const rt_camera& cam, const RenderOptions& opt, r
 
     // new_dispatcher_thread, renderer/mod.rs:66-90: ONE thread generates every primary ray
     std::thread dispatcher([&] {
-        size_t chunk_size = (size_t)((width * height) / threads / 8);
+        // chunk = w*h/threads/8 pixels (renderer/mod.rs:74); for a strided (bounded) sample the same
+        // rule is applied to the pixels actually traced, so the workers stay equally loaded
+        uint32_t traced = ((width + sx - 1) / sx) * ((height + sy - 1) / sy);
+        size_t chunk_size = (size_t)(traced / threads / 8);
         if (chunk_size == 0) chunk_size = 1;
         RayCaster rc = raycaster_new(cam, opt.image);
         PathRng rng;

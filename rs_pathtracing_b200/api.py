@@ -251,3 +251,63 @@ def measure_peaks(device: int = 0):
     a, b = C.c_double(), C.c_double()
     _check(_ffi.core().rt_measure_peaks(device, C.byref(a), C.byref(b)))
     return a.value, b.value
+
+
+# ------------------------------------------------------------------------------------------------
+# raw C-ABI rendering calls (rt_render_*), used by the sharded multi-GPU path and by tests
+# ------------------------------------------------------------------------------------------------
+def render_params(width: int, height: int, samples_number: int, max_depth: int, seed: int = 0,
+                  shard_count: int = 1, shard_index: int = 0, tile: int = 0) -> RenderParams:
+    p = RenderParams()
+    p.image = ImageParams(width, height)
+    p.samples_number = samples_number
+    p.max_depth = max_depth
+    p.seed = seed
+    p.shard_count = shard_count
+    p.shard_index = shard_index
+    p.tile_width = tile
+    p.tile_height = tile
+    return p
+
+
+def render_start(dev_scene, camera: Camera, params: RenderParams) -> None:
+    _check(_ffi.core().rt_render_start(dev_scene, C.byref(camera), C.byref(params)))
+
+
+def render_poll(dev_scene, buffer: Optional[np.ndarray]) -> bool:
+    done = C.c_int(0)
+    ptr = buffer.ctypes.data_as(C.c_void_p) if buffer is not None else None
+    _check(_ffi.core().rt_render_poll(dev_scene, ptr, C.byref(done)))
+    return bool(done.value)
+
+
+def render_wait(dev_scene, buffer: Optional[np.ndarray]) -> None:
+    ptr = buffer.ctypes.data_as(C.c_void_p) if buffer is not None else None
+    _check(_ffi.core().rt_render_wait(dev_scene, ptr))
+
+
+def render_device_result(dev_scene):
+    """(device pointer, n_float4) of the shard's tile-packed float4 accumulator."""
+    ptr, n = C.c_void_p(), C.c_uint64()
+    _check(_ffi.core().rt_render_device_result(dev_scene, C.byref(ptr), C.byref(n)))
+    return ptr.value, n.value
+
+
+def shard_float4_count(params: RenderParams, shard_index: int) -> int:
+    return _ffi.core().rt_shard_float4_count(C.byref(params), shard_index)
+
+
+def assemble_frame(dev_scene, params: RenderParams, shard_ptrs, d_frame_ptr: int, stream: int = 0) -> None:
+    arr = (C.c_void_p * len(shard_ptrs))(*shard_ptrs)
+    _check(_ffi.core().rt_assemble_frame(dev_scene, C.byref(params), arr, C.c_void_p(d_frame_ptr),
+                                         C.c_void_p(stream) if stream else None))
+
+
+class DevicePointer:
+    """Expose a raw device allocation to torch (torch.as_tensor(DevicePointer(...), device='cuda'))
+    through __cuda_array_interface__, without copying."""
+
+    def __init__(self, ptr: int, shape, typestr: str = "<f4", owner=None):
+        self._owner = owner
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr,
+                                         "version": 3, "strides": None}

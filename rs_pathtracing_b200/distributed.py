@@ -1,0 +1,87 @@
+"""One process per GPU: interleaved-tile sharding of a frame with a single NCCL gather.
+
+torch / torch.distributed are plumbing only (process group, device buffers for the gather); every
+pixel is produced by the CUDA core through the C ABI (rt_render_start with shard_count/shard_index,
+rt_render_device_result, rt_assemble_frame).  Tile k (row-major, 32x32 by default) belongs to rank
+k % world_size; the RNG is keyed by (pixel, sample, event), so the assembled frame does not depend on
+the number of GPUs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import api
+from ._ffi import Camera
+
+
+class DistributedRenderer:
+    """Renderer-trait-shaped front end for N ranks.  Every rank constructs it with the same scene and
+    calls render(); rank 0 returns the full frame (numpy, h x w x 3 float64), the others None."""
+
+    def __init__(self, scene: api.Scene, depth: int, seed: int = 0, tile: int = 32, device: Optional[int] = None):
+        import torch
+        import torch.distributed as dist
+
+        self.torch, self.dist = torch, dist
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.device = torch.cuda.current_device() if device is None else device
+        self.scene, self.depth, self.seed, self.tile = scene, depth, seed, tile
+        self.dev_scene = scene.device_scene(self.device)
+        self._gather_bufs = None
+        self._frame = None
+        self._host = None
+
+    def _params(self, w, h, spp, shard):
+        return api.render_params(w, h, spp, self.depth, self.seed, self.world, shard, tile=self.tile)
+
+    def render_device(self, camera: Camera, width: int, height: int, samples_number: int):
+        """Render this rank's tiles, gather, assemble on rank 0.  Returns the device frame tensor on
+        rank 0 (h x w x 3 float64), None elsewhere.  No host synchronisation besides NCCL's own."""
+        torch, dist = self.torch, self.dist
+        p = self._params(width, height, samples_number, self.rank)
+        api.render_start(self.dev_scene, camera, p)
+        ptr, n = api.render_device_result(self.dev_scene)   # waits for this shard's kernels
+        mine = torch.as_tensor(api.DevicePointer(ptr, (n, 4), "<f4", owner=self), device=f"cuda:{self.device}")
+        if self.world == 1:
+            shards = [mine]
+        else:
+            counts = [api.shard_float4_count(p, s) for s in range(self.world)]
+            if self.rank == 0:
+                if self._gather_bufs is None or [b.shape[0] for b in self._gather_bufs] != counts:
+                    self._gather_bufs = [torch.empty((c, 4), dtype=torch.float32, device=mine.device) for c in counts]
+                shards = self._gather_bufs
+            # one exchange per frame: every rank's tile-packed accumulator to rank 0 over NVLink.
+            # Shard sizes can differ by one tile, so this is grouped send/recv rather than dist.gather.
+            ops = []
+            if self.rank == 0:
+                shards[0].copy_(mine)
+                for s in range(1, self.world):
+                    ops.append(dist.P2POp(dist.irecv, shards[s], s))
+            else:
+                ops.append(dist.P2POp(dist.isend, mine, 0))
+            if ops:
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
+            if self.rank != 0:
+                return None
+        if self._frame is None or tuple(self._frame.shape) != (height, width, 3):
+            self._frame = torch.empty((height, width, 3), dtype=torch.float64, device=mine.device)
+        api.assemble_frame(self.dev_scene, self._params(width, height, samples_number, 0),
+                           [int(s.data_ptr()) for s in shards], int(self._frame.data_ptr()),
+                           stream=int(torch.cuda.current_stream().cuda_stream))
+        return self._frame
+
+    def render(self, camera: Camera, width: int, height: int, samples_number: int) -> Optional[np.ndarray]:
+        frame = self.render_device(camera, width, height, samples_number)
+        if frame is None:
+            return None
+        torch = self.torch
+        if self._host is None or tuple(self._host.shape) != tuple(frame.shape):
+            self._host = torch.empty(frame.shape, dtype=frame.dtype, pin_memory=True)
+        self._host.copy_(frame, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._host.numpy()

@@ -1,0 +1,164 @@
+"""GPU parity of the batched nearest-hit kernel (rt_intersect_batch through the C ABI) against the
+oracle: shape index bit-exact, t / normal / point bit-exact (the contract allows 1e-5 relative; the
+FP64 no-FMA kernel is expected to give 0 ulp and the test says so), uv within 1e-12."""
+import math
+
+import numpy as np
+import pytest
+
+import rs_pathtracing_b200 as rt
+from oracle import pyoracle as po
+
+from conftest import scene_path
+
+pytestmark = pytest.mark.gpu
+
+TRIO = {
+    "camera": {"position": [0, 0, -10], "direction": [0, 0, 1], "up": [0, 1, 0], "fov": 40.0, "focal_length": 1.0},
+    "background": [0, 0, 0],
+    "materials": {"M": {"type": "Lambertian", "albedo": {"type": "SolidColor", "color": [0.9, 0.1, 0.1]}}},
+    "shapes": [
+        {"type": "Sphere", "name": "Test sphere", "material": "M",
+         "transform": {"translate": [0, 0, 0], "rotate": [0, 0, 0], "scale": [1, 1, 1]}},
+        {"type": "Cube", "name": "Test cube", "material": "M",
+         "transform": {"translate": [0, 0, 0], "rotate": [0, 0, 0], "scale": [1, 1, 1]}},
+        {"type": "BruteForsableShape", "shape": {"type": "Heart"}, "step": 0.01, "material": "M",
+         "transform": {"translate": [0, 0, 0], "rotate": [0, 0, 0], "scale": [1, 1, 1]}},
+    ],
+}
+
+
+def bench_rays(n, seed=42, target_radius=3.0):
+    """benches/bench_intersections.rs:69-70: pos = -random_in_sphere(10), ray toward the origin;
+    here the target is jittered inside a ball so that about half of the rays miss (SURVEY §8d cfg 2)."""
+    rng = np.random.default_rng(seed)
+
+    def ball(m, r):
+        out = np.empty((0, 3))
+        while out.shape[0] < m:
+            v = rng.uniform(-r, r, (2 * m, 3))
+            out = np.concatenate([out, v[(v * v).sum(1) <= r * r]])
+        return out[:m]
+
+    o = -ball(n, 10.0)
+    tgt = ball(n, target_radius)
+    return rt.make_rays(o, tgt - o)
+
+
+def scene_rays(sc, n, seed):
+    """half primary-like rays from the camera through the viewport, half rays between random points of
+    the scene's bounding region (secondary-like)"""
+    import json
+    cam = sc.camera()
+    rng = np.random.default_rng(seed)
+    w = h = 256
+    xs, ys = rng.uniform(0, w, n // 2), rng.uniform(0, h, n // 2)
+    prim = np.array([po.get_ray(cam, w, h, x, y) for x, y in zip(xs, ys)])
+    d = sc.desc()
+    dirm = np.ctypeslib.as_array(d.direct, shape=(d.n_shapes, 12))
+    centres = dirm[:, [3, 7, 11]]
+    scale = np.abs(dirm[:, [0, 5, 10]]).max(1)
+    ok = scale < 1e4
+    a = centres[ok][rng.integers(0, ok.sum(), n - n // 2)] + rng.normal(size=(n - n // 2, 3)) * (scale[ok].mean() + 1.0)
+    b = centres[ok][rng.integers(0, ok.sum(), n - n // 2)] + rng.normal(size=(n - n // 2, 3)) * 0.3
+    sec = rt.make_rays(a, b - a)
+    return np.concatenate([prim, sec])
+
+
+def check_parity(sc, rays, t_min=0.001, t_max=math.inf, mode=rt.RT_ISECT_BRUTE):
+    osc = po.OracleScene(sc.desc())
+    want = osc.intersect_batch(rays, t_min, t_max)
+    got = sc.closest_hit(rays, t_min, t_max, mode=mode)
+    assert np.array_equal(got["index"], want["index"]), \
+        f"{(got['index'] != want['index']).sum()} of {len(rays)} nearest-hit indices differ"
+    hit = want["index"] >= 0
+    for k in ("t", "normal", "point"):
+        g, w_ = got[k][hit], want[k][hit]
+        same = (g == w_) | (np.isnan(g) & np.isnan(w_))
+        rel = np.abs(g - w_) / np.maximum(np.abs(w_), 1e-300)
+        assert same.all(), f"{k}: {(~same).sum()} values differ, max rel err {np.nanmax(rel[~same]):.3e}"
+    assert np.array_equal(got["front"][hit], want["front"][hit])
+    assert np.allclose(got["uv"][hit], want["uv"][hit], rtol=0, atol=1e-12, equal_nan=True)
+    return want
+
+
+def test_bench_trio_parity():
+    import json
+    sc = rt.Scene.from_json(json.dumps(TRIO), add_random_spheres=False)
+    rays = bench_rays(1 << 17)
+    want = check_parity(sc, rays)
+    frac = (want["index"] >= 0).mean()
+    assert 0.2 < frac < 0.9, frac
+    # the unit cube encloses the unit sphere, so the sphere (index 0) can never be the nearest hit
+    assert set(np.unique(want["index"])) == {-1, 1, 2}
+
+
+@pytest.mark.parametrize("name", ["spheres.json", "cornell_box.json", "detached_materials.json", "dupin.json",
+                                  "cube_test.json"])
+def test_fixture_scene_parity(name):
+    sc = rt.Scene.from_file(scene_path(name), random_spheres_seed=1)
+    rays = scene_rays(sc, 1 << 14, seed=7)
+    want = check_parity(sc, rays)
+    assert (want["index"] >= 0).mean() > 0.3
+    kinds = sc.shape_kinds()
+    assert len(set(kinds[want["index"][want["index"] >= 0]])) >= 2   # more than one shape type wins
+
+
+def test_finite_t_max_and_t_min():
+    sc = rt.Scene.from_file(scene_path("cornell_box.json"), random_spheres_seed=1)
+    rays = scene_rays(sc, 4096, seed=3)
+    a = check_parity(sc, rays, t_min=0.001, t_max=700.0)
+    b = check_parity(sc, rays, t_min=50.0, t_max=math.inf)
+    assert (a["index"] != b["index"]).any()
+
+
+def test_empty_and_ragged_inputs():
+    sc = rt.Scene.from_file(scene_path("cube_test.json"), random_spheres_seed=1)
+    out = sc.closest_hit(np.zeros((0, 6)))
+    assert out["index"].shape == (0,)
+    for n in (1, 31, 33, 257):   # not multiples of the warp / block size
+        check_parity(sc, scene_rays(sc, 2 * n, seed=n)[:n])
+    empty = rt.Scene.from_file(scene_path("empty.json"), add_random_spheres=False)
+    out = empty.closest_hit(bench_rays(100))
+    assert (out["index"] == -1).all()
+
+
+def test_degenerate_rays_follow_the_reference():
+    """tangent ray (D == 0 accepted without range check, t = -half_b * a),
+    origin inside a cube (hit at t_min), ray inside a rectangle's plane (NaN t), zero direction."""
+    import json
+    scene = json.loads(json.dumps(TRIO))
+    scene["shapes"] = [
+        {"type": "Rectangle", "x0": -1, "y0": -1, "x1": 1, "y1": 1, "material": "M",
+         "transform": {"translate": [0, 0, 5], "rotate": [0, 0, 0], "scale": [1, 1, 1]}},
+        {"type": "Cube", "name": "c", "material": "M",
+         "transform": {"translate": [10, 0, 0], "rotate": [0, 0, 0], "scale": [1, 1, 1]}},
+        {"type": "Sphere", "name": "s", "material": "M",
+         "transform": {"translate": [0, 0, 0], "rotate": [0, 0, 0], "scale": [1, 1, 1]}},
+        {"type": "Sphere", "name": "s2", "material": "M",
+         "transform": {"translate": [0, 0, 20], "rotate": [0, 0, 0], "scale": [2, 2, 2]}},
+    ]
+    sc = rt.Scene.from_json(json.dumps(scene), add_random_spheres=False)
+    rays = np.array([
+        [1.0, 0.0, -10.0, 0.0, 0.0, 1.0],      # tangent to the unit sphere: D == 0
+        [2.0, 0.0, -10.0, 0.0, 0.0, 1.0],      # tangent to the scaled sphere behind it
+        [10.0, 0.2, 0.1, 0.0, 0.0, 1.0],       # origin inside the cube
+        [-5.0, 0.0, 5.0, 1.0, 0.0, 0.0],       # in the rectangle's plane: t = -0/0 = NaN
+        [0.0, 0.0, -10.0, 0.0, 0.0, 0.0],      # zero direction
+        [0.0, 0.0, -10.0, math.nan, 0.0, 1.0],  # NaN direction
+        [0.0, 0.0, -10.0, 0.0, 0.0, 1.0],      # plain hit through everything
+    ])
+    want = check_parity(sc, rays)
+    assert want["index"][2] == 1 and want["t"][2] == 0.001
+
+
+def test_later_shape_wins_ties():
+    """A.3: equal t -> the later shape in the list wins (shrinking max_t accepts t == max_t)"""
+    import json
+    scene = json.loads(json.dumps(TRIO))
+    one = {"type": "Sphere", "name": "s", "material": "M",
+           "transform": {"translate": [0, 0, 0], "rotate": [0, 0, 0], "scale": [1, 1, 1]}}
+    scene["shapes"] = [one, dict(one), dict(one)]
+    sc = rt.Scene.from_json(json.dumps(scene), add_random_spheres=False)
+    want = check_parity(sc, bench_rays(2048, target_radius=0.8))
+    assert set(np.unique(want["index"])) <= {-1, 2}
