@@ -256,6 +256,8 @@ typedef struct rt_stats {
     uint64_t cull_tests;        /* conservative pre-tests executed                              */
     uint64_t march_steps;       /* implicit-surface function evaluations                        */
     uint64_t march_rays;        /* (ray, marching shape) pairs marched                          */
+    uint64_t march_long_rays;   /* ... of which needed more than 2048 evaluations               */
+    uint64_t march_max_evals;   /* most evaluations a single marched ray needed                 */
     double last_frame_ms;       /* device time of the last completed frame (CUDA events)        */
     double last_intersect_ms;   /* device time of the last rt_intersect_batch kernel            */
 } rt_stats;
@@ -264,6 +266,11 @@ int rt_reset_stats(rt_scene* scene);
 /* enable (1) / disable (0) the per-kernel work counters above (segments..march_rays); counting
  * costs a few atomics per block and is off by default.  kernel_launches / *_ms are always on. */
 int rt_set_counters(rt_scene* scene, int enabled);
+
+/* Host-only helper behind the exact-skip marcher: rigorous interval bounds G >= sup |grad f| and
+ * H >= sup |u^T Hess f u| of a ray-marched surface (params8 = the shape's params row) over its marching
+ * region.  Exposed so that tests can check them against sampled derivatives; needs no device. */
+int rt_march_region_bounds(const double* params8, double* grad_bound, double* hess_bound);
 
 /* FP64 / FP32 FMA micro-benchmarks used as roofline denominators (TFLOP/s, FMA = 2 flop). */
 int rt_measure_peaks(int device, double* fp64_tflops, double* fp32_tflops);

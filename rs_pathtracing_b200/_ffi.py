@@ -96,6 +96,8 @@ class Stats(C.Structure):
         ("cull_tests", C.c_uint64),
         ("march_steps", C.c_uint64),
         ("march_rays", C.c_uint64),
+        ("march_long_rays", C.c_uint64),
+        ("march_max_evals", C.c_uint64),
         ("last_frame_ms", C.c_double),
         ("last_intersect_ms", C.c_double),
     ]
@@ -127,6 +129,7 @@ CORE_SYMBOLS = {
     "rt_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "rt_reset_stats": (C.c_int, [C.c_void_p]),
     "rt_set_counters": (C.c_int, [C.c_void_p, C.c_int]),
+    "rt_march_region_bounds": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rt_measure_peaks": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 

@@ -23,6 +23,8 @@ CORE_SOURCES = [os.path.join(CSRC, "rt_core.cu")]
 CORE_HEADERS = [
     os.path.join(CSRC, "rt_math.cuh"),
     os.path.join(CSRC, "rt_scene.cuh"),
+    os.path.join(CSRC, "rt_march.cuh"),
+    os.path.join(CSRC, "march_bounds.hpp"),
     os.path.join(ROOT, "include", "rt_b200.h"),
 ]
 HOST_SOURCES = [os.path.join(CSRC, "host", "ray_tracing.cpp"), os.path.join(CSRC, "host", "host_c.cpp")]
@@ -40,6 +42,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math",
     "-Xptxas", "-v",
+    "-diag-suppress", "20014",   # surface_func_t<Jet2> is a host-only instantiation of a __host__ __device__ template
     "-shared", "-cudart", "static",
 ]
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-shared"]

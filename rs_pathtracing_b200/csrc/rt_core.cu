@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 
+#include "march_bounds.hpp"
 #include "rt_scene.cuh"
 
 using namespace rt;
@@ -114,9 +115,11 @@ __device__ __forceinline__ Staged stage_scene(const DevScene& S, bool use_smem) 
 
 __device__ __forceinline__ void flush_counters(const DevCounters& c, DevCounters* g) {
     // warp-reduce, one atomic per warp and counter
-    unsigned long long v[5] = {c.segments, c.shape_tests, c.cull_tests, c.march_steps, c.march_rays};
+    unsigned long long v[6] = {c.segments, c.shape_tests, c.cull_tests, c.march_steps, c.march_rays, c.march_long_rays};
+    unsigned long long mx = c.march_max_evals;
+    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
+    for (int k = 0; k < 6; k++) {
         unsigned long long x = v[k];
         for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
         v[k] = x;
@@ -127,27 +130,30 @@ __device__ __forceinline__ void flush_counters(const DevCounters& c, DevCounters
         atomicAdd(&g->cull_tests, v[2]);
         atomicAdd(&g->march_steps, v[3]);
         atomicAdd(&g->march_rays, v[4]);
+        atomicAdd(&g->march_long_rays, v[5]);
+        atomicMax(&g->march_max_evals, mx);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // K2/K3: batched nearest hit
 // ------------------------------------------------------------------------------------------------
-template <bool COUNT>
+template <bool COUNT, bool FAST>
 __global__ void __launch_bounds__(256)
 k_intersect_batch(DevScene S, bool use_smem, const rt_ray* __restrict__ rays, unsigned long long n, double t_min,
                   double t_max, int32_t* __restrict__ shape_index, double* __restrict__ t_out,
                   rt_vec3* __restrict__ normal, rt_vec3* __restrict__ point, double* __restrict__ uv,
                   uint8_t* __restrict__ front_face, DevCounters* g_counters) {
     Staged st = stage_scene(S, use_smem);
-    DevCounters c = {0, 0, 0, 0, 0};
+    DevCounters c = {0, 0, 0, 0, 0, 0, 0};
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         rt_ray r = rays[i];
         D3 ro = mk(r.origin.x, r.origin.y, r.origin.z), rd = mk(r.direction.x, r.direction.y, r.direction.z);
         double bt;
         int bi;
-        nearest_hit_brute<COUNT>(S, st.inv, st.kind, ro, rd, t_min, t_max, bt, bi, c);
+        if (FAST) nearest_hit_fast<COUNT>(S, st.inv, st.kind, ro, rd, t_min, t_max, bt, bi, c);
+        else nearest_hit_brute<COUNT>(S, st.inv, st.kind, ro, rd, t_min, t_max, bt, bi, c);
         if (shape_index) shape_index[i] = bi;
         if (bi < 0) {
             if (t_out) t_out[i] = 0.0;
@@ -235,7 +241,7 @@ k_bounce(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
          uint32_t* count_out, uint32_t level, uint32_t max_depth, ShardMap map, unsigned long long first_owned,
          uint32_t spp, uint32_t k0, uint32_t k1, float4* __restrict__ radiance, DevCounters* g_counters) {
     Staged st = stage_scene(S, use_smem);
-    DevCounters c = {0, 0, 0, 0, 0};
+    DevCounters c = {0, 0, 0, 0, 0, 0, 0};
     const uint32_t n = *count_in;
     const uint32_t n_round = (n + 31u) & ~31u;
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -250,7 +256,7 @@ k_bounce(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
             pid = in.pid[i];
             double bt;
             int bi;
-            nearest_hit_brute<COUNT>(S, st.inv, st.kind, ro, rd, 0.001, INFINITY, bt, bi, c);  // mod.rs:24
+            nearest_hit_fast<COUNT>(S, st.inv, st.kind, ro, rd, 0.001, INFINITY, bt, bi, c);  // mod.rs:24
             D3 L = mk(0.0, 0.0, 0.0);
             if (bi < 0) {
                 L = hadamard(beta, sky(rd));  // :41-43
@@ -287,6 +293,154 @@ k_bounce(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
         }
     }
     if (COUNT) flush_counters(c, g_counters);
+}
+
+// ---- the wavefront proper: extend -> march -> shade ---------------------------------------------
+// Splitting the segment into three kernels keeps the expensive, rare and irregular part — marching an
+// implicit surface — out of the regular one: k_extend runs the analytic shape list with every lane
+// busy and only QUEUES the rays whose bounding chord can still beat their best analytic hit; k_march
+// runs those rays densely packed; k_shade finalises the winner, scatters and compacts the survivors.
+
+struct HitQueue {
+    double* t;        // best t so far (max_t = +inf when nothing was hit)
+    int32_t* index;   // winning shape, -1 = none, RT_HIT_REPLAY = degenerate ray: replay the literal loop
+    uint32_t* mq_slot;  // march queue: path slot ...
+    uint32_t* mq_mask;  // ... and the marched shapes (bit k = S.march_index[k]) it still has to test
+};
+#define RT_HIT_REPLAY (-2)
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256)
+k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ count_in, HitQueue hq,
+         uint32_t* march_count, DevCounters* g_counters) {
+    Staged st = stage_scene(S, use_smem);
+    DevCounters c = {0, 0, 0, 0, 0, 0, 0};
+    const uint32_t n = *count_in;
+    const uint32_t n_round = (n + 31u) & ~31u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        uint32_t mask = 0;
+        if (i < n) {
+            D3 ro = mk(in.ox[i], in.oy[i], in.oz[i]);
+            D3 rd = mk(in.dx[i], in.dy[i], in.dz[i]);
+            double best;
+            int winner;
+            bool degenerate = analytic_nearest<COUNT>(S, st.inv, st.kind, ro, rd, 0.001, INFINITY, best, winner, c);
+            if (degenerate) {
+                winner = RT_HIT_REPLAY;
+                mask = 0xffffffffu;
+            } else {
+                for (int k = 0; k < S.n_march; k++) {
+                    const int si = S.march_index[k];
+                    D3 o, d;
+                    double start, end_c;
+                    if (march_needed(S, st.inv + 12 * si, S.params + RT_SHAPE_PARAMS * si, ro, rd, best, o, d, start, end_c))
+                        mask |= 1u << k;
+                }
+                if (COUNT) c.shape_tests += S.n_march;
+            }
+            if (COUNT) c.segments++;
+            hq.t[i] = best;
+            hq.index[i] = winner;
+        }
+        uint32_t slot = queue_append(mask != 0, march_count);
+        if (mask != 0) {
+            hq.mq_slot[slot] = i;
+            hq.mq_mask[slot] = mask;
+        }
+    }
+    if (COUNT) flush_counters(c, g_counters);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(128)
+k_march(DevScene S, PathQueue in, HitQueue hq, const uint32_t* __restrict__ march_count, DevCounters* g_counters) {
+    DevCounters c = {0, 0, 0, 0, 0, 0, 0};
+    const uint32_t n = *march_count;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const uint32_t i = hq.mq_slot[j];
+        uint32_t mask = hq.mq_mask[j];
+        D3 ro = mk(in.ox[i], in.oy[i], in.oz[i]);
+        D3 rd = mk(in.dx[i], in.dy[i], in.dz[i]);
+        double best = hq.t[i];
+        int winner = hq.index[i];
+        bool degenerate = winner == RT_HIT_REPLAY;
+        if (!degenerate) {
+            DevCounters cc = {0, 0, 0, 0, 0, 0, 0};
+            while (mask && !degenerate) {
+                int k = __ffs(mask) - 1;
+                mask &= mask - 1;
+                degenerate = march_shape_update<COUNT>(S, S.inv, k, ro, rd, 0.001, INFINITY, best, winner, cc);
+            }
+            if (COUNT) {  // shape tests were counted by k_extend
+                c.march_steps += cc.march_steps; c.march_rays += cc.march_rays; c.march_long_rays += cc.march_long_rays;
+                if (cc.march_max_evals > c.march_max_evals) c.march_max_evals = cc.march_max_evals;
+            }
+        }
+        if (degenerate) {
+            DevCounters cc = {0, 0, 0, 0, 0, 0, 0};
+            nearest_hit_brute<false>(S, S.inv, S.kind, ro, rd, 0.001, INFINITY, best, winner, cc);
+        }
+        hq.t[i] = best;
+        hq.index[i] = winner;
+    }
+    if (COUNT) flush_counters(c, g_counters);
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(256)
+k_shade(DevScene S, PathQueue in, const uint32_t* __restrict__ count_in, HitQueue hq, PathQueue out, uint32_t* count_out,
+        uint32_t level, uint32_t max_depth, ShardMap map, unsigned long long first_owned, uint32_t spp, uint32_t k0,
+        uint32_t k1, float4* __restrict__ radiance) {
+    const uint32_t n = *count_in;
+    const uint32_t n_round = (n + 31u) & ~31u;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        bool alive = false;
+        D3 no = mk(0, 0, 0), nd = mk(0, 0, 0), nb = mk(0, 0, 0);
+        uint32_t pid = 0;
+        if (i < n) {
+            D3 rd = mk(in.dx[i], in.dy[i], in.dz[i]);
+            D3 beta = mk(in.bx[i], in.by[i], in.bz[i]);
+            pid = in.pid[i];
+            const int bi = hq.index[i];
+            D3 L = mk(0.0, 0.0, 0.0);
+            if (bi < 0) {
+                L = hadamard(beta, sky(rd));  // renderer/mod.rs:41-43
+            } else if (level == max_depth) {
+                // depth == 0: black (:26-27)
+            } else {
+                D3 ro = mk(in.ox[i], in.oy[i], in.oz[i]);
+                HitRec h;
+                finalize_hit(S, bi, hq.t[i], ro, rd, h);
+                uint32_t pl = pid / spp, s = pid % spp, x, y;
+                map.pixel_of(first_owned + pl, x, y);
+                PathRng rng;
+                rng.k0 = k0; rng.k1 = k1;
+                rng.pixel = x + y * map.width;
+                rng.sample = s;
+                rng.begin_event(level + 1);
+                D3 ndir, atten;
+                if (scatter_or_emit(S, h, rd, rng, ndir, atten)) {  // :29-32
+                    alive = true;
+                    no = h.point;
+                    nd = ndir;
+                    nb = hadamard(beta, atten);
+                } else {
+                    L = hadamard(beta, atten);  // :34-36
+                }
+            }
+            if (!alive) radiance[pid] = make_float4((float)L.x, (float)L.y, (float)L.z, 1.0f);
+        }
+        uint32_t slot = queue_append(alive, count_out);
+        if (alive) {
+            out.ox[slot] = no.x; out.oy[slot] = no.y; out.oz[slot] = no.z;
+            out.dx[slot] = nd.x; out.dy[slot] = nd.y; out.dz[slot] = nd.z;
+            out.bx[slot] = nb.x; out.by[slot] = nb.y; out.bz[slot] = nb.z;
+            out.pid[slot] = pid;
+        }
+    }
 }
 
 // K5: per-pixel mean of the batch (trace_pixel_samples, src/renderer/mod.rs:151-155).  One thread
@@ -370,6 +524,8 @@ __global__ void __launch_bounds__(256) k_fma_peak(T* out, int iters, T a, T b) {
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+#define RT_MAX_LEVELS 64  // counters per batch: level 0 .. max_depth + 1
+
 struct Batch {
     uint64_t first_owned;
     uint32_t n_pixels;
@@ -403,7 +559,10 @@ struct rt_scene {
     PathQueue q[2]{};
     std::vector<void*> qallocs;
     float4* d_radiance = nullptr;
-    uint32_t* d_counts = nullptr;  // one counter per level, per batch slot (reset per batch)
+    HitQueue hq{};
+    uint32_t* d_counts = nullptr;  // [0, RT_MAX_LEVELS): live paths per level; [RT_MAX_LEVELS, 2*RT_MAX_LEVELS): march queue lengths (reset per batch)
+    int grid_extend = 0, grid_march = 0, grid_shade = 0;
+    bool wavefront = true;         // extend/march/shade; false = fused k_bounce (more than 32 marched shapes)
     float4* d_accum = nullptr;
     rt_vec3* d_frame = nullptr;    // owned order
     uint64_t frame_capacity = 0;
@@ -526,22 +685,43 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
         if (d->kind[i] == RT_SHAPE_MARCH) march.push_back((int)i);
     sc->ds.n_march = (int)march.size();
     if ((rc = upload(sc, march.data(), march.size(), &sc->ds.march_index)) != RT_OK) return bail(rc);
+    // exact-skip marching: gradient bound of each marched surface over its region (rt_march.cuh)
+    std::vector<double> march_G(march.size());
+    for (size_t k = 0; k < march.size(); k++) {
+        double H;
+        bounds::region_bounds(d->params + (size_t)march[k] * RT_SHAPE_PARAMS, &march_G[k], &H);
+        if (getenv("RT_B200_NO_MARCH_SKIP")) march_G[k] = INFINITY;
+    }
+    if ((rc = upload(sc, march_G.data(), march_G.size(), &sc->ds.march_G)) != RT_OK) return bail(rc);
 
     // shared-memory staging: 96 B of inverse rows + 1 B kind per shape
     sc->smem_bytes = (size_t)n * 12 * sizeof(double) + ((n + 15) & ~15u);
     sc->use_smem = n > 0 && sc->smem_bytes <= sc->smem_optin;
     if (!sc->use_smem) sc->smem_bytes = 0;
     if (sc->smem_bytes > 48 * 1024) {
-        cudaFuncSetAttribute(k_intersect_batch<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
-        cudaFuncSetAttribute(k_intersect_batch<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+        cudaFuncSetAttribute(k_intersect_batch<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+        cudaFuncSetAttribute(k_intersect_batch<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+        cudaFuncSetAttribute(k_intersect_batch<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+        cudaFuncSetAttribute(k_intersect_batch<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
         cudaFuncSetAttribute(k_bounce<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
         cudaFuncSetAttribute(k_bounce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+        cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+        cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
     }
     // persistent grid: a whole number of CTAs per SM
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bounce<false>, 256, sc->smem_bytes);
     if (per_sm < 1) per_sm = 1;
     sc->grid = sc->n_sm * per_sm;
+    auto occ_grid = [&](auto kernel, int threads, size_t smem) {
+        int b = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, threads, smem);
+        return sc->n_sm * std::max(b, 1);
+    };
+    sc->grid_extend = occ_grid(k_extend<false>, 256, sc->smem_bytes);
+    sc->grid_march = occ_grid(k_march<false>, 128, 0);
+    sc->grid_shade = occ_grid(k_shade<false>, 256, 0);
+    sc->wavefront = sc->ds.n_march <= 32 && !getenv("RT_B200_FUSED_BOUNCE");
 
     if (cudaMalloc(&sc->d_counters, sizeof(DevCounters)) != cudaSuccess) return bail(fail(RT_ERR_NOMEM, "cudaMalloc failed"));
     cudaMemset(sc->d_counters, 0, sizeof(DevCounters));
@@ -592,12 +772,16 @@ int rt_intersect_batch_device(rt_scene* sc, const rt_ray* d_rays, uint64_t n, do
     cudaStream_t st = stream ? (cudaStream_t)stream : sc->stream;
     uint64_t want = (n + 255) / 256;
     int grid = (int)std::min<uint64_t>(want, (uint64_t)sc->grid);
-    if (sc->counters_on)
-        k_intersect_batch<true><<<grid, 256, sc->smem_bytes, st>>>(sc->ds, sc->use_smem, d_rays, n, t_min, t_max, d_idx,
-                                                                   d_t, d_normal, d_point, d_uv, d_ff, sc->d_counters);
-    else
-        k_intersect_batch<false><<<grid, 256, sc->smem_bytes, st>>>(sc->ds, sc->use_smem, d_rays, n, t_min, t_max, d_idx,
-                                                                    d_t, d_normal, d_point, d_uv, d_ff, sc->d_counters);
+#define RT_LAUNCH_ISECT(C_, F_)                                                                                  \
+    k_intersect_batch<C_, F_><<<grid, 256, sc->smem_bytes, st>>>(sc->ds, sc->use_smem, d_rays, n, t_min, t_max, d_idx, \
+                                                                 d_t, d_normal, d_point, d_uv, d_ff, sc->d_counters)
+    const bool fast = mode == RT_ISECT_FAST;
+    if (sc->counters_on) {
+        if (fast) RT_LAUNCH_ISECT(true, true); else RT_LAUNCH_ISECT(true, false);
+    } else {
+        if (fast) RT_LAUNCH_ISECT(false, true); else RT_LAUNCH_ISECT(false, false);
+    }
+#undef RT_LAUNCH_ISECT
     sc->launches++;
     CU(cudaGetLastError());
     return RT_OK;
@@ -693,7 +877,6 @@ static int alloc_queue(rt_scene* sc, PathQueue& q, uint64_t cap) {
     return RT_OK;
 }
 
-#define RT_MAX_LEVELS 64  // counters per batch: level 0 .. max_depth + 1
 
 // enqueue the bounce loop for paths already in q[0] (count in d_counts[0]); no host sync
 static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long first_owned, uint32_t spp, uint64_t seed) {
@@ -701,14 +884,39 @@ static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long 
     for (uint32_t level = 0; level <= max_depth; level++) {
         PathQueue& in = sc->q[level & 1];
         PathQueue& out = sc->q[(level + 1) & 1];
+        uint32_t* cnt_in = sc->d_counts + level;
+        uint32_t* cnt_out = sc->d_counts + level + 1;
+        uint32_t* mcount = sc->d_counts + RT_MAX_LEVELS + level;
+        if (!sc->wavefront) {
+            if (sc->counters_on)
+                k_bounce<true><<<sc->grid, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, out, cnt_out, level,
+                                                                              max_depth, sc->map, first_owned, spp, k0, k1,
+                                                                              sc->d_radiance, sc->d_counters);
+            else
+                k_bounce<false><<<sc->grid, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, out, cnt_out, level,
+                                                                               max_depth, sc->map, first_owned, spp, k0, k1,
+                                                                               sc->d_radiance, sc->d_counters);
+            sc->launches++;
+            continue;
+        }
         if (sc->counters_on)
-            k_bounce<true><<<sc->grid, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, sc->d_counts + level, out,
-                                                                          sc->d_counts + level + 1, level, max_depth, sc->map,
-                                                                          first_owned, spp, k0, k1, sc->d_radiance, sc->d_counters);
+            k_extend<true><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, sc->d_counters);
         else
-            k_bounce<false><<<sc->grid, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, sc->d_counts + level, out,
-                                                                           sc->d_counts + level + 1, level, max_depth, sc->map,
-                                                                           first_owned, spp, k0, k1, sc->d_radiance, sc->d_counters);
+            k_extend<false><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, sc->d_counters);
+        sc->launches++;
+        if (sc->ds.n_march > 0) {
+            if (sc->counters_on)
+                k_march<true><<<sc->grid_march, 128, 0, sc->stream>>>(sc->ds, in, sc->hq, mcount, sc->d_counters);
+            else
+                k_march<false><<<sc->grid_march, 128, 0, sc->stream>>>(sc->ds, in, sc->hq, mcount, sc->d_counters);
+            sc->launches++;
+        }
+        if (sc->counters_on)
+            k_shade<true><<<sc->grid_shade, 256, 0, sc->stream>>>(sc->ds, in, cnt_in, sc->hq, out, cnt_out, level, max_depth, sc->map,
+                                                                  first_owned, spp, k0, k1, sc->d_radiance);
+        else
+            k_shade<false><<<sc->grid_shade, 256, 0, sc->stream>>>(sc->ds, in, cnt_in, sc->hq, out, cnt_out, level, max_depth, sc->map,
+                                                                   first_owned, spp, k0, k1, sc->d_radiance);
         sc->launches++;
     }
 }
@@ -723,7 +931,14 @@ static int ensure_path_buffers(rt_scene* sc, uint64_t need_paths) {
     if ((rc = alloc_queue(sc, sc->q[0], need_paths)) != RT_OK) return rc;
     if ((rc = alloc_queue(sc, sc->q[1], need_paths)) != RT_OK) return rc;
     CU(cudaMalloc(&sc->d_radiance, need_paths * sizeof(float4)));
-    if (!sc->d_counts) CU(cudaMalloc(&sc->d_counts, RT_MAX_LEVELS * sizeof(uint32_t)));
+    {
+        void* p = nullptr;
+        CU(cudaMalloc(&p, need_paths * sizeof(double))); sc->qallocs.push_back(p); sc->hq.t = (double*)p;
+        CU(cudaMalloc(&p, need_paths * sizeof(int32_t))); sc->qallocs.push_back(p); sc->hq.index = (int32_t*)p;
+        CU(cudaMalloc(&p, need_paths * sizeof(uint32_t))); sc->qallocs.push_back(p); sc->hq.mq_slot = (uint32_t*)p;
+        CU(cudaMalloc(&p, need_paths * sizeof(uint32_t))); sc->qallocs.push_back(p); sc->hq.mq_mask = (uint32_t*)p;
+    }
+    if (!sc->d_counts) CU(cudaMalloc(&sc->d_counts, 2 * RT_MAX_LEVELS * sizeof(uint32_t)));
     sc->path_capacity = need_paths;
     return RT_OK;
 }
@@ -768,7 +983,7 @@ int rt_render_start(rt_scene* sc, const rt_camera* cam, const rt_render_params* 
     CU(cudaEventRecord(sc->ev_frame_start, sc->stream));
     for (uint64_t first = 0; first < sc->owned_pixels; first += px_per_batch) {
         uint32_t npx = (uint32_t)std::min<uint64_t>(px_per_batch, sc->owned_pixels - first);
-        CU(cudaMemsetAsync(sc->d_counts, 0, RT_MAX_LEVELS * sizeof(uint32_t), sc->stream));
+        CU(cudaMemsetAsync(sc->d_counts, 0, 2 * RT_MAX_LEVELS * sizeof(uint32_t), sc->stream));
         k_raygen<<<sc->grid, 256, 0, sc->stream>>>(rcd, sc->map, first, npx, spp, k0, k1, sc->q[0], sc->d_counts, sc->d_radiance);
         sc->launches++;
         launch_bounces(sc, p->max_depth, first, spp, p->seed);
@@ -942,7 +1157,7 @@ int rt_trace_pixel_samples(rt_scene* sc, const rt_ray* rays, uint32_t n_rays, ui
     cudaMalloc(&d_acc, sizeof(float4));
     cudaMalloc(&d_mean, sizeof(rt_vec3));
     cudaMemcpyAsync(d_rays, rays, n_rays * sizeof(rt_ray), cudaMemcpyHostToDevice, sc->stream);
-    cudaMemsetAsync(sc->d_counts, 0, RT_MAX_LEVELS * sizeof(uint32_t), sc->stream);
+    cudaMemsetAsync(sc->d_counts, 0, 2 * RT_MAX_LEVELS * sizeof(uint32_t), sc->stream);
     k_load_rays<<<(n_rays + 255) / 256, 256, 0, sc->stream>>>(d_rays, n_rays, sc->q[0], sc->d_counts);
     sc->launches++;
     // a 1-pixel-wide "image" whose only pixel is pixel_index: owned pixel 0 -> (x = pixel_index, y = 0)
@@ -977,6 +1192,8 @@ int rt_get_stats(rt_scene* sc, rt_stats* out) {
     out->cull_tests = c.cull_tests;
     out->march_steps = c.march_steps;
     out->march_rays = c.march_rays;
+    out->march_long_rays = c.march_long_rays;
+    out->march_max_evals = c.march_max_evals;
     out->last_frame_ms = sc->last_frame_ms;
     out->last_intersect_ms = sc->last_intersect_ms;
     return RT_OK;
@@ -992,6 +1209,13 @@ int rt_reset_stats(rt_scene* sc) {
 int rt_set_counters(rt_scene* sc, int enabled) {
     if (!sc) return fail(RT_ERR_INVALID, "null scene");
     sc->counters_on = enabled != 0;
+    return RT_OK;
+}
+
+int rt_march_region_bounds(const double* params8, double* grad_bound, double* hess_bound) {
+    if (!params8 || !grad_bound || !hess_bound) return fail(RT_ERR_INVALID, "null argument");
+    if (!(params8[0] >= 0 && params8[0] <= RT_SURF_CUSHION)) return fail(RT_ERR_INVALID, "unknown surface kind");
+    bounds::region_bounds(params8, grad_bound, hess_bound);
     return RT_OK;
 }
 

@@ -63,50 +63,72 @@ __device__ __forceinline__ D3 xf_normal(const double* m, D3 n) {  // transpose o
 
 // ------------------------------------------------------------------------------------------------
 // implicit surfaces — src/world/shapes/ray_marching.rs:134-520.  KIND is a compile-time constant so
-// that the marching loop contains exactly one polynomial; q = params[8] of the shape.
+// that the marching loop contains exactly one polynomial; q = params[8] of the shape.  The scalar
+// type is a template parameter: T = double is the reference's arithmetic (same operand order, no
+// FMA), T = Dual gives the derivative along the ray for the safe-skip bound, and the host evaluates
+// the same text with interval jets to bound the second derivatives (march_bounds.hpp).
 // ------------------------------------------------------------------------------------------------
-template <int KIND>
-__device__ __forceinline__ double surface_func(const double* q, D3 p) {
+template <int KIND, typename T>
+__host__ __device__ __forceinline__ T surface_func_t(const double* q, T px, T py, T pz) {
     if (KIND == RT_SURF_HEART) {  // :147-155
-        double x2 = p.x * p.x;
-        double y2 = p.y * p.y;
-        double z2 = p.z * p.z;
-        double z3 = z2 * p.z;
-        double a = x2 + (9.0 / 4.0) * y2 + z2 - 1.0;
+        T x2 = px * px;
+        T y2 = py * py;
+        T z2 = pz * pz;
+        T z3 = z2 * pz;
+        T a = x2 + (9.0 / 4.0) * y2 + z2 - 1.0;
         return a * a * a - x2 * z3 - (9.0 / 80.0) * y2 * z3;
     } else if (KIND == RT_SURF_SINE) {  // :203-211
         double a_ = q[3];
-        return a_ * a_ * (p.x - p.y - p.z) * (p.x + p.y - p.z) * (p.x - p.y + p.z) * (p.x + p.y + p.z) +
-               4.0 * p.x * p.x * p.y * p.y * p.z * p.z;
+        return a_ * a_ * (px - py - pz) * (px + py - pz) * (px - py + pz) * (px + py + pz) +
+               4.0 * px * px * py * py * pz * pz;
     } else if (KIND == RT_SURF_STAR) {  // :268-274
         double a_ = q[3];
-        double x2 = p.x * p.x;
-        double y2 = p.y * p.y;
-        double z2 = p.z * p.z;
-        double c = x2 + y2 + z2 - 1.0;
+        T x2 = px * px;
+        T y2 = py * py;
+        T z2 = pz * pz;
+        T c = x2 + y2 + z2 - 1.0;
         return a_ * (x2 * y2 + x2 * z2 + y2 * z2) + (c * c * c);
     } else if (KIND == RT_SURF_DUPIN) {  // :340-345
         double a_ = q[3], b_ = q[4], c_ = q[5], d_ = q[6];
         double b2 = b_ * b_;
-        double e = p.x * p.x + p.y * p.y + p.z * p.z + b2 - d_ * d_;
-        double f = a_ * p.x - c_ * d_;
-        return e * e - 4.0 * (f * f + b2 * p.y * p.y);
+        T e = px * px + py * py + pz * pz + b2 - d_ * d_;
+        T f = a_ * px - c_ * d_;
+        return e * e - 4.0 * (f * f + b2 * py * py);
     } else if (KIND == RT_SURF_HUNTS) {  // :399-406
-        double x2 = p.x * p.x;
-        double y2 = p.y * p.y;
-        double z2 = p.z * p.z;
-        double a = x2 + y2 + z2 - 13.0;
-        double b = 3.0 * x2 + y2 - 4.0 * z2 - 12.0;
+        T x2 = px * px;
+        T y2 = py * py;
+        T z2 = pz * pz;
+        T a = x2 + y2 + z2 - 13.0;
+        T b = 3.0 * x2 + y2 - 4.0 * z2 - 12.0;
         return 4.0 * a * a * a + 27.0 * b * b;
     } else {  // RT_SURF_CUSHION, :464-478
-        double x2 = p.x * p.x;
-        double y2 = p.y * p.y;
-        double z2 = p.z * p.z;
-        double a = x2 - p.z;
-        return z2 * x2 - z2 * z2 - 2.0 * p.z * x2 + 2.0 * p.z * z2 + x2 - z2 - a * a - y2 * y2 - 2.0 * x2 * y2 -
-               y2 * z2 + 2.0 * y2 * p.z + y2;
+        T x2 = px * px;
+        T y2 = py * py;
+        T z2 = pz * pz;
+        T a = x2 - pz;
+        return z2 * x2 - z2 * z2 - 2.0 * pz * x2 + 2.0 * pz * z2 + x2 - z2 - a * a - y2 * y2 - 2.0 * x2 * y2 -
+               y2 * z2 + 2.0 * y2 * pz + y2;
     }
 }
+
+template <int KIND>
+__device__ __forceinline__ double surface_func(const double* q, D3 p) {
+    return surface_func_t<KIND, double>(q, p.x, p.y, p.z);
+}
+
+// value + derivative along the ray (forward-mode AD); products use the plain product rule
+struct Dual {
+    double v, d;
+};
+__host__ __device__ __forceinline__ Dual operator+(Dual a, Dual b) { return {a.v + b.v, a.d + b.d}; }
+__host__ __device__ __forceinline__ Dual operator-(Dual a, Dual b) { return {a.v - b.v, a.d - b.d}; }
+__host__ __device__ __forceinline__ Dual operator*(Dual a, Dual b) { return {a.v * b.v, a.d * b.v + a.v * b.d}; }
+__host__ __device__ __forceinline__ Dual operator+(Dual a, double b) { return {a.v + b, a.d}; }
+__host__ __device__ __forceinline__ Dual operator-(Dual a, double b) { return {a.v - b, a.d}; }
+__host__ __device__ __forceinline__ Dual operator*(Dual a, double b) { return {a.v * b, a.d * b}; }
+__host__ __device__ __forceinline__ Dual operator*(double a, Dual b) { return {a * b.v, a * b.d}; }
+__host__ __device__ __forceinline__ Dual operator+(double a, Dual b) { return {a + b.v, b.d}; }
+__host__ __device__ __forceinline__ Dual operator-(double a, Dual b) { return {a - b.v, -b.d}; }
 
 __device__ inline D3 surface_gradient(const double* q, D3 p) {
     switch ((int)q[0]) {
@@ -163,6 +185,8 @@ __device__ inline D3 surface_gradient(const double* q, D3 p) {
     }
 }
 
+#define RT_MARCH_BUDGET 200000000ull
+
 // solve_quadratic_equation, src/algebra/equation.rs:5-15
 __device__ __forceinline__ bool solve_quadratic(double a, double half_b, double c, double& x1, double& x2) {
     double d = half_b * half_b - a * c;
@@ -212,7 +236,9 @@ __device__ __forceinline__ bool march_loop(const double* q, D3 o, D3 d, double s
         bool finished = false;
         D3 sd = step * d;  // `step * dir` is loop-invariant until the step changes
         for (;;) {
-            if (t > end || t < start) {
+            // n > RT_MARCH_BUDGET: t + step == t (step underflowed against t); the reference would spin
+            // forever, a kernel must not: report a miss
+            if (t > end || t < start || n > RT_MARCH_BUDGET) {
                 evals += n;
                 return false;
             }
@@ -261,7 +287,8 @@ __device__ inline bool march_candidate(const double* q, D3 o, D3 d, double min_t
 // ------------------------------------------------------------------------------------------------
 
 // Sphere::ray_intersect, src/world/shapes/mod.rs:330-356
-__device__ __forceinline__ bool sphere_candidate(D3 o, D3 d, double min_t, double max_t, double& t) {
+__device__ __forceinline__ bool sphere_candidate(D3 o, D3 d, double min_t, double max_t, double& t,
+                                                 bool* degenerate = nullptr) {
     double a = dot(d, d);
     double half_b = dot(d, o);
     double c = dot(o, o) - 1.0;
@@ -269,6 +296,7 @@ __device__ __forceinline__ bool sphere_candidate(D3 o, D3 d, double min_t, doubl
     if (disc < 0.0) return false;
     if (disc == 0.0) {
         t = -half_b * a;  // sic (:343-344): multiplied, and accepted with no range check
+        if (degenerate) *degenerate = true;
         return true;
     }
     double sq = sqrt(disc);

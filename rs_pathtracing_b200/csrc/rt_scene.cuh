@@ -2,6 +2,7 @@
 // one-step integrator shared by every kernel of the core.  FP64, no FMA contraction (see rt_math.cuh).
 #pragma once
 #include "rt_math.cuh"
+#include "rt_march.cuh"
 
 namespace rt {
 
@@ -27,11 +28,14 @@ struct DevScene {
     // analytic loop walk this list)
     int n_march;
     const int* march_index;
+    const double* march_G;      // [n_march] bound of |grad f| over the marching region (inf: never skip)
 };
 
 // optional work counters (rt_stats); enabled per launch by a template flag
 struct DevCounters {
     unsigned long long segments, shape_tests, cull_tests, march_steps, march_rays;
+    unsigned long long march_long_rays;  // marched rays that needed more than 2048 evaluations
+    unsigned long long march_max_evals;  // most evaluations any single marched ray needed
 };
 
 struct HitRec {  // RayHit, src/world/ray.rs:21-29
@@ -133,6 +137,111 @@ __device__ __forceinline__ void nearest_hit_brute(const DevScene& S, const doubl
     }
     if (COUNT) c.segments++;
     best_t = min_distance;
+    best_i = winner;
+}
+
+// The same nearest hit, reorganised (RT_ISECT_FAST and the wavefront renderer):
+//   1. the analytic shapes in index order with the shrinking max_t (identical arithmetic);
+//   2. the ray-marched shapes afterwards, skipped when their bounding chord starts behind the best
+//      hit so far, clipped two steps past it otherwise, and marched with exact skipping (rt_march.cuh).
+// Every candidate t is independent of max_t except for acceptance, so the sequential
+// loop's result is the lexicographic minimum of (t, -index); step 2 applies that rule explicitly.
+// The two inputs on which the sequential loop is NOT a pure arg-min — a Sphere hit through the
+// unchecked D == 0 branch and a NaN t — are detected ("degenerate") and replayed through
+// nearest_hit_brute.
+
+// step 1.  Returns true when the ray is degenerate.
+template <bool COUNT>
+__device__ __forceinline__ bool analytic_nearest(const DevScene& S, const double* s_inv, const uint8_t* s_kind, D3 ro,
+                                                 D3 rd, double min_t, double max_t, double& best, int& winner,
+                                                 DevCounters& c) {
+    best = max_t;
+    winner = -1;
+    bool degenerate = false;
+    const int n = S.n_shapes;
+    for (int i = 0; i < n; i++) {
+        const int kind = s_kind[i];
+        if (kind == RT_SHAPE_MARCH) continue;
+        const double* m = s_inv + 12 * i;
+        D3 o = xf_point(m, ro);
+        D3 d = xf_vector(m, rd);
+        if (COUNT) c.shape_tests++;
+        double t;
+        bool ok;
+        if (kind == RT_SHAPE_SPHERE) ok = sphere_candidate(o, d, min_t, best, t, &degenerate);
+        else if (kind == RT_SHAPE_CUBE) ok = cube_candidate(o, d, min_t, best, t);
+        else ok = rect_candidate(S.params + RT_SHAPE_PARAMS * i, o, d, min_t, best, t);
+        if (ok) {
+            if (t != t) degenerate = true;
+            best = t;
+            winner = i;
+        }
+    }
+    return degenerate;
+}
+
+// does marched shape number k (position in S.march_index) have to be marched for this ray, given the
+// best hit so far?  On true, o/d are the object-space ray and [start, end_c] the (clipped) chord.
+__device__ __forceinline__ bool march_needed(const DevScene& S, const double* m, const double* q, D3 ro, D3 rd,
+                                             double best, D3& o, D3& d, double& start, double& end_c) {
+    o = xf_point(m, ro);
+    d = xf_vector(m, rd);
+    double end;
+    if (!march_bound(q, o, d, start, end)) return false;
+    const double step = q[1];
+    end_c = end;
+    if (step > 0.0) {
+        if (!(start < best)) return false;           // every candidate lies beyond start
+        end_c = fmin(end, best + 2.0 * step);        // a hit found later than this cannot win
+    }
+    return true;
+}
+
+// step 2 for one marched shape.  Returns true when the ray turned out degenerate.
+template <bool COUNT>
+__device__ __forceinline__ bool march_shape_update(const DevScene& S, const double* s_inv, int k, D3 ro, D3 rd,
+                                                   double min_t, double max_t, double& best, int& winner,
+                                                   DevCounters& c) {
+    const int i = S.march_index[k];
+    const double* q = S.params + RT_SHAPE_PARAMS * i;
+    D3 o, d;
+    double start, end_c;
+    if (COUNT) c.shape_tests++;
+    if (!march_needed(S, s_inv + 12 * i, q, ro, rd, best, o, d, start, end_c)) return false;
+    if (COUNT) c.march_rays++;
+    unsigned long long ev = 0;
+    double t;
+    bool ok = march_candidate_skip(q, o, d, start, end_c, min_t, max_t, S.march_G[k], t, ev);
+    if (COUNT) {
+        c.march_steps += ev;
+        if (ev > 2048) c.march_long_rays++;
+        if (ev > c.march_max_evals) c.march_max_evals = ev;
+    }
+    if (ok) {
+        if (t != t) return true;
+        if (t < best || (t == best && i > winner)) {
+            best = t;
+            winner = i;
+        }
+    }
+    return false;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void nearest_hit_fast(const DevScene& S, const double* s_inv, const uint8_t* s_kind,
+                                                 D3 ro, D3 rd, double min_t, double max_t, double& best_t,
+                                                 int& best_i, DevCounters& c) {
+    double best;
+    int winner;
+    bool degenerate = analytic_nearest<COUNT>(S, s_inv, s_kind, ro, rd, min_t, max_t, best, winner, c);
+    for (int k = 0; k < S.n_march && !degenerate; k++)
+        degenerate = march_shape_update<COUNT>(S, s_inv, k, ro, rd, min_t, max_t, best, winner, c);
+    if (degenerate) {
+        nearest_hit_brute<COUNT>(S, s_inv, s_kind, ro, rd, min_t, max_t, best_t, best_i, c);
+        return;
+    }
+    if (COUNT) c.segments++;
+    best_t = best;
     best_i = winner;
 }
 

@@ -65,21 +65,27 @@ def scene_rays(sc, n, seed):
     return np.concatenate([prim, sec])
 
 
-def check_parity(sc, rays, t_min=0.001, t_max=math.inf, mode=rt.RT_ISECT_BRUTE):
+def check_parity(sc, rays, t_min=0.001, t_max=math.inf, modes=(rt.RT_ISECT_BRUTE, rt.RT_ISECT_FAST)):
+    """both kernels — the literal brute-force loop and the reorganised one (analytic shapes first,
+    exact-skip marching) — must reproduce the oracle"""
     osc = po.OracleScene(sc.desc())
     want = osc.intersect_batch(rays, t_min, t_max)
-    got = sc.closest_hit(rays, t_min, t_max, mode=mode)
+    for mode in modes:
+        _compare(sc.closest_hit(rays, t_min, t_max, mode=mode), want, len(rays), mode)
+    return want
+
+
+def _compare(got, want, n, mode):
     assert np.array_equal(got["index"], want["index"]), \
-        f"{(got['index'] != want['index']).sum()} of {len(rays)} nearest-hit indices differ"
+        f"mode {mode}: {(got['index'] != want['index']).sum()} of {n} nearest-hit indices differ"
     hit = want["index"] >= 0
     for k in ("t", "normal", "point"):
         g, w_ = got[k][hit], want[k][hit]
         same = (g == w_) | (np.isnan(g) & np.isnan(w_))
         rel = np.abs(g - w_) / np.maximum(np.abs(w_), 1e-300)
-        assert same.all(), f"{k}: {(~same).sum()} values differ, max rel err {np.nanmax(rel[~same]):.3e}"
+        assert same.all(), f"mode {mode} {k}: {(~same).sum()} values differ, max rel err {np.nanmax(rel[~same]):.3e}"
     assert np.array_equal(got["front"][hit], want["front"][hit])
     assert np.allclose(got["uv"][hit], want["uv"][hit], rtol=0, atol=1e-12, equal_nan=True)
-    return want
 
 
 def test_bench_trio_parity():
@@ -162,3 +168,72 @@ def test_later_shape_wins_ties():
     sc = rt.Scene.from_json(json.dumps(scene), add_random_spheres=False)
     want = check_parity(sc, bench_rays(2048, target_radius=0.8))
     assert set(np.unique(want["index"])) <= {-1, 2}
+
+
+SURFACES = {
+    "Heart": {"type": "Heart"},
+    "Sine": {"type": "Sine", "a": 0.7, "sphere_radius": 2.0},
+    "Star": {"type": "Star", "a": 1.3, "sphere_radius": 2.0},
+    "DupinCyclide": {"type": "DupinCyclide", "a": 1.11, "b": 0.99, "c": 0.5, "d": 0.1, "sphere_radius": 2.5},
+    "HuntsSurface": {"type": "HuntsSurface", "sphere_radius": 5.0},
+    "Cushion": {"type": "Cushion", "sphere_radius": 1.5},
+}
+
+
+@pytest.mark.parametrize("surface", list(SURFACES))
+@pytest.mark.parametrize("scale,rotate,step,depth", [
+    (1.0, [0.0, 0.0, 0.0], 0.01, 4),           # axis-aligned object space
+    (82.5, [-95.0, -18.0, 0.0], 0.01, 4),      # cornell_box.json's heart: ~24 000 steps per chord
+    (2.0, [0.0, -100.0, 0.0], 0.01, 4),        # dupin.json's transform
+    (1.0, [10.0, 20.0, 30.0], 0.003, 3),
+])
+def test_exact_skip_marching_is_bit_exact(surface, scale, rotate, step, depth):
+    """the exact-skip marcher (binade arithmetic progression + derivative bound) must return the very
+    t the plain loop returns, for every implicit surface, at object scales from 1 to 82.5"""
+    import json
+    scene = json.loads(json.dumps(TRIO))
+    R = 2.6 * scale if surface != "HuntsSurface" else 5.5 * scale
+    scene["shapes"] = [
+        {"type": "BruteForsableShape", "shape": SURFACES[surface], "step": step, "depth": depth, "material": "M",
+         "transform": {"translate": [3.0, -2.0, 5.0], "rotate": rotate, "scale": [scale] * 3}},
+        # a wall behind half of the object: exercises the clipped end and the `start < best` pruning
+        {"type": "Rectangle", "x0": -1e4, "y0": -1e4, "x1": 1e4, "y1": 1e4, "material": "M",
+         "transform": {"translate": [3.0, -2.0, 5.0 + 0.3 * R], "rotate": [0, 0, 0], "scale": [1, 1, 1]}},
+    ]
+    sc = rt.Scene.from_json(json.dumps(scene), add_random_spheres=False)
+    rng = np.random.default_rng(hash(surface) % 1000 + int(scale))
+    centre = np.array([3.0, -2.0, 5.0])
+    n = 3000 if scale > 10 else 6000
+    def ball(m, r):
+        v = rng.normal(size=(m, 3))
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        return v * r * rng.uniform(0, 1, (m, 1)) ** (1 / 3)
+    o = centre + ball(n, 4.0 * R)                       # outside and inside the bound
+    tgt = centre + ball(n, 0.9 * R)
+    rays = rt.make_rays(o, tgt - o)
+    # axis-aligned rays through the centre region: some step*dir components are exactly zero
+    ax = []
+    for a in range(3):
+        for s in (-1.0, 1.0):
+            for off in rng.uniform(-0.5, 0.5, (8, 3)) * scale:
+                d = np.zeros(3); d[a] = s
+                oo = centre + off - d * 3.0 * R
+                oo[(a + 1) % 3] = centre[(a + 1) % 3]     # exactly on the object's coordinate plane
+                ax.append(np.concatenate([oo, d]))
+    rays = np.concatenate([rays, np.array(ax)])
+    want = check_parity(sc, rays, modes=(rt.RT_ISECT_FAST,))
+    assert (want["index"] == 0).mean() > 0.05, "the test rays must actually hit the surface"
+
+
+def test_exact_skip_skips(monkeypatch):
+    """the skipping marcher evaluates the polynomial far fewer times than the plain loop"""
+    sc = rt.Scene.from_file(scene_path("cornell_box.json"), random_spheres_seed=1)
+    rays = scene_rays(sc, 4096, seed=11)
+    sc.set_counters(True)
+    sc.reset_stats()
+    sc.closest_hit(rays, mode=rt.RT_ISECT_BRUTE, want=("index",))
+    plain = sc.stats().march_steps
+    sc.reset_stats()
+    sc.closest_hit(rays, mode=rt.RT_ISECT_FAST, want=("index",))
+    skip = sc.stats().march_steps
+    assert plain > 500_000 and skip * 10 < plain, (plain, skip)

@@ -196,3 +196,34 @@ def test_shard_float4_count():
     assert [lib.rt_shard_float4_count(C.byref(p), s) for s in range(4)] == [3 * 1024] * 4
     p.shard_count = 5                                            # 12 tiles over 5 shards: 3,3,2,2,2
     assert [lib.rt_shard_float4_count(C.byref(p), s) for s in range(5)] == [3072, 3072, 2048, 2048, 2048]
+
+
+def test_march_region_bounds_dominate_sampled_derivatives():
+    """the interval bounds behind the exact-skip marcher (csrc/march_bounds.hpp): G and H must dominate
+    the gradient norm and the second directional derivative of every surface polynomial anywhere in its
+    marching region"""
+    lib = _ffi.core()
+    orc = po.lib()
+    rng = np.random.default_rng(0)
+    cases = {0: [0, 0.01, 4, 0, 0, 0, 0, 0], 1: [1, 0.01, 4, 0.7, 0, 0, 0, 2.0], 2: [2, 0.01, 4, 1.3, 0, 0, 0, 2.0],
+             3: [3, 0.01, 4, 1.11, 0.99, 0.5, 0.1, 2.5], 4: [4, 0.01, 4, 0, 0, 0, 0, 5.0], 5: [5, 0.01, 4, 0, 0, 0, 0, 1.5]}
+    for k, q in cases.items():
+        qa = (C.c_double * 8)(*q)
+        G, H = C.c_double(), C.c_double()
+        assert lib.rt_march_region_bounds(qa, C.byref(G), C.byref(H)) == 0
+        G, H = G.value, H.value
+        assert math.isfinite(H) and H > 0 and math.isfinite(G) and G > 0
+        radii = np.array([1.45, 1.45 / 2.05, 1.45]) if k == 0 else np.array([q[7]] * 3)
+        f = lambda p: orc.orc_surface_func(qa, po.Vec3(*p))
+        worst2 = worst1 = 0.0
+        for _ in range(400):
+            v = rng.normal(size=3); v /= np.linalg.norm(v)
+            p = v * rng.uniform(0, 1) ** (1 / 3) * radii * 1.05
+            u = rng.normal(size=3); u /= np.linalg.norm(u)
+            h = 1e-4 * radii.min()
+            worst2 = max(worst2, abs((f(p + h * u) - 2 * f(p) + f(p - h * u)) / (h * h)))
+            grad = np.array([(f(p + h * e) - f(p - h * e)) / (2 * h) for e in np.eye(3)])
+            worst1 = max(worst1, np.linalg.norm(grad))
+        assert worst2 <= H * (1 + 1e-6) + 1e-6, (k, worst2, H)
+        assert worst1 <= G * (1 + 1e-6) + 1e-6, (k, worst1, G)
+        assert worst2 > H / 200 and worst1 > G / 200, (k, worst1, G, worst2, H)   # and not absurdly loose

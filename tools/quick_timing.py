@@ -22,4 +22,4 @@ for name, w, h, spp in [("spheres.json", 640, 480, 16), ("cornell_box.json", 256
         st = sc.stats()
         print(f"{name} {w}x{h}x{spp} counters={rep}: wall {dt*1e3:.1f} ms, device {st.last_frame_ms:.1f} ms, "
               f"{w*h*spp/st.last_frame_ms/1e3:.2f} Mpaths/s, launches {st.kernel_launches}, seg {st.segments}, "
-              f"tests {st.shape_tests}, march_steps {st.march_steps}")
+              f"tests {st.shape_tests}, march_steps {st.march_steps}, march_rays {st.march_rays}, long {st.march_long_rays}, max {st.march_max_evals}")
