@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 1
+#define RT_B200_ABI_VERSION 2
 
 typedef enum rt_status {
     RT_OK = 0,
@@ -167,8 +167,10 @@ void rt_scene_destroy(rt_scene* scene);
 enum {
     RT_ISECT_BRUTE = 0,   /* one thread per ray walks the whole shape list in index order: the
                              literal restatement of ShapeCollection::ray_intersect             */
-    RT_ISECT_FAST = 1     /* conservative culling + exact FP64 test on the survivors; provably the
+    RT_ISECT_FAST = 1,    /* conservative culling + exact FP64 test on the survivors; provably the
                              same result as RT_ISECT_BRUTE (degenerate rays fall back to it)     */
+    RT_ISECT_VERIFY = 2   /* self-check: runs FAST and BRUTE on every ray, returns BRUTE's result and
+                             counts disagreements + falsely culled (ray, shape) pairs in rt_stats   */
 };
 
 /* Host buffers in, host buffers out.  Any output pointer may be NULL.
@@ -260,12 +262,21 @@ typedef struct rt_stats {
     uint64_t march_max_evals;   /* most evaluations a single marched ray needed                 */
     double last_frame_ms;       /* device time of the last completed frame (CUDA events)        */
     double last_intersect_ms;   /* device time of the last rt_intersect_batch kernel            */
+    uint64_t verify_rays;        /* RT_ISECT_VERIFY: rays whose FAST result differs from BRUTE   */
+    uint64_t verify_false_culls; /* RT_ISECT_VERIFY: culled (ray, shape) pairs the exact test hits */
+    /* device time per kernel class since the last reset, summed over launches (CUDA event pairs on
+     * the library's stream; only while rt_set_kernel_timing is on) and the launches they cover */
+    double ms_raygen, ms_extend, ms_march, ms_shade, ms_resolve;
+    uint64_t launches_extend, launches_march, launches_shade;
 } rt_stats;
 int rt_get_stats(rt_scene* scene, rt_stats* out);
 int rt_reset_stats(rt_scene* scene);
 /* enable (1) / disable (0) the per-kernel work counters above (segments..march_rays); counting
  * costs a few atomics per block and is off by default.  kernel_launches / *_ms are always on. */
 int rt_set_counters(rt_scene* scene, int enabled);
+/* enable (1) / disable (0) per-kernel device timing (rt_stats.ms_*): one CUDA event pair around every
+ * launch of the following frames.  Not allowed while a frame is in flight. */
+int rt_set_kernel_timing(rt_scene* scene, int enabled);
 
 /* Host-only helper behind the exact-skip marcher: rigorous interval bounds G >= sup |grad f| and
  * H >= sup |u^T Hess f u| of a ray-marched surface (params8 = the shape's params row) over its marching

@@ -7,12 +7,12 @@ face with the reference's names.  Importing this package requires the native lib
 """
 from . import _ffi
 from ._ffi import (Camera, ImageParams, Ray, RenderParams, Stats, Vec3, NativeLibraryMissing,
-                   RT_ISECT_BRUTE, RT_ISECT_FAST)
+                   RT_ISECT_BRUTE, RT_ISECT_FAST, RT_ISECT_VERIFY)
 from .api import (GpuRenderer, RtError, Scene, camera_new, device_count, make_rays, measure_peaks,
                   tonemap_rgba8)
 
 __all__ = [
     "Camera", "ImageParams", "Ray", "RenderParams", "Stats", "Vec3", "NativeLibraryMissing",
-    "RT_ISECT_BRUTE", "RT_ISECT_FAST", "GpuRenderer", "RtError", "Scene", "camera_new",
+    "RT_ISECT_BRUTE", "RT_ISECT_FAST", "RT_ISECT_VERIFY", "GpuRenderer", "RtError", "Scene", "camera_new",
     "device_count", "make_rays", "measure_peaks", "tonemap_rgba8",
 ]

@@ -12,7 +12,7 @@ HOST_SO = os.path.join(HERE, "librt_b200_host.so")
 
 RT_OK = 0
 RT_ERR_INVALID, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_STATE, RT_ERR_NOMEM = -1, -2, -3, -4, -5
-RT_ISECT_BRUTE, RT_ISECT_FAST = 0, 1
+RT_ISECT_BRUTE, RT_ISECT_FAST, RT_ISECT_VERIFY = 0, 1, 2
 RT_SHAPE_SPHERE, RT_SHAPE_CUBE, RT_SHAPE_RECTANGLE, RT_SHAPE_MARCH = 0, 1, 2, 3
 RT_SURF_HEART, RT_SURF_SINE, RT_SURF_STAR, RT_SURF_DUPIN, RT_SURF_HUNTS, RT_SURF_CUSHION = range(6)
 RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT_EMPTY = range(5)
@@ -100,6 +100,16 @@ class Stats(C.Structure):
         ("march_max_evals", C.c_uint64),
         ("last_frame_ms", C.c_double),
         ("last_intersect_ms", C.c_double),
+        ("verify_rays", C.c_uint64),
+        ("verify_false_culls", C.c_uint64),
+        ("ms_raygen", C.c_double),
+        ("ms_extend", C.c_double),
+        ("ms_march", C.c_double),
+        ("ms_shade", C.c_double),
+        ("ms_resolve", C.c_double),
+        ("launches_extend", C.c_uint64),
+        ("launches_march", C.c_uint64),
+        ("launches_shade", C.c_uint64),
     ]
 
 
@@ -129,6 +139,7 @@ CORE_SYMBOLS = {
     "rt_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
     "rt_reset_stats": (C.c_int, [C.c_void_p]),
     "rt_set_counters": (C.c_int, [C.c_void_p, C.c_int]),
+    "rt_set_kernel_timing": (C.c_int, [C.c_void_p, C.c_int]),
     "rt_march_region_bounds": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rt_measure_peaks": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }

@@ -194,6 +194,9 @@ class Scene:
     def set_counters(self, enabled: bool, device: int = 0) -> None:
         _check(_ffi.core().rt_set_counters(self.device_scene(device), int(enabled)))
 
+    def set_kernel_timing(self, enabled: bool, device: int = 0) -> None:
+        _check(_ffi.core().rt_set_kernel_timing(self.device_scene(device), int(enabled)))
+
 
 class GpuRenderer:
     """Drop-in for step_by_step::ThreadPoolRenderer (src/renderer/step_by_step.rs:37) implementing the

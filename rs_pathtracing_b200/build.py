@@ -24,6 +24,7 @@ CORE_HEADERS = [
     os.path.join(CSRC, "rt_math.cuh"),
     os.path.join(CSRC, "rt_scene.cuh"),
     os.path.join(CSRC, "rt_march.cuh"),
+    os.path.join(CSRC, "rt_cull.cuh"),
     os.path.join(CSRC, "march_bounds.hpp"),
     os.path.join(ROOT, "include", "rt_b200.h"),
 ]

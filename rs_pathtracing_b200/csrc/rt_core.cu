@@ -91,26 +91,18 @@ struct RayCasterDev {  // MultisamplerRayCaster, src/camera/ray_caster.rs:17-48
 };
 
 // ------------------------------------------------------------------------------------------------
-// shared-memory staging of the shape list (inverse rows + kind): every lane of a warp reads the
-// same shape at the same time, so each read is a conflict-free broadcast
+// shared-memory staging of the cull table (16 B per shape + one valid word per 32 shapes): every lane
+// of a warp reads the same entry at the same time, so each read is a conflict-free broadcast.  The
+// FP64 inverse rows are only needed for the few survivors of the cull and stay in global memory / L1.
 // ------------------------------------------------------------------------------------------------
-struct Staged {
-    const double* inv;
-    const uint8_t* kind;
-};
 __device__ __forceinline__ Staged stage_scene(const DevScene& S, bool use_smem) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    if (!use_smem) return Staged{S.inv, S.kind};
-    double* s_inv = reinterpret_cast<double*>(smem_raw);
-    uint8_t* s_kind = reinterpret_cast<uint8_t*>(s_inv + (size_t)12 * S.n_shapes);
-    const int n12 = 12 * S.n_shapes;
-    // 16-byte vector copies: rows are 96 B, cudaMalloc aligns the base
-    const double2* src = reinterpret_cast<const double2*>(S.inv);
-    double2* dst = reinterpret_cast<double2*>(s_inv);
-    for (int k = threadIdx.x; k < n12 / 2; k += blockDim.x) dst[k] = src[k];
-    for (int k = threadIdx.x; k < S.n_shapes; k += blockDim.x) s_kind[k] = S.kind[k];
+    if (!use_smem) return Staged{false};
+    float4* s_cull = reinterpret_cast<float4*>(rt_smem_raw);
+    uint32_t* s_valid = reinterpret_cast<uint32_t*>(rt_smem_raw + (size_t)512 * S.n_chunks);
+    for (int k = threadIdx.x; k < 32 * S.n_chunks; k += blockDim.x) s_cull[k] = S.cull[k];
+    for (int k = threadIdx.x; k < S.n_chunks; k += blockDim.x) s_valid[k] = S.valid[k];
     __syncthreads();
-    return Staged{s_inv, s_kind};
+    return Staged{true};
 }
 
 __device__ __forceinline__ void flush_counters(const DevCounters& c, DevCounters* g) {
@@ -133,27 +125,59 @@ __device__ __forceinline__ void flush_counters(const DevCounters& c, DevCounters
         atomicAdd(&g->march_long_rays, v[5]);
         atomicMax(&g->march_max_evals, mx);
     }
+    if (c.verify_rays) atomicAdd(&g->verify_rays, c.verify_rays);
+    if (c.verify_false_culls) atomicAdd(&g->verify_false_culls, c.verify_false_culls);
 }
 
 // ------------------------------------------------------------------------------------------------
 // K2/K3: batched nearest hit
 // ------------------------------------------------------------------------------------------------
-template <bool COUNT, bool FAST>
+// RT_ISECT_VERIFY support: every analytic (ray, shape) pair the cull rejects is tested exactly with
+// max_t = +inf; a hit (or a degenerate branch) there is a false cull.
+__device__ __noinline__ unsigned long long count_false_culls(const DevScene& S, D3 ro, D3 rd, double min_t) {
+    const CullRay cr = make_cull_ray(ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
+    unsigned long long bad = 0;
+    for (int i = 0; i < S.n_shapes; i++) {
+        if (!((S.valid[i >> 5] >> (i & 31)) & 1u)) continue;
+        if (cull_pass(cr, S.cull[i])) continue;
+        double best = INFINITY;
+        int winner = -1;
+        bool degenerate = false;
+        DevCounters cc = {};
+        analytic_test<false>(S, i, ro, rd, min_t, best, winner, degenerate, cc);
+        if (winner >= 0 || degenerate) bad++;
+    }
+    return bad;
+}
+
+// MODE: RT_ISECT_BRUTE / RT_ISECT_FAST / RT_ISECT_VERIFY
+template <bool COUNT, int MODE>
 __global__ void __launch_bounds__(256)
 k_intersect_batch(DevScene S, bool use_smem, const rt_ray* __restrict__ rays, unsigned long long n, double t_min,
                   double t_max, int32_t* __restrict__ shape_index, double* __restrict__ t_out,
                   rt_vec3* __restrict__ normal, rt_vec3* __restrict__ point, double* __restrict__ uv,
                   uint8_t* __restrict__ front_face, DevCounters* g_counters) {
     Staged st = stage_scene(S, use_smem);
-    DevCounters c = {0, 0, 0, 0, 0, 0, 0};
+    DevCounters c = {};
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         rt_ray r = rays[i];
         D3 ro = mk(r.origin.x, r.origin.y, r.origin.z), rd = mk(r.direction.x, r.direction.y, r.direction.z);
         double bt;
         int bi;
-        if (FAST) nearest_hit_fast<COUNT>(S, st.inv, st.kind, ro, rd, t_min, t_max, bt, bi, c);
-        else nearest_hit_brute<COUNT>(S, st.inv, st.kind, ro, rd, t_min, t_max, bt, bi, c);
+        if (MODE == RT_ISECT_BRUTE) {
+            nearest_hit_brute<COUNT>(S, ro, rd, t_min, t_max, bt, bi, c);
+        } else if (MODE == RT_ISECT_FAST) {
+            nearest_hit_fast<COUNT>(S, st, ro, rd, t_min, t_max, bt, bi, c);
+        } else {
+            double ft;
+            int fi;
+            DevCounters cc = {};
+            nearest_hit_fast<false>(S, st, ro, rd, t_min, t_max, ft, fi, cc);
+            nearest_hit_brute<COUNT>(S, ro, rd, t_min, t_max, bt, bi, c);
+            if (fi != bi || (bi >= 0 && __double_as_longlong(ft) != __double_as_longlong(bt))) c.verify_rays++;
+            c.verify_false_culls += count_false_culls(S, ro, rd, t_min);
+        }
         if (shape_index) shape_index[i] = bi;
         if (bi < 0) {
             if (t_out) t_out[i] = 0.0;
@@ -173,7 +197,7 @@ k_intersect_batch(DevScene S, bool use_smem, const rt_ray* __restrict__ rays, un
             if (front_face) front_face[i] = h.front ? 1 : 0;
         }
     }
-    if (COUNT) flush_counters(c, g_counters);
+    if (COUNT || MODE == RT_ISECT_VERIFY) flush_counters(c, g_counters);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -241,7 +265,7 @@ k_bounce(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
          uint32_t* count_out, uint32_t level, uint32_t max_depth, ShardMap map, unsigned long long first_owned,
          uint32_t spp, uint32_t k0, uint32_t k1, float4* __restrict__ radiance, DevCounters* g_counters) {
     Staged st = stage_scene(S, use_smem);
-    DevCounters c = {0, 0, 0, 0, 0, 0, 0};
+    DevCounters c = {};
     const uint32_t n = *count_in;
     const uint32_t n_round = (n + 31u) & ~31u;
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -256,7 +280,7 @@ k_bounce(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
             pid = in.pid[i];
             double bt;
             int bi;
-            nearest_hit_fast<COUNT>(S, st.inv, st.kind, ro, rd, 0.001, INFINITY, bt, bi, c);  // mod.rs:24
+            nearest_hit_fast<COUNT>(S, st, ro, rd, 0.001, INFINITY, bt, bi, c);  // mod.rs:24
             D3 L = mk(0.0, 0.0, 0.0);
             if (bi < 0) {
                 L = hadamard(beta, sky(rd));  // :41-43
@@ -310,11 +334,11 @@ struct HitQueue {
 #define RT_HIT_REPLAY (-2)
 
 template <bool COUNT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ count_in, HitQueue hq,
          uint32_t* march_count, DevCounters* g_counters) {
     Staged st = stage_scene(S, use_smem);
-    DevCounters c = {0, 0, 0, 0, 0, 0, 0};
+    DevCounters c = {};
     const uint32_t n = *count_in;
     const uint32_t n_round = (n + 31u) & ~31u;
     const uint32_t stride = gridDim.x * blockDim.x;
@@ -325,7 +349,7 @@ k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
             D3 rd = mk(in.dx[i], in.dy[i], in.dz[i]);
             double best;
             int winner;
-            bool degenerate = analytic_nearest<COUNT>(S, st.inv, st.kind, ro, rd, 0.001, INFINITY, best, winner, c);
+            bool degenerate = analytic_nearest<COUNT>(S, st, ro, rd, 0.001, INFINITY, best, winner, c);
             if (degenerate) {
                 winner = RT_HIT_REPLAY;
                 mask = 0xffffffffu;
@@ -334,7 +358,7 @@ k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
                     const int si = S.march_index[k];
                     D3 o, d;
                     double start, end_c;
-                    if (march_needed(S, st.inv + 12 * si, S.params + RT_SHAPE_PARAMS * si, ro, rd, best, o, d, start, end_c))
+                    if (march_needed(S, S.inv + 12 * si, S.params + RT_SHAPE_PARAMS * si, ro, rd, best, o, d, start, end_c))
                         mask |= 1u << k;
                 }
                 if (COUNT) c.shape_tests += S.n_march;
@@ -355,7 +379,7 @@ k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
 template <bool COUNT>
 __global__ void __launch_bounds__(128)
 k_march(DevScene S, PathQueue in, HitQueue hq, const uint32_t* __restrict__ march_count, DevCounters* g_counters) {
-    DevCounters c = {0, 0, 0, 0, 0, 0, 0};
+    DevCounters c = {};
     const uint32_t n = *march_count;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
@@ -367,7 +391,7 @@ k_march(DevScene S, PathQueue in, HitQueue hq, const uint32_t* __restrict__ marc
         int winner = hq.index[i];
         bool degenerate = winner == RT_HIT_REPLAY;
         if (!degenerate) {
-            DevCounters cc = {0, 0, 0, 0, 0, 0, 0};
+            DevCounters cc = {};
             while (mask && !degenerate) {
                 int k = __ffs(mask) - 1;
                 mask &= mask - 1;
@@ -379,8 +403,8 @@ k_march(DevScene S, PathQueue in, HitQueue hq, const uint32_t* __restrict__ marc
             }
         }
         if (degenerate) {
-            DevCounters cc = {0, 0, 0, 0, 0, 0, 0};
-            nearest_hit_brute<false>(S, S.inv, S.kind, ro, rd, 0.001, INFINITY, best, winner, cc);
+            DevCounters cc = {};
+            nearest_hit_brute<false>(S, ro, rd, 0.001, INFINITY, best, winner, cc);
         }
         hq.t[i] = best;
         hq.index[i] = winner;
@@ -526,6 +550,8 @@ __global__ void __launch_bounds__(256) k_fma_peak(T* out, int iters, T a, T b) {
 // ------------------------------------------------------------------------------------------------
 #define RT_MAX_LEVELS 64  // counters per batch: level 0 .. max_depth + 1
 
+enum { RT_KCLASS_RAYGEN = 0, RT_KCLASS_EXTEND, RT_KCLASS_MARCH, RT_KCLASS_SHADE, RT_KCLASS_RESOLVE, RT_KCLASS_COUNT };
+
 struct Batch {
     uint64_t first_owned;
     uint32_t n_pixels;
@@ -549,6 +575,15 @@ struct rt_scene {
     uint64_t launches = 0, paths = 0;
     double last_frame_ms = 0.0, last_intersect_ms = 0.0;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+    // per-kernel-class device time (rt_set_kernel_timing): event pairs around every launch of a frame,
+    // resolved when the frame completes
+    bool ktiming = false;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Span { int cls; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    double ms_cls[RT_KCLASS_COUNT] = {0, 0, 0, 0, 0};
+    uint64_t n_cls[RT_KCLASS_COUNT] = {0, 0, 0, 0, 0};
 
     // render state
     bool rendering = false, frame_complete = false;
@@ -694,15 +729,34 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
     }
     if ((rc = upload(sc, march_G.data(), march_G.size(), &sc->ds.march_G)) != RT_OK) return bail(rc);
 
-    // shared-memory staging: 96 B of inverse rows + 1 B kind per shape
-    sc->smem_bytes = (size_t)n * 12 * sizeof(double) + ((n + 15) & ~15u);
+    // conservative cull table (rt_cull.cuh): one float4 per shape padded to whole chunks of 32, one
+    // valid word per chunk (bit set = analytic shape that takes part in the loop)
+    const uint32_t n_chunks = (n + 31) / 32;
+    sc->ds.n_chunks = (int)n_chunks;
+    {
+        std::vector<float4> cull((size_t)n_chunks * 32, make_float4(0.f, 0.f, 0.f, -INFINITY));
+        std::vector<uint32_t> valid(n_chunks, 0u);
+        const bool no_cull = getenv("RT_B200_NO_CULL") != nullptr;
+        for (uint32_t i = 0; i < n; i++) {
+            cull[i] = cull_entry(d->inverse + (size_t)12 * i, d->kind[i]);
+            if (d->kind[i] != RT_SHAPE_MARCH) {
+                valid[i >> 5] |= 1u << (i & 31);
+                if (no_cull) cull[i].w = INFINITY;
+            }
+        }
+        if ((rc = upload(sc, cull.data(), cull.size(), &sc->ds.cull)) != RT_OK) return bail(rc);
+        if ((rc = upload(sc, valid.data(), valid.size(), &sc->ds.valid)) != RT_OK) return bail(rc);
+    }
+    // shared-memory staging: 16 B per (padded) shape + 4 B per chunk
+    sc->smem_bytes = (size_t)n_chunks * 32 * sizeof(float4) + (((size_t)n_chunks * 4 + 15) & ~(size_t)15);
     sc->use_smem = n > 0 && sc->smem_bytes <= sc->smem_optin;
     if (!sc->use_smem) sc->smem_bytes = 0;
     if (sc->smem_bytes > 48 * 1024) {
-        cudaFuncSetAttribute(k_intersect_batch<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
-        cudaFuncSetAttribute(k_intersect_batch<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
-        cudaFuncSetAttribute(k_intersect_batch<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
-        cudaFuncSetAttribute(k_intersect_batch<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+        cudaFuncSetAttribute(k_intersect_batch<false, RT_ISECT_BRUTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+        cudaFuncSetAttribute(k_intersect_batch<true, RT_ISECT_BRUTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+        cudaFuncSetAttribute(k_intersect_batch<false, RT_ISECT_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+        cudaFuncSetAttribute(k_intersect_batch<true, RT_ISECT_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+        cudaFuncSetAttribute(k_intersect_batch<false, RT_ISECT_VERIFY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
         cudaFuncSetAttribute(k_bounce<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
         cudaFuncSetAttribute(k_bounce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
         cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
@@ -751,6 +805,7 @@ void rt_scene_destroy(rt_scene* sc) {
     free_render_buffers(sc);
     for (void* p : sc->allocs) cudaFree(p);
     cudaFree(sc->d_counters);
+    for (cudaEvent_t e : sc->ev_pool) cudaEventDestroy(e);
     if (sc->ev_a) cudaEventDestroy(sc->ev_a);
     if (sc->ev_b) cudaEventDestroy(sc->ev_b);
     if (sc->ev_frame_start) cudaEventDestroy(sc->ev_frame_start);
@@ -765,21 +820,22 @@ int rt_intersect_batch_device(rt_scene* sc, const rt_ray* d_rays, uint64_t n, do
                               int32_t* d_idx, double* d_t, rt_vec3* d_normal, rt_vec3* d_point, double* d_uv,
                               uint8_t* d_ff, void* stream) {
     if (!sc) return fail(RT_ERR_INVALID, "null scene");
-    if (mode != RT_ISECT_BRUTE && mode != RT_ISECT_FAST) return fail(RT_ERR_INVALID, "unknown intersect mode");
+    if (mode != RT_ISECT_BRUTE && mode != RT_ISECT_FAST && mode != RT_ISECT_VERIFY) return fail(RT_ERR_INVALID, "unknown intersect mode");
     if (n == 0) return RT_OK;
     if (!d_rays) return fail(RT_ERR_INVALID, "null rays");
     CU(cudaSetDevice(sc->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : sc->stream;
     uint64_t want = (n + 255) / 256;
     int grid = (int)std::min<uint64_t>(want, (uint64_t)sc->grid);
-#define RT_LAUNCH_ISECT(C_, F_)                                                                                  \
-    k_intersect_batch<C_, F_><<<grid, 256, sc->smem_bytes, st>>>(sc->ds, sc->use_smem, d_rays, n, t_min, t_max, d_idx, \
+#define RT_LAUNCH_ISECT(C_, M_)                                                                                  \
+    k_intersect_batch<C_, M_><<<grid, 256, sc->smem_bytes, st>>>(sc->ds, sc->use_smem, d_rays, n, t_min, t_max, d_idx, \
                                                                  d_t, d_normal, d_point, d_uv, d_ff, sc->d_counters)
-    const bool fast = mode == RT_ISECT_FAST;
-    if (sc->counters_on) {
-        if (fast) RT_LAUNCH_ISECT(true, true); else RT_LAUNCH_ISECT(true, false);
+    if (mode == RT_ISECT_VERIFY) {
+        RT_LAUNCH_ISECT(false, RT_ISECT_VERIFY);
+    } else if (sc->counters_on) {
+        if (mode == RT_ISECT_FAST) RT_LAUNCH_ISECT(true, RT_ISECT_FAST); else RT_LAUNCH_ISECT(true, RT_ISECT_BRUTE);
     } else {
-        if (fast) RT_LAUNCH_ISECT(false, true); else RT_LAUNCH_ISECT(false, false);
+        if (mode == RT_ISECT_FAST) RT_LAUNCH_ISECT(false, RT_ISECT_FAST); else RT_LAUNCH_ISECT(false, RT_ISECT_BRUTE);
     }
 #undef RT_LAUNCH_ISECT
     sc->launches++;
@@ -862,6 +918,44 @@ static RayCasterDev make_raycaster(const rt_camera& cam, rt_image_params img) {
     return rc;
 }
 
+static cudaEvent_t pool_event(rt_scene* sc) {
+    if (sc->ev_used == sc->ev_pool.size()) {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        sc->ev_pool.push_back(e);
+    }
+    return sc->ev_pool[sc->ev_used++];
+}
+struct KernelSpan {  // RAII: records an event pair around one launch when kernel timing is on
+    rt_scene* sc;
+    int cls;
+    cudaEvent_t a = nullptr;
+    KernelSpan(rt_scene* s, int c) : sc(s), cls(c) {
+        sc->launches++;
+        if (!sc->ktiming) return;
+        a = pool_event(sc);
+        cudaEventRecord(a, sc->stream);
+    }
+    ~KernelSpan() {
+        if (!a) return;
+        cudaEvent_t b = pool_event(sc);
+        cudaEventRecord(b, sc->stream);
+        sc->spans.push_back({cls, a, b});
+    }
+};
+static void resolve_spans(rt_scene* sc) {  // the stream must have passed every recorded event
+    for (auto& sp : sc->spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+            sc->ms_cls[sp.cls] += ms;
+            sc->n_cls[sp.cls]++;
+        }
+    }
+    cudaGetLastError();
+    sc->spans.clear();
+    sc->ev_used = 0;
+}
+
 static int alloc_queue(rt_scene* sc, PathQueue& q, uint64_t cap) {
     double** d[9] = {&q.ox, &q.oy, &q.oz, &q.dx, &q.dy, &q.dz, &q.bx, &q.by, &q.bz};
     for (int k = 0; k < 9; k++) {
@@ -888,6 +982,7 @@ static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long 
         uint32_t* cnt_out = sc->d_counts + level + 1;
         uint32_t* mcount = sc->d_counts + RT_MAX_LEVELS + level;
         if (!sc->wavefront) {
+            KernelSpan span(sc, RT_KCLASS_EXTEND);
             if (sc->counters_on)
                 k_bounce<true><<<sc->grid, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, out, cnt_out, level,
                                                                               max_depth, sc->map, first_owned, spp, k0, k1,
@@ -896,28 +991,31 @@ static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long 
                 k_bounce<false><<<sc->grid, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, out, cnt_out, level,
                                                                                max_depth, sc->map, first_owned, spp, k0, k1,
                                                                                sc->d_radiance, sc->d_counters);
-            sc->launches++;
             continue;
         }
-        if (sc->counters_on)
-            k_extend<true><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, sc->d_counters);
-        else
-            k_extend<false><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, sc->d_counters);
-        sc->launches++;
+        {
+            KernelSpan span(sc, RT_KCLASS_EXTEND);
+            if (sc->counters_on)
+                k_extend<true><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, sc->d_counters);
+            else
+                k_extend<false><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, sc->d_counters);
+        }
         if (sc->ds.n_march > 0) {
+            KernelSpan span(sc, RT_KCLASS_MARCH);
             if (sc->counters_on)
                 k_march<true><<<sc->grid_march, 128, 0, sc->stream>>>(sc->ds, in, sc->hq, mcount, sc->d_counters);
             else
                 k_march<false><<<sc->grid_march, 128, 0, sc->stream>>>(sc->ds, in, sc->hq, mcount, sc->d_counters);
-            sc->launches++;
         }
-        if (sc->counters_on)
-            k_shade<true><<<sc->grid_shade, 256, 0, sc->stream>>>(sc->ds, in, cnt_in, sc->hq, out, cnt_out, level, max_depth, sc->map,
-                                                                  first_owned, spp, k0, k1, sc->d_radiance);
-        else
-            k_shade<false><<<sc->grid_shade, 256, 0, sc->stream>>>(sc->ds, in, cnt_in, sc->hq, out, cnt_out, level, max_depth, sc->map,
-                                                                   first_owned, spp, k0, k1, sc->d_radiance);
-        sc->launches++;
+        {
+            KernelSpan span(sc, RT_KCLASS_SHADE);
+            if (sc->counters_on)
+                k_shade<true><<<sc->grid_shade, 256, 0, sc->stream>>>(sc->ds, in, cnt_in, sc->hq, out, cnt_out, level, max_depth, sc->map,
+                                                                      first_owned, spp, k0, k1, sc->d_radiance);
+            else
+                k_shade<false><<<sc->grid_shade, 256, 0, sc->stream>>>(sc->ds, in, cnt_in, sc->hq, out, cnt_out, level, max_depth, sc->map,
+                                                                       first_owned, spp, k0, k1, sc->d_radiance);
+        }
     }
 }
 
@@ -977,6 +1075,8 @@ int rt_render_start(rt_scene* sc, const rt_camera* cam, const rt_render_params* 
     for (Batch& b : sc->batches) cudaEventDestroy(b.done);
     sc->batches.clear();
     sc->delivered = 0;
+    sc->spans.clear();
+    sc->ev_used = 0;
 
     RayCasterDev rcd = make_raycaster(*cam, p->image);
     uint32_t k0 = (uint32_t)p->seed, k1 = (uint32_t)(p->seed >> 32);
@@ -984,11 +1084,15 @@ int rt_render_start(rt_scene* sc, const rt_camera* cam, const rt_render_params* 
     for (uint64_t first = 0; first < sc->owned_pixels; first += px_per_batch) {
         uint32_t npx = (uint32_t)std::min<uint64_t>(px_per_batch, sc->owned_pixels - first);
         CU(cudaMemsetAsync(sc->d_counts, 0, 2 * RT_MAX_LEVELS * sizeof(uint32_t), sc->stream));
-        k_raygen<<<sc->grid, 256, 0, sc->stream>>>(rcd, sc->map, first, npx, spp, k0, k1, sc->q[0], sc->d_counts, sc->d_radiance);
-        sc->launches++;
+        {
+            KernelSpan span(sc, RT_KCLASS_RAYGEN);
+            k_raygen<<<sc->grid, 256, 0, sc->stream>>>(rcd, sc->map, first, npx, spp, k0, k1, sc->q[0], sc->d_counts, sc->d_radiance);
+        }
         launch_bounces(sc, p->max_depth, first, spp, p->seed);
-        k_resolve<<<(npx + 255) / 256, 256, 0, sc->stream>>>(sc->d_radiance, npx, spp, first, sc->d_accum, sc->d_frame);
-        sc->launches++;
+        {
+            KernelSpan span(sc, RT_KCLASS_RESOLVE);
+            k_resolve<<<(npx + 255) / 256, 256, 0, sc->stream>>>(sc->d_radiance, npx, spp, first, sc->d_accum, sc->d_frame);
+        }
         Batch b;
         b.first_owned = first;
         b.n_pixels = npx;
@@ -1050,6 +1154,7 @@ int rt_render_poll(rt_scene* sc, rt_vec3* buffer, int* done) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, sc->ev_frame_start, sc->ev_frame_stop);
         sc->last_frame_ms = ms;
+        resolve_spans(sc);
         sc->rendering = false;
         sc->frame_complete = true;
         *done = 1;
@@ -1077,6 +1182,7 @@ int rt_render_stop(rt_scene* sc) {
     cudaSetDevice(sc->device);
     // work already enqueued cannot be recalled; drain it so the buffers can be reused
     cudaStreamSynchronize(sc->stream);
+    resolve_spans(sc);
     sc->rendering = false;
     sc->frame_complete = false;
     return RT_OK;
@@ -1173,6 +1279,7 @@ int rt_trace_pixel_samples(rt_scene* sc, const rt_ray* rays, uint32_t n_rays, ui
     sc->launches++;
     cudaMemcpyAsync(mean_out, d_mean, sizeof(rt_vec3), cudaMemcpyDeviceToHost, sc->stream);
     cudaError_t e = cudaStreamSynchronize(sc->stream);
+    resolve_spans(sc);
     cudaFree(d_rays); cudaFree(d_acc); cudaFree(d_mean);
     if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("trace_pixel_samples: ") + cudaGetErrorString(e));
     sc->paths += n_rays;
@@ -1196,6 +1303,16 @@ int rt_get_stats(rt_scene* sc, rt_stats* out) {
     out->march_max_evals = c.march_max_evals;
     out->last_frame_ms = sc->last_frame_ms;
     out->last_intersect_ms = sc->last_intersect_ms;
+    out->verify_rays = c.verify_rays;
+    out->verify_false_culls = c.verify_false_culls;
+    out->ms_raygen = sc->ms_cls[RT_KCLASS_RAYGEN];
+    out->ms_extend = sc->ms_cls[RT_KCLASS_EXTEND];
+    out->ms_march = sc->ms_cls[RT_KCLASS_MARCH];
+    out->ms_shade = sc->ms_cls[RT_KCLASS_SHADE];
+    out->ms_resolve = sc->ms_cls[RT_KCLASS_RESOLVE];
+    out->launches_extend = sc->n_cls[RT_KCLASS_EXTEND];
+    out->launches_march = sc->n_cls[RT_KCLASS_MARCH];
+    out->launches_shade = sc->n_cls[RT_KCLASS_SHADE];
     return RT_OK;
 }
 int rt_reset_stats(rt_scene* sc) {
@@ -1204,11 +1321,18 @@ int rt_reset_stats(rt_scene* sc) {
     CU(cudaMemset(sc->d_counters, 0, sizeof(DevCounters)));
     sc->launches = 0;
     sc->paths = 0;
+    for (int k = 0; k < RT_KCLASS_COUNT; k++) { sc->ms_cls[k] = 0.0; sc->n_cls[k] = 0; }
     return RT_OK;
 }
 int rt_set_counters(rt_scene* sc, int enabled) {
     if (!sc) return fail(RT_ERR_INVALID, "null scene");
     sc->counters_on = enabled != 0;
+    return RT_OK;
+}
+int rt_set_kernel_timing(rt_scene* sc, int enabled) {
+    if (!sc) return fail(RT_ERR_INVALID, "null scene");
+    if (sc->rendering) return fail(RT_ERR_STATE, "a frame is in flight");
+    sc->ktiming = enabled != 0;
     return RT_OK;
 }
 

@@ -3,6 +3,7 @@
 #pragma once
 #include "rt_math.cuh"
 #include "rt_march.cuh"
+#include "rt_cull.cuh"
 
 namespace rt {
 
@@ -29,6 +30,11 @@ struct DevScene {
     int n_march;
     const int* march_index;
     const double* march_G;      // [n_march] bound of |grad f| over the marching region (inf: never skip)
+    // conservative cull table (rt_cull.cuh): one float4 per shape, padded to a multiple of 32, and one
+    // word per chunk of 32 shapes whose bit j says "shape 32*chunk + j takes part in the analytic loop"
+    int n_chunks;
+    const float4* cull;
+    const uint32_t* valid;
 };
 
 // optional work counters (rt_stats); enabled per launch by a template flag
@@ -36,6 +42,8 @@ struct DevCounters {
     unsigned long long segments, shape_tests, cull_tests, march_steps, march_rays;
     unsigned long long march_long_rays;  // marched rays that needed more than 2048 evaluations
     unsigned long long march_max_evals;  // most evaluations any single marched ray needed
+    unsigned long long verify_rays;         // RT_ISECT_VERIFY: rays whose FAST result differs from BRUTE
+    unsigned long long verify_false_culls;  // RT_ISECT_VERIFY: (ray, shape) pairs culled although the exact test hits
 };
 
 struct HitRec {  // RayHit, src/world/ray.rs:21-29
@@ -122,15 +130,14 @@ __device__ __forceinline__ bool shape_candidate(const DevScene& S, int i, int ki
 // ShapeCollection::ray_intersect (src/world/shapes/mod.rs:573-597): index order, shrinking max_t.
 // s_inv / s_kind: the shape list staged in shared memory (or the global arrays when it does not fit).
 template <bool COUNT>
-__device__ __forceinline__ void nearest_hit_brute(const DevScene& S, const double* s_inv, const uint8_t* s_kind,
-                                                  D3 ro, D3 rd, double min_t, double max_t, double& best_t,
-                                                  int& best_i, DevCounters& c) {
+__device__ __forceinline__ void nearest_hit_brute(const DevScene& S, D3 ro, D3 rd, double min_t, double max_t,
+                                                  double& best_t, int& best_i, DevCounters& c) {
     double min_distance = max_t;
     int winner = -1;
     const int n = S.n_shapes;
     for (int i = 0; i < n; i++) {
         double t;
-        if (shape_candidate<COUNT>(S, i, s_kind[i], s_inv + 12 * i, ro, rd, min_t, min_distance, t, c)) {
+        if (shape_candidate<COUNT>(S, i, S.kind[i], S.inv + 12 * i, ro, rd, min_t, min_distance, t, c)) {
             min_distance = t;
             winner = i;
         }
@@ -150,34 +157,76 @@ __device__ __forceinline__ void nearest_hit_brute(const DevScene& S, const doubl
 // unchecked D == 0 branch and a NaN t — are detected ("degenerate") and replayed through
 // nearest_hit_brute.
 
-// step 1.  Returns true when the ray is degenerate.
+// the shape list as the analytic loop sees it: the cull table, staged in dynamic shared memory when it
+// fits (rt_core.cu: stage_scene), else read from global memory.  The shared copy is addressed through
+// the extern array itself so that the compiler emits LDS rather than generic loads.
+extern __shared__ __align__(16) unsigned char rt_smem_raw[];
+struct Staged {
+    bool smem;
+};
+
+// one exact candidate test of analytic shape i (kind != MARCH) against the current best
 template <bool COUNT>
-__device__ __forceinline__ bool analytic_nearest(const DevScene& S, const double* s_inv, const uint8_t* s_kind, D3 ro,
-                                                 D3 rd, double min_t, double max_t, double& best, int& winner,
-                                                 DevCounters& c) {
+__device__ __forceinline__ void analytic_test(const DevScene& S, int i, D3 ro, D3 rd, double min_t, double& best,
+                                              int& winner, bool& degenerate, DevCounters& c) {
+    const int kind = S.kind[i];
+    const double2* mp = reinterpret_cast<const double2*>(S.inv + 12 * i);  // rows are 96 B, 16-byte aligned
+    double m[12];
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        double2 v = __ldg(mp + k);
+        m[2 * k] = v.x;
+        m[2 * k + 1] = v.y;
+    }
+    D3 o = xf_point(m, ro);
+    D3 d = xf_vector(m, rd);
+    if (COUNT) c.shape_tests++;
+    double t;
+    bool ok;
+    if (kind == RT_SHAPE_SPHERE) ok = sphere_candidate(o, d, min_t, best, t, &degenerate);
+    else if (kind == RT_SHAPE_CUBE) ok = cube_candidate(o, d, min_t, best, t);
+    else ok = rect_candidate(S.params + RT_SHAPE_PARAMS * i, o, d, min_t, best, t);
+    if (ok) {
+        if (t != t) degenerate = true;
+        best = t;
+        winner = i;
+    }
+}
+
+// step 1.  Returns true when the ray is degenerate.  Shapes are visited in index order, 32 at a time:
+// the FP32 cull (rt_cull.cuh) of a whole chunk first, with every lane of the warp busy, then each lane
+// runs the exact test on its own survivors.
+template <bool COUNT, bool SMEM>
+__device__ __forceinline__ bool analytic_nearest_impl(const DevScene& S, D3 ro, D3 rd, double min_t, double max_t,
+                                                      double& best, int& winner, DevCounters& c) {
     best = max_t;
     winner = -1;
     bool degenerate = false;
-    const int n = S.n_shapes;
-    for (int i = 0; i < n; i++) {
-        const int kind = s_kind[i];
-        if (kind == RT_SHAPE_MARCH) continue;
-        const double* m = s_inv + 12 * i;
-        D3 o = xf_point(m, ro);
-        D3 d = xf_vector(m, rd);
-        if (COUNT) c.shape_tests++;
-        double t;
-        bool ok;
-        if (kind == RT_SHAPE_SPHERE) ok = sphere_candidate(o, d, min_t, best, t, &degenerate);
-        else if (kind == RT_SHAPE_CUBE) ok = cube_candidate(o, d, min_t, best, t);
-        else ok = rect_candidate(S.params + RT_SHAPE_PARAMS * i, o, d, min_t, best, t);
-        if (ok) {
-            if (t != t) degenerate = true;
-            best = t;
-            winner = i;
+    const CullRay cr = make_cull_ray(ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
+    const float4* cull = SMEM ? reinterpret_cast<const float4*>(rt_smem_raw) : S.cull;
+    const uint32_t* vmask = SMEM ? reinterpret_cast<const uint32_t*>(rt_smem_raw + (size_t)512 * S.n_chunks) : S.valid;
+    for (int ch = 0; ch < S.n_chunks; ch++) {
+        const float4* tab = cull + 32 * ch;
+        uint32_t mask = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++)
+            if (cull_pass(cr, tab[j])) mask |= 1u << j;
+        const uint32_t valid = vmask[ch];
+        mask &= valid;
+        if (COUNT) c.cull_tests += __popc(valid);
+        while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            analytic_test<COUNT>(S, 32 * ch + j, ro, rd, min_t, best, winner, degenerate, c);
         }
     }
     return degenerate;
+}
+template <bool COUNT>
+__device__ __forceinline__ bool analytic_nearest(const DevScene& S, const Staged& st, D3 ro, D3 rd, double min_t,
+                                                 double max_t, double& best, int& winner, DevCounters& c) {
+    if (st.smem) return analytic_nearest_impl<COUNT, true>(S, ro, rd, min_t, max_t, best, winner, c);
+    return analytic_nearest_impl<COUNT, false>(S, ro, rd, min_t, max_t, best, winner, c);
 }
 
 // does marched shape number k (position in S.march_index) have to be marched for this ray, given the
@@ -228,16 +277,15 @@ __device__ __forceinline__ bool march_shape_update(const DevScene& S, const doub
 }
 
 template <bool COUNT>
-__device__ __forceinline__ void nearest_hit_fast(const DevScene& S, const double* s_inv, const uint8_t* s_kind,
-                                                 D3 ro, D3 rd, double min_t, double max_t, double& best_t,
-                                                 int& best_i, DevCounters& c) {
+__device__ __forceinline__ void nearest_hit_fast(const DevScene& S, const Staged& st, D3 ro, D3 rd, double min_t,
+                                                 double max_t, double& best_t, int& best_i, DevCounters& c) {
     double best;
     int winner;
-    bool degenerate = analytic_nearest<COUNT>(S, s_inv, s_kind, ro, rd, min_t, max_t, best, winner, c);
+    bool degenerate = analytic_nearest<COUNT>(S, st, ro, rd, min_t, max_t, best, winner, c);
     for (int k = 0; k < S.n_march && !degenerate; k++)
-        degenerate = march_shape_update<COUNT>(S, s_inv, k, ro, rd, min_t, max_t, best, winner, c);
+        degenerate = march_shape_update<COUNT>(S, S.inv, k, ro, rd, min_t, max_t, best, winner, c);
     if (degenerate) {
-        nearest_hit_brute<COUNT>(S, s_inv, s_kind, ro, rd, min_t, max_t, best_t, best_i, c);
+        nearest_hit_brute<COUNT>(S, ro, rd, min_t, max_t, best_t, best_i, c);
         return;
     }
     if (COUNT) c.segments++;

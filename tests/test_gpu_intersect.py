@@ -237,3 +237,96 @@ def test_exact_skip_skips(monkeypatch):
     sc.closest_hit(rays, mode=rt.RT_ISECT_FAST, want=("index",))
     skip = sc.stats().march_steps
     assert plain > 500_000 and skip * 10 < plain, (plain, skip)
+
+
+# ---- conservative cull (rt_cull.cuh) ---------------------------------------------------------------
+def grazing_rays(sc, n_shapes, seed):
+    """rays that pass at distance r*(1 + eps) from the centre of small spheres / cubes, from near and
+    far: the inputs on which an over-eager cull would drop a real hit"""
+    rng = np.random.default_rng(seed)
+    d = sc.desc()
+    dirm = np.ctypeslib.as_array(d.direct, shape=(d.n_shapes, 12))
+    kinds = sc.shape_kinds()
+    cand = np.where((kinds == 0) | (kinds == 1))[0]
+    pick = cand[rng.integers(0, len(cand), n_shapes)]
+    rays = []
+    for i in pick:
+        C = dirm[i, [3, 7, 11]]
+        r = np.abs(dirm[i, [0, 5, 10]]).max() * (math.sqrt(3.0) if kinds[i] == 1 else 1.0)
+        for eps in (0.0, 1e-14, -1e-14, 1e-9, -1e-9, 1e-6, -1e-6, 1e-3, -1e-3, 0.02, 0.045, 0.06, 0.2, -0.3):
+            for dist in (0.0, 0.5 * r, 3.0 * r, 50.0, 1e3, 1e5):
+                u = rng.normal(size=3); u /= np.linalg.norm(u)
+                w = np.cross(u, rng.normal(size=3)); w /= np.linalg.norm(w)
+                o = C + w * r * (1.0 + eps) - u * dist
+                rays.append(np.concatenate([o, u]))
+                rays.append(np.concatenate([o, -u]))      # the same line walked the other way (behind test)
+    r = np.array(rays)
+    return rt.make_rays(r[:, :3], r[:, 3:])
+
+
+@pytest.mark.parametrize("name", ["spheres.json", "cornell_box.json", "detached_materials.json", "dupin.json",
+                                  "cube_test.json"])
+def test_cull_is_conservative_on_fixture_scenes(name):
+    """RT_ISECT_VERIFY: FAST == BRUTE on every ray and no culled (ray, shape) pair hits in the exact test"""
+    sc = rt.Scene.from_file(scene_path(name), random_spheres_seed=1)
+    rays = np.concatenate([scene_rays(sc, 1 << 13, seed=5), grazing_rays(sc, 40, seed=6)])
+    sc.reset_stats()
+    got = sc.closest_hit(rays, mode=rt.RT_ISECT_VERIFY)
+    st = sc.stats()
+    assert st.verify_rays == 0, f"{st.verify_rays} rays differ between the culled and the literal loop"
+    assert st.verify_false_culls == 0, f"{st.verify_false_culls} culled pairs are hits in the exact test"
+    osc = po.OracleScene(sc.desc())
+    _compare(got, osc.intersect_batch(rays), len(rays), rt.RT_ISECT_VERIFY)
+    _compare(sc.closest_hit(rays, mode=rt.RT_ISECT_FAST), osc.intersect_batch(rays), len(rays), rt.RT_ISECT_FAST)
+
+
+def test_cull_far_and_ill_conditioned_shapes():
+    """small shapes far from the origin (FP32 cancellation in C - o), flattened / rotated shapes
+    (condition number > 30: never culled), huge shapes, rays from 1e6 away"""
+    import json
+    scene = json.loads(json.dumps(TRIO))
+    T = lambda t, r, s: {"translate": t, "rotate": r, "scale": s}
+    scene["shapes"] = [
+        {"type": "Sphere", "name": "far small", "material": "M", "transform": T([1e6, 2e6, -3e6], [0, 0, 0], [0.2] * 3)},
+        {"type": "Sphere", "name": "flat", "material": "M", "transform": T([0, 5, 0], [0, -100, 0], [10, 0.1, 10])},
+        {"type": "Cube", "name": "rot cube", "material": "M", "transform": T([4, 1, 2], [30, 45, 60], [1, 2, 3])},
+        {"type": "Cube", "name": "far cube", "material": "M", "transform": T([-5e5, 10, 7e5], [10, 20, 30], [0.5] * 3)},
+        {"type": "Sphere", "name": "sun", "material": "M", "transform": T([0, 1.476e11, 0], [0, 0, 0], [7e8] * 3)},
+        {"type": "Sphere", "name": "ellipsoid", "material": "M", "transform": T([-3, 0, 4], [15, 25, 35], [1, 2, 4])},
+        {"type": "Sphere", "name": "tiny", "material": "M", "transform": T([0.5, 0.5, 0.5], [0, 0, 0], [1e-4] * 3)},
+    ]
+    sc = rt.Scene.from_json(json.dumps(scene), add_random_spheres=False)
+    rng = np.random.default_rng(12)
+    d = sc.desc()
+    dirm = np.ctypeslib.as_array(d.direct, shape=(d.n_shapes, 12))
+    rays = [grazing_rays(sc, 60, seed=13)]
+    for i in range(d.n_shapes):   # rays aimed at / near each shape from random distances
+        C = dirm[i, [3, 7, 11]]
+        r = np.abs(dirm[i, [0, 5, 10]]).max()
+        for dist in (2.0, 1e2, 1e4, 1e6):
+            u = rng.normal(size=(300, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+            o = C + u * (r + dist)
+            tgt = C + rng.normal(size=(300, 3)) * r * 0.8
+            rays.append(rt.make_rays(o, tgt - o))
+    rays = np.concatenate(rays)
+    sc.reset_stats()
+    got = sc.closest_hit(rays, mode=rt.RT_ISECT_VERIFY)
+    st = sc.stats()
+    assert st.verify_rays == 0 and st.verify_false_culls == 0, (st.verify_rays, st.verify_false_culls)
+    want = po.OracleScene(sc.desc()).intersect_batch(rays)
+    _compare(got, want, len(rays), rt.RT_ISECT_VERIFY)
+    _compare(sc.closest_hit(rays, mode=rt.RT_ISECT_FAST), want, len(rays), rt.RT_ISECT_FAST)
+    assert len(set(np.unique(want["index"])) - {-1}) >= 6   # (nearly) every shape is hit by some ray
+
+
+def test_cull_removes_most_exact_tests():
+    """on cornell_box (481 small spheres in one corner) the exact FP64 test runs for a few percent of the pairs"""
+    sc = rt.Scene.from_file(scene_path("cornell_box.json"), random_spheres_seed=1)
+    rays = scene_rays(sc, 1 << 14, seed=21)
+    sc.set_counters(True)
+    sc.reset_stats()
+    sc.closest_hit(rays, mode=rt.RT_ISECT_FAST, want=("index",))
+    st = sc.stats()
+    sc.set_counters(False)
+    assert st.cull_tests >= len(rays) * 480
+    assert st.shape_tests * 10 < st.cull_tests, (st.shape_tests, st.cull_tests)

@@ -13,6 +13,7 @@ for name, w, h, spp in [("spheres.json", 640, 480, 16), ("cornell_box.json", 256
     ds = sc.device_scene(0)
     for rep in range(2):
         sc.set_counters(rep == 1)
+        sc.set_kernel_timing(rep == 0)
         sc.reset_stats()
         p = api.render_params(w, h, spp, 8, seed=1)
         t0 = time.time()
@@ -22,4 +23,6 @@ for name, w, h, spp in [("spheres.json", 640, 480, 16), ("cornell_box.json", 256
         st = sc.stats()
         print(f"{name} {w}x{h}x{spp} counters={rep}: wall {dt*1e3:.1f} ms, device {st.last_frame_ms:.1f} ms, "
               f"{w*h*spp/st.last_frame_ms/1e3:.2f} Mpaths/s, launches {st.kernel_launches}, seg {st.segments}, "
-              f"tests {st.shape_tests}, march_steps {st.march_steps}, march_rays {st.march_rays}, long {st.march_long_rays}, max {st.march_max_evals}")
+              f"exact {st.shape_tests}, cull {st.cull_tests}, march_steps {st.march_steps}, march_rays {st.march_rays}, "
+              f"long {st.march_long_rays}, max {st.march_max_evals} | ms raygen {st.ms_raygen:.2f} extend {st.ms_extend:.2f} "
+              f"march {st.ms_march:.2f} shade {st.ms_shade:.2f} resolve {st.ms_resolve:.2f}")
