@@ -268,6 +268,9 @@ typedef struct rt_stats {
      * the library's stream; only while rt_set_kernel_timing is on) and the launches they cover */
     double ms_raygen, ms_extend, ms_march, ms_shade, ms_resolve;
     uint64_t launches_extend, launches_march, launches_shade;
+    /* k_march work breakdown (with counters on): literal steps at level 0, literal steps at the
+     * refinement levels, exact multi-step jumps, hops of the skip bound */
+    uint64_t march_prof[4];
 } rt_stats;
 int rt_get_stats(rt_scene* scene, rt_stats* out);
 int rt_reset_stats(rt_scene* scene);

@@ -110,6 +110,7 @@ class Stats(C.Structure):
         ("launches_extend", C.c_uint64),
         ("launches_march", C.c_uint64),
         ("launches_shade", C.c_uint64),
+        ("march_prof", C.c_uint64 * 4),
     ]
 
 

@@ -103,6 +103,25 @@ inline void bounds_cell(const double* q, Iv x, Iv y, Iv z, double* G, double* H)
     *H = std::sqrt(s) * (1.0 + 1e-12);
 }
 
+constexpr double kRegionInflate = 1.06;  // samples may overshoot the bound by one step; see march guard
+
+// magnitude arithmetic: every operation returns an upper bound of the sum of the absolute values of the
+// terms it combines, so evaluating the polynomial text on it bounds the "absolute-value polynomial"
+// F >= sum |monomial| over the region.  The rounding error of evaluating f in floating point with n
+// operations is at most gamma_n * F (running error analysis).
+struct Mag {
+    double v;
+};
+inline Mag operator+(Mag a, Mag b) { return Mag{a.v + b.v}; }
+inline Mag operator-(Mag a, Mag b) { return Mag{a.v + b.v}; }
+inline Mag operator*(Mag a, Mag b) { return Mag{a.v * b.v}; }
+inline Mag operator+(Mag a, double b) { return Mag{a.v + std::fabs(b)}; }
+inline Mag operator-(Mag a, double b) { return Mag{a.v + std::fabs(b)}; }
+inline Mag operator*(Mag a, double b) { return Mag{a.v * std::fabs(b)}; }
+inline Mag operator+(double a, Mag b) { return Mag{std::fabs(a) + b.v}; }
+inline Mag operator-(double a, Mag b) { return Mag{std::fabs(a) + b.v}; }
+inline Mag operator*(double a, Mag b) { return Mag{std::fabs(a) * b.v}; }
+
 // radii of the marching bound (ShapeFunction::intersect_bound / get_bounds)
 inline void bound_radii(const double* q, double r[3]) {
     if ((int)q[0] == RT_SURF_HEART) {
@@ -113,7 +132,26 @@ inline void bound_radii(const double* q, double r[3]) {
     }
 }
 
-constexpr double kRegionInflate = 1.06;  // samples may overshoot the bound by one step; see march guard
+// F >= sum of |monomials| of f anywhere in the inflated bounding box of the marching region
+inline double region_magnitude(const double* q) {
+    const double INF = std::numeric_limits<double>::infinity();
+    double r[3];
+    bound_radii(q, r);
+    for (int a = 0; a < 3; a++)
+        if (!(r[a] > 0.0) || !std::isfinite(r[a])) return INF;
+    Mag x{r[0] * kRegionInflate}, y{r[1] * kRegionInflate}, z{r[2] * kRegionInflate};
+    Mag f;
+    switch ((int)q[0]) {
+        case RT_SURF_HEART: f = surface_func_t<RT_SURF_HEART, Mag>(q, x, y, z); break;
+        case RT_SURF_SINE: f = surface_func_t<RT_SURF_SINE, Mag>(q, x, y, z); break;
+        case RT_SURF_STAR: f = surface_func_t<RT_SURF_STAR, Mag>(q, x, y, z); break;
+        case RT_SURF_DUPIN: f = surface_func_t<RT_SURF_DUPIN, Mag>(q, x, y, z); break;
+        case RT_SURF_HUNTS: f = surface_func_t<RT_SURF_HUNTS, Mag>(q, x, y, z); break;
+        default: f = surface_func_t<RT_SURF_CUSHION, Mag>(q, x, y, z); break;
+    }
+    if (!(f.v == f.v)) return INF;
+    return f.v * (1.0 + 1e-9);
+}
 
 // G >= sup |grad f| and H >= sup |u^T Hess f u| over the inflated bounding ellipsoid; +inf when the
 // parameters are unusable (the marcher then never skips and behaves exactly like the plain loop)

@@ -127,6 +127,12 @@ __device__ __forceinline__ void flush_counters(const DevCounters& c, DevCounters
     }
     if (c.verify_rays) atomicAdd(&g->verify_rays, c.verify_rays);
     if (c.verify_false_culls) atomicAdd(&g->verify_false_culls, c.verify_false_culls);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        unsigned long long x = c.march_prof[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+        if ((threadIdx.x & 31) == 0 && x) atomicAdd(&g->march_prof[k], x);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -327,16 +333,24 @@ k_bounce(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
 
 struct HitQueue {
     double* t;        // best t so far (max_t = +inf when nothing was hit)
-    int32_t* index;   // winning shape, -1 = none, RT_HIT_REPLAY = degenerate ray: replay the literal loop
+    int32_t* index;   // winning shape, -1 = none
     uint32_t* mq_slot;  // march queue: path slot ...
     uint32_t* mq_mask;  // ... and the marched shapes (bit k = S.march_index[k]) it still has to test
+    uint32_t* rq_slot;  // replay queue: degenerate rays (Sphere D == 0, NaN t) that must go through the literal loop
 };
-#define RT_HIT_REPLAY (-2)
+
+// per-level counters of one batch (zeroed by one memset): live paths, march / replay queue lengths and
+// the march kernels' queue heads (one per surface kind)
+#define RT_CNT_LIVE 0
+#define RT_CNT_MARCH (RT_MAX_LEVELS)
+#define RT_CNT_REPLAY (2 * RT_MAX_LEVELS)
+#define RT_CNT_HEAD (3 * RT_MAX_LEVELS)              // + kind * RT_MAX_LEVELS
+#define RT_CNT_WORDS (9 * RT_MAX_LEVELS)
 
 template <bool COUNT>
 __global__ void __launch_bounds__(256, 3)
 k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ count_in, HitQueue hq,
-         uint32_t* march_count, DevCounters* g_counters) {
+         uint32_t* march_count, uint32_t* replay_count, DevCounters* g_counters) {
     Staged st = stage_scene(S, use_smem);
     DevCounters c = {};
     const uint32_t n = *count_in;
@@ -344,16 +358,14 @@ k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         uint32_t mask = 0;
+        bool degenerate = false;
         if (i < n) {
             D3 ro = mk(in.ox[i], in.oy[i], in.oz[i]);
             D3 rd = mk(in.dx[i], in.dy[i], in.dz[i]);
             double best;
             int winner;
-            bool degenerate = analytic_nearest<COUNT>(S, st, ro, rd, 0.001, INFINITY, best, winner, c);
-            if (degenerate) {
-                winner = RT_HIT_REPLAY;
-                mask = 0xffffffffu;
-            } else {
+            degenerate = analytic_nearest<COUNT>(S, st, ro, rd, 0.001, INFINITY, best, winner, c);
+            if (!degenerate) {
                 for (int k = 0; k < S.n_march; k++) {
                     const int si = S.march_index[k];
                     D3 o, d;
@@ -372,44 +384,152 @@ k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
             hq.mq_slot[slot] = i;
             hq.mq_mask[slot] = mask;
         }
+        slot = queue_append(degenerate, replay_count);
+        if (degenerate) hq.rq_slot[slot] = i;
     }
     if (COUNT) flush_counters(c, g_counters);
 }
 
-template <bool COUNT>
+// a marched candidate came out NaN: the sequential loop is not an arg-min for this ray -> literal loop
+__device__ __noinline__ void replay_brute(const DevScene& S, const PathQueue& in, const HitQueue& hq, uint32_t i) {
+    D3 ro = mk(in.ox[i], in.oy[i], in.oz[i]);
+    D3 rd = mk(in.dx[i], in.dy[i], in.dz[i]);
+    double best;
+    int winner;
+    DevCounters cc = {};
+    nearest_hit_brute<false>(S, ro, rd, 0.001, INFINITY, best, winner, cc);
+    hq.t[i] = best;
+    hq.index[i] = winner;
+}
+
+// K3: exact-skip marching of the queued (ray, marched shapes) entries, one surface kind per launch.
+// Per-ray cost is heavy-tailed (a grazing ray needs 50x the work of a typical one), so lanes are
+// persistent: a lane that finishes its entry takes the next one from the queue (warp-aggregated atomic on
+// `head`) while the other lanes of its warp keep marching.
+#define RT_MARCH_REFILL_MIN 4    // refill when at least this many lanes of the warp are idle (or none is busy)
+#define RT_MARCH_ATTEMPT_MIN 8   // run the attempt phase when this many lanes want it (or nobody can step)
+#define RT_MARCH_LITERAL_BURST 4 // literal steps per literal phase
+template <int KIND, bool COUNT>
 __global__ void __launch_bounds__(128)
-k_march(DevScene S, PathQueue in, HitQueue hq, const uint32_t* __restrict__ march_count, DevCounters* g_counters) {
+k_march(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32_t* __restrict__ march_count,
+        uint32_t* head, DevCounters* g_counters) {
     DevCounters c = {};
     const uint32_t n = *march_count;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    bool have = false, marching = false, exhausted = false;
+    uint32_t slot = 0, mask = 0, entry = 0;
+    int shape = -1, winner = -1;
+    double best = 0.0;
+    Marcher<KIND, COUNT> m;
+    for (;;) {
+        // ---- refill ------------------------------------------------------------------------------
+        const unsigned idle = __ballot_sync(FULL, !have && !exhausted);
+        const unsigned busy = __ballot_sync(FULL, have);
+        if (idle && (busy == 0 || __popc(idle) >= RT_MARCH_REFILL_MIN)) {
+            uint32_t base = 0;
+            const int leader = __ffs(idle) - 1;
+            if (lane == leader) base = atomicAdd(head, (uint32_t)__popc(idle));
+            base = __shfl_sync(FULL, base, leader);
+            if (!have && !exhausted) {
+                const uint32_t j = base + __popc(idle & ((1u << lane) - 1u));
+                if (j < n) {
+                    entry = j;
+                    slot = hq.mq_slot[j];
+                    mask = hq.mq_mask[j] & kind_mask;
+                    best = hq.t[slot];
+                    winner = hq.index[slot];
+                    have = mask != 0;
+                    marching = false;
+                } else {
+                    exhausted = true;
+                }
+            }
+        }
+        if (__ballot_sync(FULL, have) == 0) {
+            if (__ballot_sync(FULL, !exhausted) == 0) break;
+            continue;
+        }
+        // ---- start the next marched shape of this lane's entry (batched like the refill) -------------
+        const unsigned need_start = __ballot_sync(FULL, have && !marching);
+        const unsigned marching_any = __ballot_sync(FULL, marching);
+        if (have && !marching && (marching_any == 0 || __popc(need_start) >= RT_MARCH_REFILL_MIN)) {
+            if (mask == 0) {
+                hq.t[slot] = best;
+                hq.index[slot] = winner;
+                have = false;
+            } else {
+                const int k = __ffs(mask) - 1;
+                mask &= mask - 1;
+                shape = S.march_index[k];
+                const double* q = S.params + RT_SHAPE_PARAMS * shape;
+                D3 ro = mk(in.ox[slot], in.oy[slot], in.oz[slot]);
+                D3 rd = mk(in.dx[slot], in.dy[slot], in.dz[slot]);
+                D3 o, d;
+                double start, end_c;
+                if (march_needed(S, S.inv + 12 * shape, q, ro, rd, best, o, d, start, end_c)) {
+                    m.begin(q, o, d, start, end_c, S.march_G[k], S.march_F[k]);
+                    marching = true;
+                    if (COUNT) c.march_rays++;
+                }
+            }
+        }
+        // ---- marching: the warp votes between the expensive exact-jump attempt and the cheap literal
+        //      steps, so that attempts run with many lanes at once ---------------------------------------
+        int ph = marching ? m.phase() : -1;
+        if (ph == RT_PHASE_END) {
+            marching = false;
+            if (COUNT) {
+                c.march_steps += m.n;
+                for (int k = 0; k < 4; k++) c.march_prof[k] += m.prof[k];
+                if (m.n > 2048) c.march_long_rays++;
+                if (m.n > c.march_max_evals) c.march_max_evals = m.n;
+            }
+            if (m.finish() == RT_MARCH_DONE && !(m.t < 0.001)) {  // ray_marching.rs:55 with max_t = +inf
+                const double t = m.t;
+                if (t != t) {  // NaN candidate: replay now, and hide the entry from later kind passes
+                    replay_brute(S, in, hq, slot);
+                    hq.mq_mask[entry] = 0;
+                    have = false;
+                } else if (t < best || (t == best && shape > winner)) {
+                    best = t;
+                    winner = shape;
+                }
+            }
+        }
+        const unsigned want_attempt = __ballot_sync(FULL, ph == RT_PHASE_ATTEMPT);
+        const unsigned want_literal = __ballot_sync(FULL, ph == RT_PHASE_LITERAL);
+        if (want_attempt && (want_literal == 0 || __popc(want_attempt) >= RT_MARCH_ATTEMPT_MIN)) {
+            if (ph == RT_PHASE_ATTEMPT) m.attempt();
+        } else if (want_literal) {
+            if (ph == RT_PHASE_LITERAL) {
+#pragma unroll 1
+                for (int rep = 0; rep < RT_MARCH_LITERAL_BURST; rep++) {
+                    m.literal();
+                    if (m.phase() != RT_PHASE_LITERAL) break;
+                }
+            }
+        }
+    }
+    if (COUNT) flush_counters(c, g_counters);
+}
+
+// degenerate rays: the literal ShapeCollection loop, in index order
+__global__ void __launch_bounds__(128)
+k_replay(DevScene S, PathQueue in, HitQueue hq, const uint32_t* __restrict__ replay_count) {
+    const uint32_t n = *replay_count;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const uint32_t i = hq.mq_slot[j];
-        uint32_t mask = hq.mq_mask[j];
+        const uint32_t i = hq.rq_slot[j];
         D3 ro = mk(in.ox[i], in.oy[i], in.oz[i]);
         D3 rd = mk(in.dx[i], in.dy[i], in.dz[i]);
-        double best = hq.t[i];
-        int winner = hq.index[i];
-        bool degenerate = winner == RT_HIT_REPLAY;
-        if (!degenerate) {
-            DevCounters cc = {};
-            while (mask && !degenerate) {
-                int k = __ffs(mask) - 1;
-                mask &= mask - 1;
-                degenerate = march_shape_update<COUNT>(S, S.inv, k, ro, rd, 0.001, INFINITY, best, winner, cc);
-            }
-            if (COUNT) {  // shape tests were counted by k_extend
-                c.march_steps += cc.march_steps; c.march_rays += cc.march_rays; c.march_long_rays += cc.march_long_rays;
-                if (cc.march_max_evals > c.march_max_evals) c.march_max_evals = cc.march_max_evals;
-            }
-        }
-        if (degenerate) {
-            DevCounters cc = {};
-            nearest_hit_brute<false>(S, ro, rd, 0.001, INFINITY, best, winner, cc);
-        }
+        double best;
+        int winner;
+        DevCounters cc = {};
+        nearest_hit_brute<false>(S, ro, rd, 0.001, INFINITY, best, winner, cc);
         hq.t[i] = best;
         hq.index[i] = winner;
     }
-    if (COUNT) flush_counters(c, g_counters);
 }
 
 template <bool COUNT>
@@ -595,8 +715,9 @@ struct rt_scene {
     std::vector<void*> qallocs;
     float4* d_radiance = nullptr;
     HitQueue hq{};
-    uint32_t* d_counts = nullptr;  // [0, RT_MAX_LEVELS): live paths per level; [RT_MAX_LEVELS, 2*RT_MAX_LEVELS): march queue lengths (reset per batch)
+    uint32_t* d_counts = nullptr;  // RT_CNT_WORDS per batch (reset per batch), see RT_CNT_*
     int grid_extend = 0, grid_march = 0, grid_shade = 0;
+    uint32_t kind_mask[6] = {0, 0, 0, 0, 0, 0};  // marched shapes (bits of the march-queue mask) per surface kind
     bool wavefront = true;         // extend/march/shade; false = fused k_bounce (more than 32 marched shapes)
     float4* d_accum = nullptr;
     rt_vec3* d_frame = nullptr;    // owned order
@@ -728,6 +849,13 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
         if (getenv("RT_B200_NO_MARCH_SKIP")) march_G[k] = INFINITY;
     }
     if ((rc = upload(sc, march_G.data(), march_G.size(), &sc->ds.march_G)) != RT_OK) return bail(rc);
+    std::vector<double> march_F(march.size());
+    for (size_t k = 0; k < march.size(); k++) {
+        const double* q = d->params + (size_t)march[k] * RT_SHAPE_PARAMS;
+        march_F[k] = bounds::region_magnitude(q);
+        if (k < 32) sc->kind_mask[(int)q[0]] |= 1u << k;
+    }
+    if ((rc = upload(sc, march_F.data(), march_F.size(), &sc->ds.march_F)) != RT_OK) return bail(rc);
 
     // conservative cull table (rt_cull.cuh): one float4 per shape padded to whole chunks of 32, one
     // valid word per chunk (bit set = analytic shape that takes part in the loop)
@@ -773,7 +901,7 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
         return sc->n_sm * std::max(b, 1);
     };
     sc->grid_extend = occ_grid(k_extend<false>, 256, sc->smem_bytes);
-    sc->grid_march = occ_grid(k_march<false>, 128, 0);
+    sc->grid_march = occ_grid(k_march<RT_SURF_HEART, false>, 128, 0);
     sc->grid_shade = occ_grid(k_shade<false>, 256, 0);
     sc->wavefront = sc->ds.n_march <= 32 && !getenv("RT_B200_FUSED_BOUNCE");
 
@@ -980,7 +1108,8 @@ static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long 
         PathQueue& out = sc->q[(level + 1) & 1];
         uint32_t* cnt_in = sc->d_counts + level;
         uint32_t* cnt_out = sc->d_counts + level + 1;
-        uint32_t* mcount = sc->d_counts + RT_MAX_LEVELS + level;
+        uint32_t* mcount = sc->d_counts + RT_CNT_MARCH + level;
+        uint32_t* rcount = sc->d_counts + RT_CNT_REPLAY + level;
         if (!sc->wavefront) {
             KernelSpan span(sc, RT_KCLASS_EXTEND);
             if (sc->counters_on)
@@ -996,16 +1125,40 @@ static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long 
         {
             KernelSpan span(sc, RT_KCLASS_EXTEND);
             if (sc->counters_on)
-                k_extend<true><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, sc->d_counters);
+                k_extend<true><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, rcount, sc->d_counters);
             else
-                k_extend<false><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, sc->d_counters);
+                k_extend<false><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, rcount, sc->d_counters);
         }
         if (sc->ds.n_march > 0) {
             KernelSpan span(sc, RT_KCLASS_MARCH);
-            if (sc->counters_on)
-                k_march<true><<<sc->grid_march, 128, 0, sc->stream>>>(sc->ds, in, sc->hq, mcount, sc->d_counters);
-            else
-                k_march<false><<<sc->grid_march, 128, 0, sc->stream>>>(sc->ds, in, sc->hq, mcount, sc->d_counters);
+            for (int kind = 0; kind < 6; kind++) {
+                if (!sc->kind_mask[kind]) continue;
+                uint32_t* head = sc->d_counts + RT_CNT_HEAD + kind * RT_MAX_LEVELS + level;
+#define RT_LAUNCH_MARCH(K_)                                                                                             \
+    case K_:                                                                                                            \
+        if (sc->counters_on)                                                                                            \
+            k_march<K_, true><<<sc->grid_march, 128, 0, sc->stream>>>(sc->ds, sc->kind_mask[kind], in, sc->hq, mcount,  \
+                                                                     head, sc->d_counters);                            \
+        else                                                                                                            \
+            k_march<K_, false><<<sc->grid_march, 128, 0, sc->stream>>>(sc->ds, sc->kind_mask[kind], in, sc->hq, mcount, \
+                                                                      head, sc->d_counters);                           \
+        break;
+                switch (kind) {
+                    RT_LAUNCH_MARCH(RT_SURF_HEART)
+                    RT_LAUNCH_MARCH(RT_SURF_SINE)
+                    RT_LAUNCH_MARCH(RT_SURF_STAR)
+                    RT_LAUNCH_MARCH(RT_SURF_DUPIN)
+                    RT_LAUNCH_MARCH(RT_SURF_HUNTS)
+                    RT_LAUNCH_MARCH(RT_SURF_CUSHION)
+                }
+#undef RT_LAUNCH_MARCH
+                sc->launches++;
+            }
+            sc->launches--;  // the span already counted one launch
+        }
+        {   // degenerate rays (rare; the kernel exits at once when its queue is empty)
+            KernelSpan span(sc, RT_KCLASS_MARCH);
+            k_replay<<<sc->n_sm, 128, 0, sc->stream>>>(sc->ds, in, sc->hq, rcount);
         }
         {
             KernelSpan span(sc, RT_KCLASS_SHADE);
@@ -1035,8 +1188,9 @@ static int ensure_path_buffers(rt_scene* sc, uint64_t need_paths) {
         CU(cudaMalloc(&p, need_paths * sizeof(int32_t))); sc->qallocs.push_back(p); sc->hq.index = (int32_t*)p;
         CU(cudaMalloc(&p, need_paths * sizeof(uint32_t))); sc->qallocs.push_back(p); sc->hq.mq_slot = (uint32_t*)p;
         CU(cudaMalloc(&p, need_paths * sizeof(uint32_t))); sc->qallocs.push_back(p); sc->hq.mq_mask = (uint32_t*)p;
+        CU(cudaMalloc(&p, need_paths * sizeof(uint32_t))); sc->qallocs.push_back(p); sc->hq.rq_slot = (uint32_t*)p;
     }
-    if (!sc->d_counts) CU(cudaMalloc(&sc->d_counts, 2 * RT_MAX_LEVELS * sizeof(uint32_t)));
+    if (!sc->d_counts) CU(cudaMalloc(&sc->d_counts, RT_CNT_WORDS * sizeof(uint32_t)));
     sc->path_capacity = need_paths;
     return RT_OK;
 }
@@ -1083,7 +1237,7 @@ int rt_render_start(rt_scene* sc, const rt_camera* cam, const rt_render_params* 
     CU(cudaEventRecord(sc->ev_frame_start, sc->stream));
     for (uint64_t first = 0; first < sc->owned_pixels; first += px_per_batch) {
         uint32_t npx = (uint32_t)std::min<uint64_t>(px_per_batch, sc->owned_pixels - first);
-        CU(cudaMemsetAsync(sc->d_counts, 0, 2 * RT_MAX_LEVELS * sizeof(uint32_t), sc->stream));
+        CU(cudaMemsetAsync(sc->d_counts, 0, RT_CNT_WORDS * sizeof(uint32_t), sc->stream));
         {
             KernelSpan span(sc, RT_KCLASS_RAYGEN);
             k_raygen<<<sc->grid, 256, 0, sc->stream>>>(rcd, sc->map, first, npx, spp, k0, k1, sc->q[0], sc->d_counts, sc->d_radiance);
@@ -1263,7 +1417,7 @@ int rt_trace_pixel_samples(rt_scene* sc, const rt_ray* rays, uint32_t n_rays, ui
     cudaMalloc(&d_acc, sizeof(float4));
     cudaMalloc(&d_mean, sizeof(rt_vec3));
     cudaMemcpyAsync(d_rays, rays, n_rays * sizeof(rt_ray), cudaMemcpyHostToDevice, sc->stream);
-    cudaMemsetAsync(sc->d_counts, 0, 2 * RT_MAX_LEVELS * sizeof(uint32_t), sc->stream);
+    cudaMemsetAsync(sc->d_counts, 0, RT_CNT_WORDS * sizeof(uint32_t), sc->stream);
     k_load_rays<<<(n_rays + 255) / 256, 256, 0, sc->stream>>>(d_rays, n_rays, sc->q[0], sc->d_counts);
     sc->launches++;
     // a 1-pixel-wide "image" whose only pixel is pixel_index: owned pixel 0 -> (x = pixel_index, y = 0)
@@ -1305,6 +1459,7 @@ int rt_get_stats(rt_scene* sc, rt_stats* out) {
     out->last_intersect_ms = sc->last_intersect_ms;
     out->verify_rays = c.verify_rays;
     out->verify_false_culls = c.verify_false_culls;
+    for (int k = 0; k < 4; k++) out->march_prof[k] = c.march_prof[k];
     out->ms_raygen = sc->ms_cls[RT_KCLASS_RAYGEN];
     out->ms_extend = sc->ms_cls[RT_KCLASS_EXTEND];
     out->ms_march = sc->ms_cls[RT_KCLASS_MARCH];

@@ -16,21 +16,29 @@
 //      integer operations, and the result is the very double the reference's loop would hold.
 //
 //  (2) Proving that the skipped samples are uneventful (safe_extent).  Restricted to the ray the
-//      surface function is a univariate polynomial g(tau) = f(p0 + tau d) of degree <= 6; its Taylor
-//      coefficients are obtained once per ray by evaluating the same polynomial text on truncated
-//      Taylor series.  Starting from a point where |g| > M, hops of length
+//      surface function is a univariate polynomial g(tau) = f(p0 + tau d) of degree <= 6; its
+//      coefficients are obtained once per ray by evaluating the same polynomial text on
+//      degree-tracking polynomials (Poly<N>).  Starting from a point where |g| > M, hops of length
 //          dtau = 2b / (|g'| + sqrt(g'^2 + 2 B2 b)),   b = |g| - M,   B2 >= max |g''| on the chord
-//      stay inside {|g| >= M, same sign} by Taylor's theorem.  M bounds (64-fold) everything the
-//      exact-arithmetic model ignores: the drift of the accumulated t and p against p0 + tau d (at
-//      most half an ulp per step, N steps) seen through the largest slope of g on the chord, plus
-//      the rounding of evaluating f.  On every skipped sample the reference's loop would therefore
-//      have found no sign change, no |f| < 1e-15 and no range violation: it would only have executed
-//      `r = next`.
+//      stay inside {|g| >= M, same sign} by Taylor's theorem.  M bounds everything the
+//      exact-arithmetic model ignores, with a 16-fold margin:
+//        * the displacement of the accumulated sample against the model line p0 + tau d: MEASURED at
+//          the current sample (e = p - (p0 + (t - t0) d)), plus at most half an ulp of t and of p per
+//          future step for the m steps the jump may cover; seen through G >= sup |grad f| over the
+//          marching region (march_bounds.hpp);
+//        * the rounding of evaluating f (<= gamma_40 * F, F = the polynomial evaluated with absolute
+//          values over the region, march_bounds.hpp) and of the model itself (1e-13 * sum |c_k| T^k).
+//      On every skipped sample the reference's loop would therefore have found no sign change, no
+//      |f| < 1e-15 and no range violation: it would only have executed `r = next`.
 //
 // After a skip the surface function is evaluated at the landing sample like the reference does
 // (`r = next`) and compared with the polynomial's prediction; a mismatch (the model does not apply to
 // this ray) restores the saved state and finishes the ray with the plain loop.  Wherever skipping is
 // not worthwhile or not provable the reference's literal step is taken.
+//
+// The loop is written as a resumable state machine (Marcher::advance = one iteration of the
+// reference's inner loop or one exact multi-step skip) so that k_march can hand a finished lane its next
+// ray while the other lanes of the warp keep marching.
 // tests/test_gpu_intersect.py compares t bit-exactly with the oracle for all six surfaces.
 #pragma once
 #include "rt_math.cuh"
@@ -73,12 +81,18 @@ __device__ __forceinline__ double advance_exact(double a, double s, long long m)
             continue;
         }
         if (D == 0) return a;  // a + s == a for every remaining step
-        // steps that provably stay inside this binade.  The quotient is taken in floating point
-        // (operands < 2^53 are exact; the -2 absorbs its rounding): 64-bit integer division is far
-        // more expensive on the GPU.  Going down, the landing mantissa must stay >= 1.
-        double roomf = (up ? (double)(MANT - mant) : (double)(mant - 1)) / (double)D - 2.0;
-        long long room = roomf > 0.0 ? (long long)roomf : 0;
-        long long take = room < m ? room : m;
+        // steps that provably stay inside this binade (going down, the landing mantissa must stay >= 1):
+        // take <= num / D - 2.  All operands are < 2^53, hence exact as doubles.
+        const double num = up ? (double)(MANT - mant) : (double)(mant - 1);
+        const double Df = (double)D;
+        long long take;
+        if (((double)m * Df) * (1.0 + 1e-15) + 2.0 * Df <= num) {
+            take = m;  // the whole jump stays inside the binade (the common case): no division
+        } else {
+            double roomf = num / Df - 2.0;  // the -2 absorbs the rounding of the quotient
+            long long room = roomf > 0.0 ? (long long)roomf : 0;
+            take = room < m ? room : m;
+        }
         if (take > 0) {
             a = __longlong_as_double(up ? bits + take * D : bits - take * D);
             m -= take;
@@ -92,235 +106,337 @@ __device__ __forceinline__ double advance_exact(double a, double s, long long m)
 }
 
 // ---- (2) the surface function along the ray as a univariate polynomial ---------------------------
-#define RT_POLY_N 7  // degree <= 6 for every ShapeFunction of the reference
-struct Jet {
-    double c[RT_POLY_N];
+// Degree-tracking polynomial in tau: the product of a Poly<A> and a Poly<B> is a Poly<A+B>, so
+// expanding a surface of degree 6 costs ~80 FMAs instead of the ~300 of a fixed-size truncated series.
+template <int N>
+struct Poly {
+    static constexpr int degree = N;
+    double c[N + 1];
 };
-__device__ __forceinline__ Jet jet_lin(double v, double d) {
-    Jet r;
-    r.c[0] = v;
-    r.c[1] = d;
+template <int A, int B>
+__host__ __device__ __forceinline__ Poly<A + B> operator*(const Poly<A>& a, const Poly<B>& b) {
+    Poly<A + B> r;
 #pragma unroll
-    for (int i = 2; i < RT_POLY_N; i++) r.c[i] = 0.0;
-    return r;
-}
-__device__ __forceinline__ Jet operator+(Jet a, Jet b) {
-#pragma unroll
-    for (int i = 0; i < RT_POLY_N; i++) a.c[i] += b.c[i];
-    return a;
-}
-__device__ __forceinline__ Jet operator-(Jet a, Jet b) {
-#pragma unroll
-    for (int i = 0; i < RT_POLY_N; i++) a.c[i] -= b.c[i];
-    return a;
-}
-__device__ __forceinline__ Jet operator*(Jet a, Jet b) {
-    Jet r;
-#pragma unroll
-    for (int k = 0; k < RT_POLY_N; k++) {
+    for (int k = 0; k <= A + B; k++) {
         double s = 0.0;
 #pragma unroll
-        for (int i = 0; i <= k; i++) s = fma(a.c[i], b.c[k - i], s);
+        for (int i = 0; i <= A; i++)
+            if (k - i >= 0 && k - i <= B) s = fma(a.c[i], b.c[k - i], s);
         r.c[k] = s;
     }
     return r;
 }
-__device__ __forceinline__ Jet operator+(Jet a, double b) { a.c[0] += b; return a; }
-__device__ __forceinline__ Jet operator-(Jet a, double b) { a.c[0] -= b; return a; }
-__device__ __forceinline__ Jet operator+(double a, Jet b) { b.c[0] += a; return b; }
-__device__ __forceinline__ Jet operator-(double a, Jet b) {
+template <int A, int B>
+__host__ __device__ __forceinline__ Poly<(A > B ? A : B)> operator+(const Poly<A>& a, const Poly<B>& b) {
+    Poly<(A > B ? A : B)> r;
 #pragma unroll
-    for (int i = 0; i < RT_POLY_N; i++) b.c[i] = -b.c[i];
+    for (int k = 0; k <= (A > B ? A : B); k++) r.c[k] = (k <= A ? a.c[k] : 0.0) + (k <= B ? b.c[k] : 0.0);
+    return r;
+}
+template <int A, int B>
+__host__ __device__ __forceinline__ Poly<(A > B ? A : B)> operator-(const Poly<A>& a, const Poly<B>& b) {
+    Poly<(A > B ? A : B)> r;
+#pragma unroll
+    for (int k = 0; k <= (A > B ? A : B); k++) r.c[k] = (k <= A ? a.c[k] : 0.0) - (k <= B ? b.c[k] : 0.0);
+    return r;
+}
+template <int A>
+__host__ __device__ __forceinline__ Poly<A> operator+(Poly<A> a, double b) { a.c[0] += b; return a; }
+template <int A>
+__host__ __device__ __forceinline__ Poly<A> operator-(Poly<A> a, double b) { a.c[0] -= b; return a; }
+template <int A>
+__host__ __device__ __forceinline__ Poly<A> operator+(double a, Poly<A> b) { b.c[0] += a; return b; }
+template <int A>
+__host__ __device__ __forceinline__ Poly<A> operator-(double a, Poly<A> b) {
+#pragma unroll
+    for (int i = 0; i <= A; i++) b.c[i] = -b.c[i];
     b.c[0] += a;
     return b;
 }
-__device__ __forceinline__ Jet operator*(Jet a, double b) {
+template <int A>
+__host__ __device__ __forceinline__ Poly<A> operator*(Poly<A> a, double b) {
 #pragma unroll
-    for (int i = 0; i < RT_POLY_N; i++) a.c[i] *= b;
+    for (int i = 0; i <= A; i++) a.c[i] *= b;
     return a;
 }
-__device__ __forceinline__ Jet operator*(double a, Jet b) { return b * a; }
+template <int A>
+__host__ __device__ __forceinline__ Poly<A> operator*(double a, Poly<A> b) { return b * a; }
+__host__ __device__ __forceinline__ Poly<1> poly_lin(double v, double d) {
+    Poly<1> r;
+    r.c[0] = v;
+    r.c[1] = d;
+    return r;
+}
 
-struct RayPoly {
-    double c[RT_POLY_N];  // g(tau) = sum c[k] tau^k, tau = t - t0
-    double t0;            // the value t had at the expansion point
-    double M;             // {|g| >= M} is the provably uneventful region
-    double B2;            // >= max |g''| for tau in [0, tau_hi]
-    double tau_hi;        // the model covers tau in [0, tau_hi]
-    __device__ __forceinline__ void eval(double tau, double& g, double& dg) const {
-        double v = c[RT_POLY_N - 1], d = 0.0;
-#pragma unroll
-        for (int k = RT_POLY_N - 2; k >= 0; k--) {
-            d = fma(d, tau, v);
-            v = fma(v, tau, c[k]);
-        }
-        g = v;
-        dg = d;
-    }
+// degree of the surface polynomial along a ray
+template <int KIND>
+struct SurfDeg {
+    static constexpr int value = (KIND == RT_SURF_DUPIN || KIND == RT_SURF_CUSHION) ? 4 : 6;
 };
 
-// Taylor expansion of f along the ray around the current sample (t, p); n_steps = an upper bound of the
-// number of steps the reference can still take on this ray (drift bound), dlen = |d|.
+template <int DEG>
+struct RayPoly {
+    double c[DEG + 1];  // g(tau) = sum c[k] tau^k, tau = t - t0
+    double t0;          // the value t had at the expansion point ...
+    D3 p0;              // ... and the sample position there: the model line is p0 + tau d
+    double tau_hi;      // the model covers tau in [0, tau_hi]
+    double err0;        // evaluation / model rounding term of M
+    double drift1;      // displacement bound per future step, already multiplied by the safety factor and G
+};
+
+#define RT_MARCH_SAFETY 16.0
+
+// expansion of f along the ray around the current sample (t, p); the model must cover tau in [0, tau_hi]
 template <int KIND>
 __device__ __forceinline__ void expand_ray(const double* q, D3 p, D3 d, double t, double t_end, double tau_hi,
-                                           double n_steps, double G, RayPoly& P) {
-    Jet g = surface_func_t<KIND, Jet>(q, jet_lin(p.x, d.x), jet_lin(p.y, d.y), jet_lin(p.z, d.z));
-    double scale = 0.0, g1 = 0.0, b2 = 0.0;
+                                           double G, double F, RayPoly<SurfDeg<KIND>::value>& P) {
+    constexpr int DEG = SurfDeg<KIND>::value;
+    auto g = surface_func_t<KIND>(q, poly_lin(p.x, d.x), poly_lin(p.y, d.y), poly_lin(p.z, d.z));
+    static_assert(decltype(g)::degree == DEG, "SurfDeg out of date");
+    double scale = 0.0;
     double pw = 1.0;  // tau_hi^k
 #pragma unroll
-    for (int k = 0; k < RT_POLY_N; k++) {
+    for (int k = 0; k <= DEG; k++) {
         P.c[k] = g.c[k];
         scale += fabs(g.c[k]) * pw;
         pw *= tau_hi;
     }
-    pw = 1.0;
-#pragma unroll
-    for (int k = 1; k < RT_POLY_N; k++) {
-        g1 += (double)k * fabs(g.c[k]) * pw;             // >= max |g'|
-        if (k >= 2) b2 += (double)(k * (k - 1)) * fabs(g.c[k]) * (pw / tau_hi);  // >= max |g''|
-        pw *= tau_hi;
-    }
-    // drift of the accumulators against the exact line p0 + tau d: at most half an ulp per step.  A
-    // drift of t shifts the sample along the ray (seen through max |g'| <= g1); a drift e of p changes
-    // f by at most G |e|, G >= sup |grad f| over the marching region (march_bounds.hpp).
-    const double EPS = 1.1102230246251565e-16;  // 2^-53
-    double tmax = fmax(fabs(t), fabs(t_end)) + tau_hi;
-    double drift_t = n_steps * EPS * tmax;
-    double pmax = fmax(fmax(fabs(p.x), fabs(p.y)), fabs(p.z)) + tau_hi * fmax(fmax(fabs(d.x), fabs(d.y)), fabs(d.z));
-    double drift_p = 1.7320508075688772 * n_steps * EPS * pmax;
+    const double EPS = 1.1102230246251565e-16;  // 2^-53: half an ulp, relative
+    const double tmax = fmax(fabs(t), fabs(t_end)) + tau_hi;
+    const double dmax = fmax(fmax(fabs(d.x), fabs(d.y)), fabs(d.z));
+    const double pmax = fmax(fmax(fabs(p.x), fabs(p.y)), fabs(p.z)) + tau_hi * dmax;
+    const double dlen = fabs(d.x) + fabs(d.y) + fabs(d.z);  // >= |d|
+    // one step moves the sample off the model line by at most half an ulp of p per component, half an ulp
+    // of t along d, and the rounding of `step * dir` (relative 2^-53 of one step, far below the former)
+    const double per_step = EPS * (2.0 * pmax + tmax * dlen);
     P.t0 = t;
-    P.M = 64.0 * (g1 * drift_t + G * drift_p) + 1e-9 * scale + 1e-300;
-    P.B2 = b2 * (1.0 + 1e-9);
+    P.p0 = p;
     P.tau_hi = tau_hi;
-}
-
-// furthest tau from `tau` in direction dir (+1 / -1), not beyond tau_lim, such that the whole stretch
-// is provably inside {|g| >= M, sign(g) constant}
-__device__ __forceinline__ double safe_extent(const RayPoly& P, double tau, double dir, double tau_lim, double min_hop) {
-    double g, dg;
-    P.eval(tau, g, dg);
-    for (int hop = 0; hop < 64; hop++) {
-        double b = fabs(g) - P.M;
-        if (!(b > 0.0)) break;
-        double a = fabs(dg);
-        double dt = 2.0 * b / (a + sqrt(a * a + 2.0 * P.B2 * b));
-        dt *= 0.999;  // rounding of the bound arithmetic itself
-        double nt = tau + dir * dt;
-        if ((dir > 0.0) ? (nt >= tau_lim) : (nt <= tau_lim)) return tau_lim;
-        if (!(dt > min_hop)) break;
-        tau = nt;
-        P.eval(tau, g, dg);
-    }
-    return tau;
+    P.drift1 = RT_MARCH_SAFETY * G * per_step;
+    // rounding of f (gamma_n F with n ~ 40 operations -> 4.4e-15 F), of the model's coefficients and of
+    // its Horner evaluation / Taylor shift (a few 1e-16 * scale), of measuring e (8 steps' worth)
+    P.err0 = RT_MARCH_SAFETY * (1e-14 * F + 1e-14 * scale) + 8.0 * P.drift1 + 1e-300;
 }
 
 #define RT_MARCH_MIN_JUMP 8
+enum { RT_MARCH_MORE = 0, RT_MARCH_DONE = 1, RT_MARCH_MISS = 2 };
+enum { RT_PHASE_END = 0, RT_PHASE_ATTEMPT = 1, RT_PHASE_LITERAL = 2 };
 
-// RayMarchingShape::ray_intersect's loops (ray_marching.rs:27-57) with exact skipping.
-// G = gradient bound of the surface over its marching region; a non-finite G (or a chord of few
-// steps) gives exactly the plain loop.
-template <int KIND>
-__device__ __forceinline__ bool march_loop_skip(const double* q, D3 o, D3 d, double start, double end, double min_t,
-                                                double max_t, double G, double& t_out, unsigned long long& evals) {
-    double step = q[1];
-    const int depth = (int)q[2];
-    double t = start;
-    D3 p = o + t * d;
-    double r = surface_func<KIND>(q, p);
-    unsigned long long n = 0;
-    const double step0 = step;
-    // skipping pays when the chord holds many steps (NaN-proof comparisons)
-    bool skip_ok = (G == G) && G < 1e300 && step > 0.0 && (end - start) > 64.0 * step && (end - start) < 1e300;
-    bool have_poly = false;
-    RayPoly P;
-    for (int it = 0; it < depth; it++) {
-        bool finished = false;
-        D3 sd = step * d;  // `step * dir`, loop-invariant until the step changes
+// RayMarchingShape::ray_intersect's loops (ray_marching.rs:27-57) as a resumable state machine.
+// G / F = gradient and magnitude bounds of the surface over its marching region; a non-finite bound
+// (or a chord of few steps) gives exactly the plain loop.
+//
+// One iteration of the reference's inner loop is  [range check]  then either
+//   attempt():  try to replace the next m >= RT_MARCH_MIN_JUMP iterations by one exact jump, or
+//   literal():  the reference's own step.
+// phase() says which of the two the lane would do next; k_march lets a warp vote so that the expensive
+// attempt runs with many lanes at once.
+template <int KIND, bool PROF = false>
+struct Marcher {
+    static constexpr int DEG = SurfDeg<KIND>::value;
+    unsigned prof[4];  // PROF only: literal steps at level 0 / at refinement levels, jumps, hops
+    const double* q;
+    D3 d;
+    double start, end, G, F;
+    // the reference's loop state
+    double t, r, step;
+    D3 p, sd;
+    int it, depth;
+    unsigned long long n;  // surface evaluations (statistics, and the spin guard)
+    // skip machinery
+    double step0;
+    bool skip_ok, have_poly;
+    int cooldown, backoff;
+    RayPoly<DEG> P;
+
+    __device__ __forceinline__ void begin(const double* q_, D3 o_, D3 d_, double start_, double end_, double G_,
+                                          double F_) {
+        q = q_; d = d_; start = start_; end = end_; G = G_; F = F_;
+        step = q[1];
+        step0 = step;
+        depth = (int)q[2];
+        t = start;
+        p = o_ + t * d;
+        r = surface_func<KIND>(q, p);
+        n = 0;
+        it = 0;
+        sd = step * d;  // `step * dir`, loop-invariant until the step changes
+        cooldown = 0;
+        backoff = 4;
+        have_poly = false;
+        if (PROF) prof[0] = prof[1] = prof[2] = prof[3] = 0;
+        // skipping pays when the chord holds many steps (NaN-proof comparisons)
+        skip_ok = (G == G) && G < 1e300 && (F == F) && F < 1e300 && step > 0.0 && (end - start) > 64.0 * step &&
+                  (end - start) < 1e300;
+    }
+
+    // what the next iteration starts with.  RT_PHASE_END: the loops are over (finish() tells how)
+    __device__ __forceinline__ int phase() const {
+        if (it >= depth) return RT_PHASE_END;
+        // n > RT_MARCH_BUDGET: t + step == t (step underflowed against t); the reference would spin
+        // forever, a kernel must not: report a miss
+        if (t > end || t < start || n > RT_MARCH_BUDGET) return RT_PHASE_END;
+        return (skip_ok && cooldown == 0) ? RT_PHASE_ATTEMPT : RT_PHASE_LITERAL;
+    }
+    // valid when phase() == RT_PHASE_END
+    __device__ __forceinline__ int finish() const { return it >= depth ? RT_MARCH_DONE : RT_MARCH_MISS; }
+
+    // Try one exact multi-step jump from the current sample.  Afterwards either the state is m
+    // iterations further (the reference would have executed exactly `r = next` in each of them), or
+    // nothing changed except cooldown / skip_ok, so that phase() now answers RT_PHASE_LITERAL.
+    __device__ __forceinline__ void attempt() {
+        if (!have_poly) {
+            // expand around the current sample (the first one); covers every later sample of the ray
+            double tau_hi = (end - t) + 4.0 * step0;
+            expand_ray<KIND>(q, p, d, t, end, tau_hi, G, F, P);
+            n += 2;  // cost of the expansion in evaluation-equivalents (statistics only)
+            have_poly = true;
+        }
         const double abs_step = fabs(step);
         const double dir = step > 0.0 ? 1.0 : -1.0;
-        int cooldown = 0, backoff = 4;
-        for (;;) {
-            if (t > end || t < start || n > RT_MARCH_BUDGET) {
-                evals += n;
-                return false;
-            }
-            if (skip_ok && cooldown == 0) {
-                if (!have_poly) {
-                    // expand around the current sample (the first one); covers every later sample of the ray
-                    double tau_hi = (end - t) + 4.0 * step0;
-                    expand_ray<KIND>(q, p, d, t, end, tau_hi, tau_hi / step0 + 1024.0, G, P);
-                    n += 8;  // cost of the expansion in evaluation-equivalents (statistics only)
-                    have_poly = true;
-                }
-                const double tau = t - P.t0;
-                // the range checks must not fire on skipped samples: stay 2 steps inside [start, end]
-                double tau_lim = (dir > 0.0 ? end : start) - P.t0 - dir * 2.0 * abs_step;
-                tau_lim = fmin(fmax(tau_lim, 0.0), P.tau_hi);
-                double ts = safe_extent(P, tau, dir, tau_lim, abs_step);
-                double mf = (ts - tau) * dir / abs_step * (1.0 - 1e-9) - 2.0;
-                if (mf >= (double)RT_MARCH_MIN_JUMP) {
-                    const long long m = (long long)fmin(mf, 1.0e15);
-                    const double st = t;
-                    const D3 sp = p;
-                    t = advance_exact(t, step, m);
-                    p.x = advance_exact(p.x, sd.x, m);
-                    p.y = advance_exact(p.y, sd.y, m);
-                    p.z = advance_exact(p.z, sd.z, m);
-                    double land = surface_func<KIND>(q, p);  // the reference's `r = next` at the landing sample
-                    n++;
-                    double gp, dgp;
-                    P.eval(t - P.t0, gp, dgp);
-                    // self-check: the landing value must be what the polynomial predicts and keep the sign
-                    bool same_sign = ((land > 0.0) == (r > 0.0)) && land != 0.0;
-                    if (same_sign && fabs(land - gp) <= 0.25 * P.M && fabs(land) >= 0.5 * P.M) {
-                        r = land;
-                        backoff = 4;
-                        continue;
-                    }
-                    t = st;  // the model does not describe this ray: undo and finish it with the plain loop
-                    p = sp;
-                    skip_ok = false;
-                } else {
-                    // inside the |g| < M zone or next to a range limit: plain steps, retry later
-                    cooldown = backoff;
-                    backoff = min(backoff * 2, 64);
-                }
-            }
-            if (cooldown > 0) cooldown--;
-            t += step;
-            p.x += sd.x;
-            p.y += sd.y;
-            p.z += sd.z;
-            double next = surface_func<KIND>(q, p);
-            n++;
-            if (approx_zero(next)) {
-                finished = true;
-                break;
-            }
-            if ((r < 0.0 && next > 0.0) || (r > 0.0 && next < 0.0)) {
-                step *= -0.01;
-                r = next;
-                break;
-            }
-            r = next;
+        const double tau = t - P.t0;
+        // Taylor shift to the current sample: g(tau + sigma) = sum s[k] sigma^k
+        double s[DEG + 1];
+#pragma unroll
+        for (int k = 0; k <= DEG; k++) s[k] = P.c[k];
+#pragma unroll
+        for (int i = 0; i < DEG; i++)
+#pragma unroll
+            for (int j = DEG - 1; j >= i; j--) s[j] = fma(tau, s[j + 1], s[j]);
+        // the range checks must not fire on skipped samples: stay 2 steps inside [start, end] and the model
+        double tau_lim = (dir > 0.0 ? end : start) - P.t0 - dir * 2.0 * abs_step;
+        tau_lim = fmin(fmax(tau_lim, 0.0), P.tau_hi);
+        // do not look further than twice the Newton distance to the next root: M grows with the span
+        double span = fmax((tau_lim - tau) * dir, 0.0);
+        span = fmin(span, (2.0 * fabs(s[0]) / fabs(s[1]) + 32.0 * abs_step));  // fmin ignores a NaN quotient
+        const double m_max = span / abs_step + 4.0;
+        // M for this jump: measured displacement now + the steps the jump may cover
+        const double ex = p.x - fma(tau, d.x, P.p0.x), ey = p.y - fma(tau, d.y, P.p0.y),
+                     ez = p.z - fma(tau, d.z, P.p0.z);
+        const double M = RT_MARCH_SAFETY * G * (fabs(ex) + fabs(ey) + fabs(ez)) + m_max * P.drift1 + P.err0;
+        // furthest sigma in [0, span] such that the whole stretch is provably inside {|g| >= M, same sign}:
+        // hops of length 2b / (|g'| + sqrt(g'^2 + 2 B2 b)), b = |g| - M, B2 >= max |g''| over the span.
+        // The hop length is a lower bound, so it is computed in FP32 (rounded toward safety, shortened 1 %).
+        double b2 = 0.0, pw = 1.0;
+#pragma unroll
+        for (int k = 2; k <= DEG; k++) {
+            b2 += (double)(k * (k - 1)) * fabs(s[k]) * pw;
+            pw *= span;
         }
-        if (finished) break;
+        const float B2 = __double2float_ru(b2 * (1.0 + 1e-9));
+        double sig = 0.0, g = s[0], dg = s[1];
+        for (int hop = 0; hop < 32; hop++) {
+            if (PROF) prof[3]++;
+            const double b = fabs(g) - M;
+            if (!(b > 0.0)) break;
+            const float bf = __double2float_rd(b);
+            const float af = __double2float_ru(fabs(dg));
+            const float den = af + sqrtf(fmaf(af, af, 2.0f * B2 * bf));
+            const double dt = (double)(0.99f * (2.0f * bf / den));
+            const double ns = sig + dt;
+            if (ns >= span) {
+                sig = span;
+                break;
+            }
+            if (!(dt > abs_step)) break;
+            sig = ns;
+            const double x = dir * sig;
+            double v = s[DEG], dv = 0.0;
+#pragma unroll
+            for (int k = DEG - 1; k >= 0; k--) {
+                dv = fma(dv, x, v);
+                v = fma(v, x, s[k]);
+            }
+            g = v;
+            dg = dv;
+        }
+        const double mf = sig / abs_step * (1.0 - 1e-9) - 2.0;
+        if (mf >= (double)RT_MARCH_MIN_JUMP) {
+            const long long m = (long long)fmin(mf, 1.0e15);
+            const double st = t;
+            const D3 sp = p;
+            t = advance_exact(t, step, m);
+            p.x = advance_exact(p.x, sd.x, m);
+            p.y = advance_exact(p.y, sd.y, m);
+            p.z = advance_exact(p.z, sd.z, m);
+            const double land = surface_func<KIND>(q, p);  // the reference's `r = next` at the landing sample
+            n++;
+            if (PROF) prof[2]++;
+            const double x = t - st;
+            double gp = s[DEG];
+#pragma unroll
+            for (int k = DEG - 1; k >= 0; k--) gp = fma(gp, x, s[k]);
+            // self-check: the landing value must be what the polynomial predicts and keep the sign
+            const bool same_sign = ((land > 0.0) == (r > 0.0)) && land != 0.0;
+            if (same_sign && fabs(land - gp) <= 0.25 * M && fabs(land) >= 0.5 * M) {
+                r = land;
+                backoff = 4;
+                return;
+            }
+            t = st;  // the model does not describe this ray: undo and finish it with the plain loop
+            p = sp;
+            skip_ok = false;
+        } else {
+            // inside the |g| < M zone or next to a range limit: plain steps, retry later
+            cooldown = backoff;
+            backoff = min(backoff * 2, 64);
+        }
     }
-    evals += n;
-    if (t < min_t || t > max_t) return false;
-    t_out = t;
+
+    // the reference's literal step (ray_marching.rs:37-51)
+    __device__ __forceinline__ void literal() {
+        if (cooldown > 0) cooldown--;
+        t += step;
+        p.x += sd.x;
+        p.y += sd.y;
+        p.z += sd.z;
+        const double next = surface_func<KIND>(q, p);
+        n++;
+        if (PROF) prof[it == 0 ? 0 : 1]++;
+        if (approx_zero(next)) {
+            it = depth;  // `finished`
+            return;
+        }
+        if ((r < 0.0 && next > 0.0) || (r > 0.0 && next < 0.0)) {
+            step *= -0.01;
+            r = next;
+            it++;
+            sd = step * d;
+            cooldown = 0;
+            backoff = 4;
+            return;
+        }
+        r = next;
+    }
+};
+
+template <int KIND>
+__device__ __forceinline__ bool march_loop_skip(const double* q, D3 o, D3 d, double start, double end, double min_t,
+                                                double max_t, double G, double F, double& t_out,
+                                                unsigned long long& evals) {
+    Marcher<KIND> m;
+    m.begin(q, o, d, start, end, G, F);
+    int ph;
+    while ((ph = m.phase()) != RT_PHASE_END) {
+        if (ph == RT_PHASE_ATTEMPT) m.attempt();
+        else m.literal();
+    }
+    evals += m.n;
+    if (m.finish() == RT_MARCH_MISS) return false;
+    if (m.t < min_t || m.t > max_t) return false;
+    t_out = m.t;
     return true;
 }
 
 __device__ inline bool march_candidate_skip(const double* q, D3 o, D3 d, double start, double end, double min_t,
-                                            double max_t, double G, double& t, unsigned long long& evals) {
+                                            double max_t, double G, double F, double& t, unsigned long long& evals) {
     switch ((int)q[0]) {
-        case RT_SURF_HEART: return march_loop_skip<RT_SURF_HEART>(q, o, d, start, end, min_t, max_t, G, t, evals);
-        case RT_SURF_SINE: return march_loop_skip<RT_SURF_SINE>(q, o, d, start, end, min_t, max_t, G, t, evals);
-        case RT_SURF_STAR: return march_loop_skip<RT_SURF_STAR>(q, o, d, start, end, min_t, max_t, G, t, evals);
-        case RT_SURF_DUPIN: return march_loop_skip<RT_SURF_DUPIN>(q, o, d, start, end, min_t, max_t, G, t, evals);
-        case RT_SURF_HUNTS: return march_loop_skip<RT_SURF_HUNTS>(q, o, d, start, end, min_t, max_t, G, t, evals);
-        default: return march_loop_skip<RT_SURF_CUSHION>(q, o, d, start, end, min_t, max_t, G, t, evals);
+        case RT_SURF_HEART: return march_loop_skip<RT_SURF_HEART>(q, o, d, start, end, min_t, max_t, G, F, t, evals);
+        case RT_SURF_SINE: return march_loop_skip<RT_SURF_SINE>(q, o, d, start, end, min_t, max_t, G, F, t, evals);
+        case RT_SURF_STAR: return march_loop_skip<RT_SURF_STAR>(q, o, d, start, end, min_t, max_t, G, F, t, evals);
+        case RT_SURF_DUPIN: return march_loop_skip<RT_SURF_DUPIN>(q, o, d, start, end, min_t, max_t, G, F, t, evals);
+        case RT_SURF_HUNTS: return march_loop_skip<RT_SURF_HUNTS>(q, o, d, start, end, min_t, max_t, G, F, t, evals);
+        default: return march_loop_skip<RT_SURF_CUSHION>(q, o, d, start, end, min_t, max_t, G, F, t, evals);
     }
 }
 

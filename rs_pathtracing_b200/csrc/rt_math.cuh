@@ -69,43 +69,44 @@ __device__ __forceinline__ D3 xf_normal(const double* m, D3 n) {  // transpose o
 // the same text with interval jets to bound the second derivatives (march_bounds.hpp).
 // ------------------------------------------------------------------------------------------------
 template <int KIND, typename T>
-__host__ __device__ __forceinline__ T surface_func_t(const double* q, T px, T py, T pz) {
-    if (KIND == RT_SURF_HEART) {  // :147-155
-        T x2 = px * px;
-        T y2 = py * py;
-        T z2 = pz * pz;
-        T z3 = z2 * pz;
-        T a = x2 + (9.0 / 4.0) * y2 + z2 - 1.0;
+__host__ __device__ __forceinline__ auto surface_func_t(const double* q, T px, T py, T pz) {
+    // `auto` everywhere: with T = a degree-tracking polynomial (rt_march.cuh) every product has its own type
+    if constexpr (KIND == RT_SURF_HEART) {  // :147-155
+        auto x2 = px * px;
+        auto y2 = py * py;
+        auto z2 = pz * pz;
+        auto z3 = z2 * pz;
+        auto a = x2 + (9.0 / 4.0) * y2 + z2 - 1.0;
         return a * a * a - x2 * z3 - (9.0 / 80.0) * y2 * z3;
-    } else if (KIND == RT_SURF_SINE) {  // :203-211
+    } else if constexpr (KIND == RT_SURF_SINE) {  // :203-211
         double a_ = q[3];
         return a_ * a_ * (px - py - pz) * (px + py - pz) * (px - py + pz) * (px + py + pz) +
                4.0 * px * px * py * py * pz * pz;
-    } else if (KIND == RT_SURF_STAR) {  // :268-274
+    } else if constexpr (KIND == RT_SURF_STAR) {  // :268-274
         double a_ = q[3];
-        T x2 = px * px;
-        T y2 = py * py;
-        T z2 = pz * pz;
-        T c = x2 + y2 + z2 - 1.0;
+        auto x2 = px * px;
+        auto y2 = py * py;
+        auto z2 = pz * pz;
+        auto c = x2 + y2 + z2 - 1.0;
         return a_ * (x2 * y2 + x2 * z2 + y2 * z2) + (c * c * c);
-    } else if (KIND == RT_SURF_DUPIN) {  // :340-345
+    } else if constexpr (KIND == RT_SURF_DUPIN) {  // :340-345
         double a_ = q[3], b_ = q[4], c_ = q[5], d_ = q[6];
         double b2 = b_ * b_;
-        T e = px * px + py * py + pz * pz + b2 - d_ * d_;
-        T f = a_ * px - c_ * d_;
+        auto e = px * px + py * py + pz * pz + b2 - d_ * d_;
+        auto f = a_ * px - c_ * d_;
         return e * e - 4.0 * (f * f + b2 * py * py);
-    } else if (KIND == RT_SURF_HUNTS) {  // :399-406
-        T x2 = px * px;
-        T y2 = py * py;
-        T z2 = pz * pz;
-        T a = x2 + y2 + z2 - 13.0;
-        T b = 3.0 * x2 + y2 - 4.0 * z2 - 12.0;
+    } else if constexpr (KIND == RT_SURF_HUNTS) {  // :399-406
+        auto x2 = px * px;
+        auto y2 = py * py;
+        auto z2 = pz * pz;
+        auto a = x2 + y2 + z2 - 13.0;
+        auto b = 3.0 * x2 + y2 - 4.0 * z2 - 12.0;
         return 4.0 * a * a * a + 27.0 * b * b;
     } else {  // RT_SURF_CUSHION, :464-478
-        T x2 = px * px;
-        T y2 = py * py;
-        T z2 = pz * pz;
-        T a = x2 - pz;
+        auto x2 = px * px;
+        auto y2 = py * py;
+        auto z2 = pz * pz;
+        auto a = x2 - pz;
         return z2 * x2 - z2 * z2 - 2.0 * pz * x2 + 2.0 * pz * z2 + x2 - z2 - a * a - y2 * y2 - 2.0 * x2 * y2 -
                y2 * z2 + 2.0 * y2 * pz + y2;
     }

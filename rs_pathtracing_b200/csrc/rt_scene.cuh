@@ -30,6 +30,7 @@ struct DevScene {
     int n_march;
     const int* march_index;
     const double* march_G;      // [n_march] bound of |grad f| over the marching region (inf: never skip)
+    const double* march_F;      // [n_march] bound of sum |monomials of f| over the region (rounding of f)
     // conservative cull table (rt_cull.cuh): one float4 per shape, padded to a multiple of 32, and one
     // word per chunk of 32 shapes whose bit j says "shape 32*chunk + j takes part in the analytic loop"
     int n_chunks;
@@ -44,6 +45,7 @@ struct DevCounters {
     unsigned long long march_max_evals;  // most evaluations any single marched ray needed
     unsigned long long verify_rays;         // RT_ISECT_VERIFY: rays whose FAST result differs from BRUTE
     unsigned long long verify_false_culls;  // RT_ISECT_VERIFY: (ray, shape) pairs culled although the exact test hits
+    unsigned long long march_prof[4];       // k_march: literal steps at level 0 / deeper, exact jumps, bound hops
 };
 
 struct HitRec {  // RayHit, src/world/ray.rs:21-29
@@ -260,7 +262,7 @@ __device__ __forceinline__ bool march_shape_update(const DevScene& S, const doub
     if (COUNT) c.march_rays++;
     unsigned long long ev = 0;
     double t;
-    bool ok = march_candidate_skip(q, o, d, start, end_c, min_t, max_t, S.march_G[k], t, ev);
+    bool ok = march_candidate_skip(q, o, d, start, end_c, min_t, max_t, S.march_G[k], S.march_F[k], t, ev);
     if (COUNT) {
         c.march_steps += ev;
         if (ev > 2048) c.march_long_rays++;

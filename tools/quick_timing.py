@@ -25,4 +25,4 @@ for name, w, h, spp in [("spheres.json", 640, 480, 16), ("cornell_box.json", 256
               f"{w*h*spp/st.last_frame_ms/1e3:.2f} Mpaths/s, launches {st.kernel_launches}, seg {st.segments}, "
               f"exact {st.shape_tests}, cull {st.cull_tests}, march_steps {st.march_steps}, march_rays {st.march_rays}, "
               f"long {st.march_long_rays}, max {st.march_max_evals} | ms raygen {st.ms_raygen:.2f} extend {st.ms_extend:.2f} "
-              f"march {st.ms_march:.2f} shade {st.ms_shade:.2f} resolve {st.ms_resolve:.2f}")
+              f"march {st.ms_march:.2f} shade {st.ms_shade:.2f} resolve {st.ms_resolve:.2f} | prof lit0 {st.march_prof[0]} lit+ {st.march_prof[1]} jumps {st.march_prof[2]} hops {st.march_prof[3]}")
