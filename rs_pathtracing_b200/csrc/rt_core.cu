@@ -406,13 +406,19 @@ __device__ __noinline__ void replay_brute(const DevScene& S, const PathQueue& in
 // Per-ray cost is heavy-tailed (a grazing ray needs 50x the work of a typical one), so lanes are
 // persistent: a lane that finishes its entry takes the next one from the queue (warp-aggregated atomic on
 // `head`) while the other lanes of its warp keep marching.
-#define RT_MARCH_REFILL_MIN 4    // refill when at least this many lanes of the warp are idle (or none is busy)
-#define RT_MARCH_ATTEMPT_MIN 8   // run the attempt phase when this many lanes want it (or nobody can step)
-#define RT_MARCH_LITERAL_BURST 4 // literal steps per literal phase
+#ifndef RT_MARCH_MIN_BLOCKS
+#define RT_MARCH_MIN_BLOCKS 4
+#endif
+// tune.x: refill / start a shape when at least this many lanes of the warp are idle (or none is busy)
+// tune.y: run the attempt phase when this many lanes want it (or nobody can step)
+// tune.z: literal steps per literal phase
+#define RT_MARCH_REFILL_MIN tune.x
+#define RT_MARCH_ATTEMPT_MIN tune.y
+#define RT_MARCH_LITERAL_BURST tune.z
 template <int KIND, bool COUNT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, RT_MARCH_MIN_BLOCKS)
 k_march(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32_t* __restrict__ march_count,
-        uint32_t* head, DevCounters* g_counters) {
+        uint32_t* head, DevCounters* g_counters, int3 tune) {
     DevCounters c = {};
     const uint32_t n = *march_count;
     const unsigned FULL = 0xffffffffu;
@@ -718,6 +724,8 @@ struct rt_scene {
     uint32_t* d_counts = nullptr;  // RT_CNT_WORDS per batch (reset per batch), see RT_CNT_*
     int grid_extend = 0, grid_march = 0, grid_shade = 0;
     uint32_t kind_mask[6] = {0, 0, 0, 0, 0, 0};  // marched shapes (bits of the march-queue mask) per surface kind
+    int3 march_tune = make_int3(8, 8, 8);        // k_march scheduling thresholds (RT_B200_MARCH_TUNE=a,b,c)
+    int march_grid_scale = 100;                  // percent of the occupancy grid
     bool wavefront = true;         // extend/march/shade; false = fused k_bounce (more than 32 marched shapes)
     float4* d_accum = nullptr;
     rt_vec3* d_frame = nullptr;    // owned order
@@ -901,7 +909,13 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
         return sc->n_sm * std::max(b, 1);
     };
     sc->grid_extend = occ_grid(k_extend<false>, 256, sc->smem_bytes);
-    sc->grid_march = occ_grid(k_march<RT_SURF_HEART, false>, 128, 0);
+    if (const char* tv = getenv("RT_B200_MARCH_TUNE")) {
+        int a = 8, b = 8, c2 = 8, g = 0;
+        if (sscanf(tv, "%d,%d,%d,%d", &a, &b, &c2, &g) >= 3) sc->march_tune = make_int3(std::max(a, 1), std::max(b, 1), std::max(c2, 1));
+        if (g > 0) sc->march_grid_scale = g;
+    }
+    sc->grid_march = occ_grid(k_march<RT_SURF_HEART, false>, 128, 0) * sc->march_grid_scale / 100;
+    if (sc->grid_march < 1) sc->grid_march = 1;
     sc->grid_shade = occ_grid(k_shade<false>, 256, 0);
     sc->wavefront = sc->ds.n_march <= 32 && !getenv("RT_B200_FUSED_BOUNCE");
 
@@ -1138,10 +1152,10 @@ static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long 
     case K_:                                                                                                            \
         if (sc->counters_on)                                                                                            \
             k_march<K_, true><<<sc->grid_march, 128, 0, sc->stream>>>(sc->ds, sc->kind_mask[kind], in, sc->hq, mcount,  \
-                                                                     head, sc->d_counters);                            \
+                                                                     head, sc->d_counters, sc->march_tune);            \
         else                                                                                                            \
             k_march<K_, false><<<sc->grid_march, 128, 0, sc->stream>>>(sc->ds, sc->kind_mask[kind], in, sc->hq, mcount, \
-                                                                      head, sc->d_counters);                           \
+                                                                      head, sc->d_counters, sc->march_tune);           \
         break;
                 switch (kind) {
                     RT_LAUNCH_MARCH(RT_SURF_HEART)

@@ -82,24 +82,33 @@ __device__ __forceinline__ double advance_exact(double a, double s, long long m)
         }
         if (D == 0) return a;  // a + s == a for every remaining step
         // steps that provably stay inside this binade (going down, the landing mantissa must stay >= 1):
-        // take <= num / D - 2.  All operands are < 2^53, hence exact as doubles.
-        const double num = up ? (double)(MANT - mant) : (double)(mant - 1);
-        const double Df = (double)D;
+        // take <= num / D - 2, in integer arithmetic (64-bit int <-> double conversions and a double
+        // division per binade used to dominate the marcher)
+        const unsigned long long num = (unsigned long long)(up ? (MANT - mant) : (mant - 1));
+        const unsigned long long Du = (unsigned long long)D, mu = (unsigned long long)m;
+        const unsigned long long lo = mu * Du;
         long long take;
-        if (((double)m * Df) * (1.0 + 1e-15) + 2.0 * Df <= num) {
-            take = m;  // the whole jump stays inside the binade (the common case): no division
+        if (__umul64hi(mu, Du) == 0 && lo <= num && num - lo >= 2 * Du) {
+            take = m;  // the whole jump stays inside the binade (the common case)
         } else {
-            double roomf = num / Df - 2.0;  // the -2 absorbs the rounding of the quotient
-            long long room = roomf > 0.0 ? (long long)roomf : 0;
+            // floor(num / D) - 2 from a float quotient rounded down at every stage (a smaller take is
+            // always safe: the remaining steps are simply handled by the next iteration)
+            const float qf = __fdiv_rd(__ull2float_rd(num), __ull2float_ru(Du));
+            long long room = (long long)qf - 2;
+            if (room < 0) room = 0;
             take = room < m ? room : m;
         }
         if (take > 0) {
             a = __longlong_as_double(up ? bits + take * D : bits - take * D);
             m -= take;
         }
-        if (m > 0) {  // next to the binade edge: literal steps carry it across
-            a = a + s;
-            m--;
+        // next to the binade edge (the margin above leaves 2-3 steps): literal steps carry it across
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            if (m > 0) {
+                a = a + s;
+                m--;
+            }
         }
     }
     return a;
