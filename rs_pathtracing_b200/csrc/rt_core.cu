@@ -91,16 +91,16 @@ struct RayCasterDev {  // MultisamplerRayCaster, src/camera/ray_caster.rs:17-48
 };
 
 // ------------------------------------------------------------------------------------------------
-// shared-memory staging of the cull table (16 B per shape + one valid word per 32 shapes): every lane
-// of a warp reads the same entry at the same time, so each read is a conflict-free broadcast.  The
-// FP64 inverse rows are only needed for the few survivors of the cull and stay in global memory / L1.
+// shared-memory staging of the cull tree (rt_cull.cuh; 16 B per root / group / leaf / flat entry): the
+// flat list, the roots and the groups are read by every lane at the same address (broadcast), the leaves
+// of a lane's own groups at per-lane addresses.  The FP64 inverse rows are only needed for the few
+// survivors of the cull and stay in global memory / L1.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ Staged stage_scene(const DevScene& S, bool use_smem) {
     if (!use_smem) return Staged{false};
-    float4* s_cull = reinterpret_cast<float4*>(rt_smem_raw);
-    uint32_t* s_valid = reinterpret_cast<uint32_t*>(rt_smem_raw + (size_t)512 * S.n_chunks);
-    for (int k = threadIdx.x; k < 32 * S.n_chunks; k += blockDim.x) s_cull[k] = S.cull[k];
-    for (int k = threadIdx.x; k < S.n_chunks; k += blockDim.x) s_valid[k] = S.valid[k];
+    float4* s_tab = reinterpret_cast<float4*>(rt_smem_raw);
+    const int n = S.ctab_entries();
+    for (int k = threadIdx.x; k < n; k += blockDim.x) s_tab[k] = S.ctab[k];
     __syncthreads();
     return Staged{true};
 }
@@ -138,14 +138,19 @@ __device__ __forceinline__ void flush_counters(const DevCounters& c, DevCounters
 // ------------------------------------------------------------------------------------------------
 // K2/K3: batched nearest hit
 // ------------------------------------------------------------------------------------------------
-// RT_ISECT_VERIFY support: every analytic (ray, shape) pair the cull rejects is tested exactly with
-// max_t = +inf; a hit (or a degenerate branch) there is a false cull.
+// RT_ISECT_VERIFY support: every analytic (ray, shape) pair the cull rejects -- at its root, its group or
+// its own leaf entry -- is tested exactly with max_t = +inf; a hit (or a degenerate branch) there is a
+// false cull.
 __device__ __noinline__ unsigned long long count_false_culls(const DevScene& S, D3 ro, D3 rd, double min_t) {
     const CullRay cr = make_cull_ray(ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
     unsigned long long bad = 0;
     for (int i = 0; i < S.n_shapes; i++) {
-        if (!((S.valid[i >> 5] >> (i & 31)) & 1u)) continue;
-        if (cull_pass(cr, S.cull[i])) continue;
+        const int g = S.cull_group[i];
+        if (g == -2) continue;
+        bool reached = cull_pass(cr, S.cull[i]);
+        if (g >= 0)
+            reached = reached && cull_pass_node(cr, S.ctab[g / RT_CULL_ROOT_FANOUT]) && cull_pass_node(cr, S.ctab[S.n_roots + g]);
+        if (reached) continue;
         double best = INFINITY;
         int winner = -1;
         bool degenerate = false;
@@ -865,27 +870,22 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
     }
     if ((rc = upload(sc, march_F.data(), march_F.size(), &sc->ds.march_F)) != RT_OK) return bail(rc);
 
-    // conservative cull table (rt_cull.cuh): one float4 per shape padded to whole chunks of 32, one
-    // valid word per chunk (bit set = analytic shape that takes part in the loop)
-    const uint32_t n_chunks = (n + 31) / 32;
-    sc->ds.n_chunks = (int)n_chunks;
+    // conservative cull tree (rt_cull.cuh)
     {
-        std::vector<float4> cull((size_t)n_chunks * 32, make_float4(0.f, 0.f, 0.f, -INFINITY));
-        std::vector<uint32_t> valid(n_chunks, 0u);
-        const bool no_cull = getenv("RT_B200_NO_CULL") != nullptr;
-        for (uint32_t i = 0; i < n; i++) {
-            cull[i] = cull_entry(d->inverse + (size_t)12 * i, d->kind[i]);
-            if (d->kind[i] != RT_SHAPE_MARCH) {
-                valid[i >> 5] |= 1u << (i & 31);
-                if (no_cull) cull[i].w = INFINITY;
-            }
-        }
-        if ((rc = upload(sc, cull.data(), cull.size(), &sc->ds.cull)) != RT_OK) return bail(rc);
-        if ((rc = upload(sc, valid.data(), valid.size(), &sc->ds.valid)) != RT_OK) return bail(rc);
+        CullTree ct = cull_build(d->inverse, d->kind, (int)n, getenv("RT_B200_NO_CULL") != nullptr,
+                                 getenv("RT_B200_NO_CULL_TREE") != nullptr || getenv("RT_B200_NO_CULL") != nullptr);
+        sc->ds.n_roots = ct.n_roots;
+        sc->ds.n_groups = ct.n_groups;
+        sc->ds.n_flat = ct.n_flat;
+        sc->ds.n_flat_real = ct.n_flat_real;
+        if ((rc = upload(sc, ct.table.data(), ct.table.size(), &sc->ds.ctab)) != RT_OK) return bail(rc);
+        if ((rc = upload(sc, ct.ids.data(), ct.ids.size(), &sc->ds.cids)) != RT_OK) return bail(rc);
+        if ((rc = upload(sc, ct.leaf.data(), ct.leaf.size(), &sc->ds.cull)) != RT_OK) return bail(rc);
+        if ((rc = upload(sc, ct.group_of.data(), ct.group_of.size(), &sc->ds.cull_group)) != RT_OK) return bail(rc);
     }
-    // shared-memory staging: 16 B per (padded) shape + 4 B per chunk
-    sc->smem_bytes = (size_t)n_chunks * 32 * sizeof(float4) + (((size_t)n_chunks * 4 + 15) & ~(size_t)15);
-    sc->use_smem = n > 0 && sc->smem_bytes <= sc->smem_optin;
+    // shared-memory staging: 16 B per table entry
+    sc->smem_bytes = (size_t)sc->ds.ctab_entries() * sizeof(float4);
+    sc->use_smem = n > 0 && sc->smem_bytes > 0 && sc->smem_bytes <= sc->smem_optin;
     if (!sc->use_smem) sc->smem_bytes = 0;
     if (sc->smem_bytes > 48 * 1024) {
         cudaFuncSetAttribute(k_intersect_batch<false, RT_ISECT_BRUTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);

@@ -31,10 +31,31 @@
 // (SURVEY A.6), whatever its distance from the rectangle.  Ray-marched shapes are handled by march_needed.
 // Evidence: RT_ISECT_VERIFY runs the literal loop beside the culled one on every ray and tests every
 // culled (ray, shape) pair exactly; tests/test_gpu_intersect.py requires zero disagreements.
+//
+// Hierarchy (CullTree).  Testing ~490 leaf balls per segment made k_extend FP32-issue bound, so the leaf
+// balls sit under two levels of bounding balls: the culled shapes are clustered spatially (median
+// splits) into GROUPS of <= 16, every 32 consecutive groups share a ROOT.  A lane tests the roots, the 32
+// group balls under each root its line touches, the 16 leaf balls under each group it touches, and runs
+// the exact FP64 test on the surviving leaves.  The visiting order is no longer the shape order; the
+// sequential loop's "later shape wins ties" is applied explicitly (analytic_test).  Shapes that are
+// never culled (Rectangles, ill-conditioned transforms), whose ball is much larger than the typical one
+// (ground spheres) or scenes too small to be worth a tree go to a FLAT list tested as before.
+// A node ball (c, Rn) encloses every member ball: Rn >= |C_i - c| + R_i.  It is rejected iff
+//     |p|^2 > An + 101 * 3B |o|^2,    An = 1.01 (s Rn + sqrt(3B) (|c| + Rn))^2,  s = sqrt(1.1),
+// which implies the member's own (exact-arithmetic) rejection with the FP64 slack it needs:
+//   * (x + y)^2 <= 1.01 x^2 + 101 y^2, so rejection means |p|_computed > s Rn + sqrt(3B)(|c| + Rn + |o|);
+//   * the FP32 error of |p| is delta <= 28u * 2(|c| + |o|) = 3.3e-6 (|c| + |o|) < (sqrt(3B) - sqrt(3e-10))(...),
+//     so the true distance D of the line from c exceeds s Rn + sqrt(E), E = 3e-10 ((|c| + Rn)^2 + |o|^2)
+//     >= the member's FP64 slack 3e-10 (|C_i|^2 + |o|^2);
+//   * the distance from C_i is >= D - |C_i - c| > s R_i + (s - 1)|C_i - c| + sqrt(E) >= s R_i + sqrt(E),
+//     i.e. d_i^2 > 1.1 R_i^2 + E: exactly what the leaf test certifies.  c is chosen FP32-representable.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+
+#include <algorithm>
+#include <vector>
 
 #include "../../include/rt_b200.h"
 
@@ -46,7 +67,8 @@ namespace rt {
 // ---- host: one table entry per shape --------------------------------------------------------------
 // (cx, cy, cz, A): A = 1.1 R^2 + 3B|C|^2 rounded up; A = +inf: never culled; A = -inf: never tested
 // (padding and ray-marched shapes, masked out by the chunk's valid bits anyway).
-inline float4 cull_entry(const double* m, int kind) {
+inline float4 cull_entry(const double* m, int kind, double* radius_out = nullptr) {
+    if (radius_out) *radius_out = INFINITY;
     const float INF = INFINITY;
     float4 never = make_float4(0.f, 0.f, 0.f, INF);
     if (kind == RT_SHAPE_MARCH) return make_float4(0.f, 0.f, 0.f, -INF);
@@ -89,12 +111,165 @@ inline float4 cull_entry(const double* m, int kind) {
     if (!isfinite(A) || !isfinite(C[0]) || !isfinite(C[1]) || !isfinite(C[2])) return never;
     float Af = (float)A;
     if ((double)Af < A) Af = nextafterf(Af, INF);
+    if (radius_out) *radius_out = sqrt(R2);
     return make_float4((float)C[0], (float)C[1], (float)C[2], Af);
+}
+
+// ---- host: the two-level tree over the leaf entries -------------------------------------------------
+#define RT_CULL_GROUP 16        // leaves per group
+#define RT_CULL_ROOT_FANOUT 32  // groups per root
+#define RT_CULL_NODE_RAY 101.0  // node tests use rhs = An + 101 * 3B |o|^2
+
+struct CullTree {
+    // table = [roots: n_roots][groups: n_groups (multiple of 8)][leaves: 16 * n_groups][flat: n_flat (multiple of 8)]
+    std::vector<float4> table;
+    std::vector<int> ids;       // [16 * n_groups + n_flat] shape index of every leaf / flat slot, -1 = padding
+    std::vector<int> group_of;  // [n_shapes] group of a shape, -1 = flat list, -2 = not in the analytic loop
+    std::vector<float4> leaf;   // [n_shapes] the shape's own entry (RT_ISECT_VERIFY)
+    int n_roots = 0, n_groups = 0, n_flat = 0, n_flat_real = 0;
+};
+
+struct CullBall {
+    double c[3], r;
+};
+
+// ball around member balls, FP32-representable centre
+inline CullBall cull_enclose(const std::vector<CullBall>& m) {
+    double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (const CullBall& b : m)
+        for (int k = 0; k < 3; k++) {
+            lo[k] = fmin(lo[k], b.c[k] - b.r);
+            hi[k] = fmax(hi[k], b.c[k] + b.r);
+        }
+    CullBall n;
+    for (int k = 0; k < 3; k++) n.c[k] = (double)(float)(0.5 * (lo[k] + hi[k]));
+    n.r = 0.0;
+    for (const CullBall& b : m) {
+        double dx = b.c[0] - n.c[0], dy = b.c[1] - n.c[1], dz = b.c[2] - n.c[2];
+        n.r = fmax(n.r, sqrt(dx * dx + dy * dy + dz * dz) * (1.0 + 1e-12) + b.r);
+    }
+    n.r *= 1.0 + 1e-9;
+    return n;
+}
+
+inline float4 cull_node_entry(const CullBall& n) {
+    const double s = sqrt(1.1) * (1.0 + 1e-12);
+    const double cn = sqrt(n.c[0] * n.c[0] + n.c[1] * n.c[1] + n.c[2] * n.c[2]);
+    const double x = s * n.r + sqrt(3.0 * RT_CULL_B) * (cn + n.r);
+    const double A = 1.0101 * x * x;  // 1.01 for the inequality above, the rest for the FP32 roundings of An + rhs
+    if (!isfinite(A)) return make_float4(0.f, 0.f, 0.f, INFINITY);
+    float Af = (float)A;
+    if ((double)Af < A) Af = nextafterf(Af, INFINITY);
+    return make_float4((float)n.c[0], (float)n.c[1], (float)n.c[2], Af);
+}
+
+// `inverse`: [n][12] inverse rows, `kind`: [n].  no_cull: every analytic shape goes to the flat list with
+// A = +inf (debug switch RT_B200_NO_CULL); no_tree: flat list only (RT_B200_NO_CULL_TREE).
+inline CullTree cull_build(const double* inverse, const uint8_t* kind, int n, bool no_cull, bool no_tree) {
+    const float4 pad = make_float4(0.f, 0.f, 0.f, -INFINITY);
+    CullTree t;
+    t.group_of.assign(n, -2);
+    t.leaf.assign(n, pad);
+    std::vector<CullBall> ball(n);
+    std::vector<int> tree, flat;
+    std::vector<double> radii;
+    for (int i = 0; i < n; i++) {
+        if (kind[i] == RT_SHAPE_MARCH) continue;
+        double r;
+        t.leaf[i] = cull_entry(inverse + (size_t)12 * i, kind[i], &r);
+        if (no_cull) t.leaf[i].w = INFINITY;
+        ball[i] = CullBall{{(double)t.leaf[i].x, (double)t.leaf[i].y, (double)t.leaf[i].z}, r};
+        // the leaf entry's centre is the FP32-rounded one; the enclosing balls must contain the true ball:
+        // pad the radius by the rounding of the centre
+        if (isfinite(r)) {
+            double cn = fabs(ball[i].c[0]) + fabs(ball[i].c[1]) + fabs(ball[i].c[2]);
+            ball[i].r = r + cn * 1.2e-7;
+            radii.push_back(ball[i].r);
+        }
+    }
+    double typical = 0.0;
+    if (!radii.empty()) {
+        std::nth_element(radii.begin(), radii.begin() + radii.size() / 2, radii.end());
+        typical = radii[radii.size() / 2];
+    }
+    for (int i = 0; i < n; i++) {
+        if (kind[i] == RT_SHAPE_MARCH) continue;
+        const bool finite = isfinite(t.leaf[i].w) && isfinite(ball[i].r);
+        if (no_tree || !finite || ball[i].r > 8.0 * typical) flat.push_back(i);
+        else tree.push_back(i);
+    }
+    if ((int)tree.size() < 4 * RT_CULL_GROUP) {  // not worth a tree
+        flat.insert(flat.end(), tree.begin(), tree.end());
+        std::sort(flat.begin(), flat.end());
+        tree.clear();
+    }
+    // spatial clustering: median split along the widest axis of the centres; the left part takes a whole
+    // number of groups so that groups come out full
+    std::vector<std::vector<int>> groups;
+    struct Rec {
+        static void split(std::vector<int> ids, const std::vector<CullBall>& ball, std::vector<std::vector<int>>& out) {
+            if ((int)ids.size() <= RT_CULL_GROUP) {
+                if (!ids.empty()) out.push_back(ids);
+                return;
+            }
+            double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            for (int i : ids)
+                for (int k = 0; k < 3; k++) {
+                    lo[k] = fmin(lo[k], ball[i].c[k]);
+                    hi[k] = fmax(hi[k], ball[i].c[k]);
+                }
+            int ax = 0;
+            if (hi[1] - lo[1] > hi[ax] - lo[ax]) ax = 1;
+            if (hi[2] - lo[2] > hi[ax] - lo[ax]) ax = 2;
+            std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return ball[a].c[ax] < ball[b].c[ax]; });
+            size_t n_groups = (ids.size() + RT_CULL_GROUP - 1) / RT_CULL_GROUP;
+            size_t left = (n_groups / 2) * RT_CULL_GROUP;
+            split(std::vector<int>(ids.begin(), ids.begin() + left), ball, out);
+            split(std::vector<int>(ids.begin() + left, ids.end()), ball, out);
+        }
+    };
+    Rec::split(tree, ball, groups);
+    t.n_groups = (int)((groups.size() + 7) / 8 * 8);
+    t.n_roots = (t.n_groups + RT_CULL_ROOT_FANOUT - 1) / RT_CULL_ROOT_FANOUT;
+    t.n_flat_real = (int)flat.size();
+    t.n_flat = (int)((flat.size() + 7) / 8 * 8);
+    t.table.assign((size_t)t.n_roots + t.n_groups + (size_t)RT_CULL_GROUP * t.n_groups + t.n_flat, pad);
+    t.ids.assign((size_t)RT_CULL_GROUP * t.n_groups + t.n_flat, -1);
+    float4* roots = t.table.data();
+    float4* grp = roots + t.n_roots;
+    float4* leaves = grp + t.n_groups;
+    float4* fl = leaves + (size_t)RT_CULL_GROUP * t.n_groups;
+    std::vector<CullBall> gball(groups.size());
+    for (size_t g = 0; g < groups.size(); g++) {
+        std::vector<CullBall> m;
+        std::sort(groups[g].begin(), groups[g].end());
+        for (size_t k = 0; k < groups[g].size(); k++) {
+            const int i = groups[g][k];
+            m.push_back(ball[i]);
+            leaves[g * RT_CULL_GROUP + k] = t.leaf[i];
+            t.ids[g * RT_CULL_GROUP + k] = i;
+            t.group_of[i] = (int)g;
+        }
+        gball[g] = cull_enclose(m);
+        grp[g] = cull_node_entry(gball[g]);
+    }
+    for (int r = 0; r < t.n_roots; r++) {
+        std::vector<CullBall> m;
+        for (size_t g = (size_t)r * RT_CULL_ROOT_FANOUT; g < std::min(groups.size(), (size_t)(r + 1) * RT_CULL_ROOT_FANOUT); g++)
+            m.push_back(gball[g]);
+        roots[r] = m.empty() ? pad : cull_node_entry(cull_enclose(m));
+    }
+    for (size_t k = 0; k < flat.size(); k++) {
+        fl[k] = t.leaf[flat[k]];
+        t.ids[(size_t)RT_CULL_GROUP * t.n_groups + k] = flat[k];
+        t.group_of[flat[k]] = -1;
+    }
+    return t;
 }
 
 // ---- device -----------------------------------------------------------------------------------------
 struct CullRay {
-    float ox, oy, oz, dx, dy, dz, rhs0;  // rhs0 = 3B|o|^2
+    float ox, oy, oz, dx, dy, dz, rhs0, rhs1;  // rhs0 = 3B|o|^2 (leaf tests), rhs1 = 101 * 3B|o|^2 (node tests)
 };
 
 __device__ __forceinline__ CullRay make_cull_ray(double ox, double oy, double oz, double dx, double dy, double dz) {
@@ -111,17 +286,20 @@ __device__ __forceinline__ CullRay make_cull_ray(double ox, double oy, double oz
     r.dz = __fmul_rn(z, inv);
     float oo = __fmaf_rn(r.oz, r.oz, __fmaf_rn(r.oy, r.oy, __fmul_rn(r.ox, r.ox)));
     r.rhs0 = __fmul_rn((float)(3.0 * RT_CULL_B), oo);
+    r.rhs1 = __fmul_rn((float)(RT_CULL_NODE_RAY * 3.0 * RT_CULL_B * (1.0 + 1e-6)), oo);
     return r;
 }
 
 // true: the exact test must run.  s = (C, A) from cull_entry.
-__device__ __forceinline__ bool cull_pass(const CullRay& r, float4 s) {
+__device__ __forceinline__ bool cull_pass(const CullRay& r, float4 s, float ray_rhs) {
     float ocx = __fsub_rn(s.x, r.ox), ocy = __fsub_rn(s.y, r.oy), ocz = __fsub_rn(s.z, r.oz);
     float b = __fmaf_rn(ocz, r.dz, __fmaf_rn(ocy, r.dy, __fmul_rn(ocx, r.dx)));
     float px = __fmaf_rn(-b, r.dx, ocx), py = __fmaf_rn(-b, r.dy, ocy), pz = __fmaf_rn(-b, r.dz, ocz);
     float p2 = __fmaf_rn(pz, pz, __fmaf_rn(py, py, __fmul_rn(px, px)));
-    float rhs = __fadd_rn(s.w, r.rhs0);
+    float rhs = __fadd_rn(s.w, ray_rhs);
     return !(p2 > rhs);
 }
+__device__ __forceinline__ bool cull_pass(const CullRay& r, float4 s) { return cull_pass(r, s, r.rhs0); }
+__device__ __forceinline__ bool cull_pass_node(const CullRay& r, float4 s) { return cull_pass(r, s, r.rhs1); }
 
 }  // namespace rt

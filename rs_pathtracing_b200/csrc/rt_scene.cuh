@@ -31,11 +31,15 @@ struct DevScene {
     const int* march_index;
     const double* march_G;      // [n_march] bound of |grad f| over the marching region (inf: never skip)
     const double* march_F;      // [n_march] bound of sum |monomials of f| over the region (rounding of f)
-    // conservative cull table (rt_cull.cuh): one float4 per shape, padded to a multiple of 32, and one
-    // word per chunk of 32 shapes whose bit j says "shape 32*chunk + j takes part in the analytic loop"
-    int n_chunks;
+    // conservative cull tree (rt_cull.cuh, CullTree): ctab = [roots][groups][16 leaves per group][flat list],
+    // cids = shape index of every leaf / flat slot (-1 = padding)
+    int n_roots, n_groups, n_flat, n_flat_real;
+    const float4* ctab;
+    const int* cids;
+    // per shape (RT_ISECT_VERIFY): its own leaf entry and its group (-1 flat list, -2 not analytic)
     const float4* cull;
-    const uint32_t* valid;
+    const int* cull_group;
+    __host__ __device__ int ctab_entries() const { return n_roots + n_groups + RT_CULL_GROUP * n_groups + n_flat; }
 };
 
 // optional work counters (rt_stats); enabled per launch by a template flag
@@ -188,16 +192,18 @@ __device__ __forceinline__ void analytic_test(const DevScene& S, int i, D3 ro, D
     if (kind == RT_SHAPE_SPHERE) ok = sphere_candidate(o, d, min_t, best, t, &degenerate);
     else if (kind == RT_SHAPE_CUBE) ok = cube_candidate(o, d, min_t, best, t);
     else ok = rect_candidate(S.params + RT_SHAPE_PARAMS * i, o, d, min_t, best, t);
-    if (ok) {
+    if (ok) {  // ok means t <= best (or a degenerate candidate); shapes are not visited in index order, so the
+               // loop's "later shape wins ties" is explicit
         if (t != t) degenerate = true;
-        best = t;
-        winner = i;
+        if (t < best || i > winner || degenerate) {
+            best = t;
+            winner = i;
+        }
     }
 }
 
-// step 1.  Returns true when the ray is degenerate.  Shapes are visited in index order, 32 at a time:
-// the FP32 cull (rt_cull.cuh) of a whole chunk first, with every lane of the warp busy, then each lane
-// runs the exact test on its own survivors.
+// step 1.  Returns true when the ray is degenerate.  FP32 culling first (rt_cull.cuh): the flat list,
+// then roots -> groups -> leaves of the tree; each lane runs the exact test on its own survivors.
 template <bool COUNT, bool SMEM>
 __device__ __forceinline__ bool analytic_nearest_impl(const DevScene& S, D3 ro, D3 rd, double min_t, double max_t,
                                                       double& best, int& winner, DevCounters& c) {
@@ -205,21 +211,46 @@ __device__ __forceinline__ bool analytic_nearest_impl(const DevScene& S, D3 ro, 
     winner = -1;
     bool degenerate = false;
     const CullRay cr = make_cull_ray(ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
-    const float4* cull = SMEM ? reinterpret_cast<const float4*>(rt_smem_raw) : S.cull;
-    const uint32_t* vmask = SMEM ? reinterpret_cast<const uint32_t*>(rt_smem_raw + (size_t)512 * S.n_chunks) : S.valid;
-    for (int ch = 0; ch < S.n_chunks; ch++) {
-        const float4* tab = cull + 32 * ch;
+    const float4* roots = SMEM ? reinterpret_cast<const float4*>(rt_smem_raw) : S.ctab;
+    const float4* groups = roots + S.n_roots;
+    const float4* leaves = groups + S.n_groups;
+    const float4* flat = leaves + RT_CULL_GROUP * S.n_groups;
+    const int* flat_ids = S.cids + RT_CULL_GROUP * S.n_groups;
+    for (int f0 = 0; f0 < S.n_flat; f0 += 32) {
+        const int nf = min(32, S.n_flat - f0);  // a multiple of 8
         uint32_t mask = 0;
-#pragma unroll
-        for (int j = 0; j < 32; j++)
-            if (cull_pass(cr, tab[j])) mask |= 1u << j;
-        const uint32_t valid = vmask[ch];
-        mask &= valid;
-        if (COUNT) c.cull_tests += __popc(valid);
+#pragma unroll 8
+        for (int j = 0; j < nf; j++)
+            if (cull_pass(cr, flat[f0 + j])) mask |= 1u << j;
         while (mask) {
             const int j = __ffs(mask) - 1;
             mask &= mask - 1;
-            analytic_test<COUNT>(S, 32 * ch + j, ro, rd, min_t, best, winner, degenerate, c);
+            analytic_test<COUNT>(S, __ldg(flat_ids + f0 + j), ro, rd, min_t, best, winner, degenerate, c);
+        }
+    }
+    if (COUNT) c.cull_tests += S.n_flat_real + S.n_roots;
+    for (int r = 0; r < S.n_roots; r++) {
+        if (!cull_pass_node(cr, roots[r])) continue;
+        const int g0 = RT_CULL_ROOT_FANOUT * r;
+        const int ng = min(RT_CULL_ROOT_FANOUT, S.n_groups - g0);  // a multiple of 8
+        uint32_t gmask = 0;
+#pragma unroll 8
+        for (int j = 0; j < ng; j++)
+            if (cull_pass_node(cr, groups[g0 + j])) gmask |= 1u << j;
+        if (COUNT) c.cull_tests += ng + RT_CULL_GROUP * __popc(gmask);
+        while (gmask) {
+            const int g = g0 + __ffs(gmask) - 1;
+            gmask &= gmask - 1;
+            const float4* lv = leaves + RT_CULL_GROUP * g;
+            uint32_t mask = 0;
+#pragma unroll
+            for (int j = 0; j < RT_CULL_GROUP; j++)
+                if (cull_pass(cr, lv[j])) mask |= 1u << j;
+            while (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1;
+                analytic_test<COUNT>(S, __ldg(S.cids + RT_CULL_GROUP * g + j), ro, rd, min_t, best, winner, degenerate, c);
+            }
         }
     }
     return degenerate;

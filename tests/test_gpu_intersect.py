@@ -319,8 +319,10 @@ def test_cull_far_and_ill_conditioned_shapes():
     assert len(set(np.unique(want["index"])) - {-1}) >= 6   # (nearly) every shape is hit by some ray
 
 
-def test_cull_removes_most_exact_tests():
-    """on cornell_box (481 small spheres in one corner) the exact FP64 test runs for a few percent of the pairs"""
+def test_cull_tree_removes_most_tests():
+    """on cornell_box the 481 small spheres sit in one corner under one root ball: a segment costs a few
+    dozen FP32 ball tests (flat list + root + the groups / leaves its line touches) instead of ~490, and
+    the exact FP64 test runs for a few percent of the (segment, shape) pairs"""
     sc = rt.Scene.from_file(scene_path("cornell_box.json"), random_spheres_seed=1)
     rays = scene_rays(sc, 1 << 14, seed=21)
     sc.set_counters(True)
@@ -328,5 +330,41 @@ def test_cull_removes_most_exact_tests():
     sc.closest_hit(rays, mode=rt.RT_ISECT_FAST, want=("index",))
     st = sc.stats()
     sc.set_counters(False)
-    assert st.cull_tests >= len(rays) * 480
-    assert st.shape_tests * 10 < st.cull_tests, (st.shape_tests, st.cull_tests)
+    pairs = len(rays) * (sc.shape_count - 1)
+    assert st.cull_tests >= len(rays) * 8           # the never-culled shapes and the root are always looked at
+    assert st.cull_tests * 4 < pairs, (st.cull_tests, pairs)
+    assert st.shape_tests * 20 < pairs, (st.shape_tests, pairs)
+
+
+@pytest.mark.parametrize("n_spheres,spread,offset", [(40, 3.0, 0.0), (700, 30.0, 0.0), (1500, 8.0, 0.0),
+                                                     (300, 4.0, 2e5)])
+def test_cull_tree_sizes(n_spheres, spread, offset):
+    """scenes below the tree threshold (flat list only), with more than one root (> 512 tree shapes) and
+    with heavily overlapping groups, and a cluster 3.7e5 away from the origin (FP32 cancellation in the node
+    tests): FAST == BRUTE == oracle bit for bit, and RT_ISECT_VERIFY finds no false cull at any level"""
+    rng = np.random.default_rng(n_spheres)
+    shapes = []
+    off = np.array([offset, 1.5 * offset, -2.5 * offset])
+    for k in range(n_spheres):
+        c = rng.uniform(-spread, spread, 3) + off
+        r = float(rng.uniform(0.05, 0.6))
+        kind = "Cube" if k % 7 == 0 else "Sphere"
+        shapes.append({"type": kind, "name": f"s{k}", "material": "M",
+                       "transform": {"translate": c.tolist(), "rotate": rng.uniform(-90, 90, 3).tolist(),
+                                     "scale": [r, r * float(rng.uniform(0.5, 1.5)), r]}})
+    shapes.append({"type": "Sphere", "name": "ground", "material": "M",
+                   "transform": {"translate": [0, -1000 - spread, 0], "rotate": [0, 0, 0], "scale": [1000, 1000, 1000]}})
+    data = dict(TRIO)
+    data["shapes"] = shapes
+    import json
+    sc = rt.Scene.from_json(json.dumps(data), add_random_spheres=False)
+    o = rng.uniform(-1.5 * spread, 1.5 * spread, (6000, 3)) + off
+    o[::3] = rng.uniform(-1.5 * spread, 1.5 * spread, (2000, 3))   # a third of the rays start near the world origin
+    tgt = rng.uniform(-spread, spread, (6000, 3)) + off
+    rays = rt.make_rays(o, tgt - o)
+    want = check_parity(sc, rays)
+    assert (want["index"] >= 0).mean() > (0.3 if offset == 0.0 else 0.05)
+    sc.reset_stats()
+    sc.closest_hit(rays, mode=rt.RT_ISECT_VERIFY, want=("index",))
+    st = sc.stats()
+    assert st.verify_rays == 0 and st.verify_false_culls == 0
