@@ -54,7 +54,18 @@ __device__ __forceinline__ double advance_exact(double a, double s, long long m)
     const int sexp = (int)(sb >> 52);
     const long long Ms = (sb & MANT) | (1LL << 52);
     const bool s_neg = s < 0.0;
+    // Near zero (|a| < 32 |s|) a binade holds fewer than 32 steps: walking it literally (one DADD per step)
+    // is cheaper than the per-binade bookkeeping below, and an accumulator that changes sign would
+    // otherwise pay that bookkeeping for every binade between |s| and its starting magnitude, twice.
+    const double near = 32.0 * fabs(s);
     while (m > 0) {
+        if (fabs(a) < near) {
+            do {
+                a = a + s;
+                m--;
+            } while (m > 0 && fabs(a) < near);
+            continue;
+        }
         const long long bits = __double_as_longlong(a);
         const int exp = (int)((bits >> 52) & 0x7ff);
         const long long mant = bits & MANT;
@@ -293,7 +304,17 @@ struct Marcher {
     // Try one exact multi-step jump from the current sample.  Afterwards either the state is m
     // iterations further (the reference would have executed exactly `r = next` in each of them), or
     // nothing changed except cooldown / skip_ok, so that phase() now answers RT_PHASE_LITERAL.
-    __device__ __forceinline__ void attempt() {
+    // The attempt is split in three so that k_march can run the middle part -- the exact advance of the
+    // four accumulators t, p.x, p.y, p.z, whose loops over binades are the most divergent code of the
+    // marcher -- cooperatively, one accumulator per lane (coop_advance in rt_core.cu):
+    //   attempt_plan():  how many iterations m can provably be skipped (0: none; cooldown is set)
+    //   [advance t, p by m steps exactly]
+    //   attempt_land():  the reference's `r = next` at the landing sample + the model self-check
+    struct Plan {
+        double s[DEG + 1];  // Taylor shift of the model to the current sample
+        double M;           // the uncertainty band of this jump
+    };
+    __device__ __forceinline__ long long attempt_plan(Plan& pl) {
         if (!have_poly) {
             // expand around the current sample (the first one); covers every later sample of the ray
             double tau_hi = (end - t) + 4.0 * step0;
@@ -301,11 +322,11 @@ struct Marcher {
             n += 2;  // cost of the expansion in evaluation-equivalents (statistics only)
             have_poly = true;
         }
+        double(&s)[DEG + 1] = pl.s;
         const double abs_step = fabs(step);
         const double dir = step > 0.0 ? 1.0 : -1.0;
         const double tau = t - P.t0;
         // Taylor shift to the current sample: g(tau + sigma) = sum s[k] sigma^k
-        double s[DEG + 1];
 #pragma unroll
         for (int k = 0; k <= DEG; k++) s[k] = P.c[k];
 #pragma unroll
@@ -323,6 +344,7 @@ struct Marcher {
         const double ex = p.x - fma(tau, d.x, P.p0.x), ey = p.y - fma(tau, d.y, P.p0.y),
                      ez = p.z - fma(tau, d.z, P.p0.z);
         const double M = RT_MARCH_SAFETY * G * (fabs(ex) + fabs(ey) + fabs(ez)) + m_max * P.drift1 + P.err0;
+        pl.M = M;
         // furthest sigma in [0, span] such that the whole stretch is provably inside {|g| >= M, same sign}:
         // hops of length 2b / (|g'| + sqrt(g'^2 + 2 B2 b)), b = |g| - M, B2 >= max |g''| over the span.
         // The hop length is a lower bound, so it is computed in FP32 (rounded toward safety, shortened 1 %).
@@ -360,36 +382,43 @@ struct Marcher {
             dg = dv;
         }
         const double mf = sig / abs_step * (1.0 - 1e-9) - 2.0;
-        if (mf >= (double)RT_MARCH_MIN_JUMP) {
-            const long long m = (long long)fmin(mf, 1.0e15);
-            const double st = t;
-            const D3 sp = p;
-            t = advance_exact(t, step, m);
-            p.x = advance_exact(p.x, sd.x, m);
-            p.y = advance_exact(p.y, sd.y, m);
-            p.z = advance_exact(p.z, sd.z, m);
-            const double land = surface_func<KIND>(q, p);  // the reference's `r = next` at the landing sample
-            n++;
-            if (PROF) prof[2]++;
-            const double x = t - st;
-            double gp = s[DEG];
+        if (mf >= (double)RT_MARCH_MIN_JUMP) return (long long)fmin(mf, 1.0e15);
+        // inside the |g| < M zone or next to a range limit: plain steps, retry later
+        cooldown = backoff;
+        backoff = min(backoff * 2, 64);
+        return 0;
+    }
+    // nt / np: t and p after m more iterations (advance_exact of t by step and of p by sd)
+    __device__ __forceinline__ void attempt_land(const Plan& pl, double nt, D3 np) {
+        const double land = surface_func<KIND>(q, np);  // the reference's `r = next` at the landing sample
+        n++;
+        if (PROF) prof[2]++;
+        const double x = nt - t;
+        double gp = pl.s[DEG];
 #pragma unroll
-            for (int k = DEG - 1; k >= 0; k--) gp = fma(gp, x, s[k]);
-            // self-check: the landing value must be what the polynomial predicts and keep the sign
-            const bool same_sign = ((land > 0.0) == (r > 0.0)) && land != 0.0;
-            if (same_sign && fabs(land - gp) <= 0.25 * M && fabs(land) >= 0.5 * M) {
-                r = land;
-                backoff = 4;
-                return;
-            }
-            t = st;  // the model does not describe this ray: undo and finish it with the plain loop
-            p = sp;
-            skip_ok = false;
-        } else {
-            // inside the |g| < M zone or next to a range limit: plain steps, retry later
-            cooldown = backoff;
-            backoff = min(backoff * 2, 64);
+        for (int k = DEG - 1; k >= 0; k--) gp = fma(gp, x, pl.s[k]);
+        // self-check: the landing value must be what the polynomial predicts and keep the sign
+        const bool same_sign = ((land > 0.0) == (r > 0.0)) && land != 0.0;
+        if (same_sign && fabs(land - gp) <= 0.25 * pl.M && fabs(land) >= 0.5 * pl.M) {
+            t = nt;
+            p = np;
+            r = land;
+            backoff = 4;
+            return;
         }
+        skip_ok = false;  // the model does not describe this ray: finish it with the plain loop
+    }
+    // the serial form (fused kernels, rt_intersect_batch)
+    __device__ __forceinline__ void attempt() {
+        Plan pl;
+        const long long m = attempt_plan(pl);
+        if (m <= 0) return;
+        const double nt = advance_exact(t, step, m);
+        D3 np;
+        np.x = advance_exact(p.x, sd.x, m);
+        np.y = advance_exact(p.y, sd.y, m);
+        np.z = advance_exact(p.z, sd.z, m);
+        attempt_land(pl, nt, np);
     }
 
     // the reference's literal step (ray_marching.rs:37-51)

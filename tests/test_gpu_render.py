@@ -189,9 +189,9 @@ def test_tonemap_matches_the_bins_formula():
 
 
 def test_work_counters_match_oracle():
-    """the instrumented kernels see the same segments and (segment, shape) pairs as the oracle's
-    brute-force loop; most pairs are settled by the FP32 cull, the exact FP64 test runs on the rest,
-    and the number of march evaluations is much smaller (exact skipping)"""
+    """the instrumented kernels see the same segments as the oracle's brute-force loop; most (segment,
+    shape) pairs are settled by the FP32 cull tree without even being looked at, the exact FP64 test runs
+    on a small rest, and the number of march evaluations is much smaller (exact skipping)"""
     sc = rt.Scene.from_file(scene_path("spheres.json"), random_spheres_seed=1)
     cam = sc.camera()
     sc.set_counters(True)
@@ -203,7 +203,7 @@ def test_work_counters_match_oracle():
     assert st.paths == 32 * 24 * 2
     n_march = int((sc.shape_kinds() == 3).sum())
     assert st.segments == c["segments"]
-    assert st.cull_tests + st.segments * n_march == c["shape_tests"]
+    assert st.segments * 8 < st.cull_tests < c["shape_tests"] // 2
     assert st.segments * n_march < st.shape_tests < c["shape_tests"] // 4
     assert 0 < st.march_steps < c["march_steps"]
     assert st.kernel_launches > 0
