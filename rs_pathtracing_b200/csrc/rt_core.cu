@@ -144,6 +144,12 @@ __device__ __forceinline__ void flush_counters(const DevCounters& c, DevCounters
 __device__ __noinline__ unsigned long long count_false_culls(const DevScene& S, D3 ro, D3 rd, double min_t) {
     const CullRay cr = make_cull_ray(ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
     unsigned long long bad = 0;
+    for (int k = 0; k < S.n_march; k++) {  // a culled marching bound must be a miss of intersect_bound
+        if (cull_pass(cr, S.march_cull[k])) continue;
+        const int i = S.march_index[k];
+        double start, end;
+        if (march_bound(S.params + RT_SHAPE_PARAMS * i, xf_point(S.inv + 12 * i, ro), xf_vector(S.inv + 12 * i, rd), start, end)) bad++;
+    }
     for (int i = 0; i < S.n_shapes; i++) {
         const int g = S.cull_group[i];
         if (g == -2) continue;
@@ -369,16 +375,18 @@ k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
             D3 rd = mk(in.dx[i], in.dy[i], in.dz[i]);
             double best;
             int winner;
-            degenerate = analytic_nearest<COUNT>(S, st, ro, rd, 0.001, INFINITY, best, winner, c);
+            const CullRay cr = make_cull_ray(ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
+            degenerate = analytic_nearest<COUNT>(S, st, cr, ro, rd, 0.001, INFINITY, best, winner, c);
             if (!degenerate) {
                 for (int k = 0; k < S.n_march; k++) {
+                    if (!cull_pass(cr, S.march_cull[k])) continue;  // the line misses the marching bound
                     const int si = S.march_index[k];
                     D3 o, d;
                     double start, end_c;
                     if (march_needed(S, S.inv + 12 * si, S.params + RT_SHAPE_PARAMS * si, ro, rd, best, o, d, start, end_c))
                         mask |= 1u << k;
                 }
-                if (COUNT) c.shape_tests += S.n_march;
+                if (COUNT) c.cull_tests += S.n_march;
             }
             if (COUNT) c.segments++;
             hq.t[i] = best;
@@ -1220,6 +1228,15 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
         if (k < 32) sc->kind_mask[(int)q[0]] |= 1u << k;
     }
     if ((rc = upload(sc, march_F.data(), march_F.size(), &sc->ds.march_F)) != RT_OK) return bail(rc);
+    std::vector<float4> march_cull(march.size());
+    for (size_t k = 0; k < march.size(); k++) {
+        const double* q = d->params + (size_t)march[k] * RT_SHAPE_PARAMS;
+        double radius[3] = {q[7], q[7], q[7]};
+        if ((int)q[0] == RT_SURF_HEART) { radius[0] = 1.45; radius[1] = 1.45 / 2.05; radius[2] = 1.45; }  // march_bound
+        march_cull[k] = cull_entry_march_bound(d->inverse + (size_t)12 * march[k], radius);
+        if (getenv("RT_B200_NO_CULL")) march_cull[k].w = INFINITY;
+    }
+    if ((rc = upload(sc, march_cull.data(), march_cull.size(), &sc->ds.march_cull)) != RT_OK) return bail(rc);
 
     // conservative cull tree (rt_cull.cuh)
     {

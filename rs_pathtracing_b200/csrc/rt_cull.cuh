@@ -115,6 +115,18 @@ inline float4 cull_entry(const double* m, int kind, double* radius_out = nullptr
     return make_float4((float)C[0], (float)C[1], (float)C[2], Af);
 }
 
+// Bound of a ray-marched shape (ShapeFunction::intersect_bound, ray_marching.rs:135-145, 213-225): the
+// reference solves the unit-sphere quadratic on o / radius, d / radius, i.e. a Sphere test with the inverse
+// rows scaled by 1 / radius (componentwise for the Heart's ellipsoid).  A negative discriminant there means
+// None for every max_t, so the same entry as for a Sphere applies (march_needed is skipped when the line
+// misses the ball).  `radius`: the three object-space radii.
+inline float4 cull_entry_march_bound(const double* m, const double radius[3]) {
+    double ms[12];
+    for (int r = 0; r < 3; r++)
+        for (int k = 0; k < 4; k++) ms[4 * r + k] = m[4 * r + k] / radius[r];
+    return cull_entry(ms, RT_SHAPE_SPHERE);
+}
+
 // ---- host: the two-level tree over the leaf entries -------------------------------------------------
 #define RT_CULL_GROUP 16        // leaves per group
 #define RT_CULL_ROOT_FANOUT 32  // groups per root

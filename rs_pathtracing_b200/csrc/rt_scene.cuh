@@ -31,6 +31,7 @@ struct DevScene {
     const int* march_index;
     const double* march_G;      // [n_march] bound of |grad f| over the marching region (inf: never skip)
     const double* march_F;      // [n_march] bound of sum |monomials of f| over the region (rounding of f)
+    const float4* march_cull;   // [n_march] conservative ball around the marching bound (rt_cull.cuh)
     // conservative cull tree (rt_cull.cuh, CullTree): ctab = [roots][groups][16 leaves per group][flat list],
     // cids = shape index of every leaf / flat slot (-1 = padding)
     int n_roots, n_groups, n_flat, n_flat_real;
@@ -177,21 +178,44 @@ __device__ __forceinline__ void analytic_test(const DevScene& S, int i, D3 ro, D
                                               int& winner, bool& degenerate, DevCounters& c) {
     const int kind = S.kind[i];
     const double2* mp = reinterpret_cast<const double2*>(S.inv + 12 * i);  // rows are 96 B, 16-byte aligned
-    double m[12];
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-        double2 v = __ldg(mp + k);
-        m[2 * k] = v.x;
-        m[2 * k + 1] = v.y;
-    }
-    D3 o = xf_point(m, ro);
-    D3 d = xf_vector(m, rd);
     if (COUNT) c.shape_tests++;
     double t;
     bool ok;
-    if (kind == RT_SHAPE_SPHERE) ok = sphere_candidate(o, d, min_t, best, t, &degenerate);
-    else if (kind == RT_SHAPE_CUBE) ok = cube_candidate(o, d, min_t, best, t);
-    else ok = rect_candidate(S.params + RT_SHAPE_PARAMS * i, o, d, min_t, best, t);
+    if (kind == RT_SHAPE_RECTANGLE) {
+        // Rectangle::ray_intersect (shapes/mod.rs:181-190) needs only o.z, d.z to reject most rays: row 2 of the
+        // inverse first, the other rows when x = -o.z / d.z is in range (same operations, same order as
+        // xf_point / xf_vector + rect_candidate, so the same bits).
+        const double2 r20 = __ldg(mp + 4), r21 = __ldg(mp + 5);
+        const double oz = ro.x * r20.x + ro.y * r20.y + ro.z * r21.x + r21.y;
+        const double dz = rd.x * r20.x + rd.y * r20.y + rd.z * r21.x;
+        // o.z and d.z finite, non-zero and of the same sign: x = -o.z / d.z is negative (or -0), below min_t > 0
+        const double sgn = oz * dz;
+        if (min_t > 0.0 && sgn > 0.0 && sgn < INFINITY) return;
+        const double x = -oz / dz;
+        if (x < min_t || x > best) return;
+        const double2 r00 = __ldg(mp), r01 = __ldg(mp + 1), r10 = __ldg(mp + 2), r11 = __ldg(mp + 3);
+        const double ox = ro.x * r00.x + ro.y * r00.y + ro.z * r01.x + r01.y;
+        const double oy = ro.x * r10.x + ro.y * r10.y + ro.z * r11.x + r11.y;
+        const double dx = rd.x * r00.x + rd.y * r00.y + rd.z * r01.x;
+        const double dy = rd.x * r10.x + rd.y * r10.y + rd.z * r11.x;
+        const double* q = S.params + RT_SHAPE_PARAMS * i;
+        const double px = ox + dx * x, py = oy + dy * x;
+        if (px < q[0] || px > q[2] || py < q[1] || py > q[3]) return;
+        t = x;
+        ok = true;
+    } else {
+        double m[12];
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            double2 v = __ldg(mp + k);
+            m[2 * k] = v.x;
+            m[2 * k + 1] = v.y;
+        }
+        D3 o = xf_point(m, ro);
+        D3 d = xf_vector(m, rd);
+        if (kind == RT_SHAPE_SPHERE) ok = sphere_candidate(o, d, min_t, best, t, &degenerate);
+        else ok = cube_candidate(o, d, min_t, best, t);
+    }
     if (ok) {  // ok means t <= best (or a degenerate candidate); shapes are not visited in index order, so the
                // loop's "later shape wins ties" is explicit
         if (t != t) degenerate = true;
@@ -205,12 +229,11 @@ __device__ __forceinline__ void analytic_test(const DevScene& S, int i, D3 ro, D
 // step 1.  Returns true when the ray is degenerate.  FP32 culling first (rt_cull.cuh): the flat list,
 // then roots -> groups -> leaves of the tree; each lane runs the exact test on its own survivors.
 template <bool COUNT, bool SMEM>
-__device__ __forceinline__ bool analytic_nearest_impl(const DevScene& S, D3 ro, D3 rd, double min_t, double max_t,
-                                                      double& best, int& winner, DevCounters& c) {
+__device__ __forceinline__ bool analytic_nearest_impl(const DevScene& S, const CullRay& cr, D3 ro, D3 rd, double min_t,
+                                                      double max_t, double& best, int& winner, DevCounters& c) {
     best = max_t;
     winner = -1;
     bool degenerate = false;
-    const CullRay cr = make_cull_ray(ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
     const float4* roots = SMEM ? reinterpret_cast<const float4*>(rt_smem_raw) : S.ctab;
     const float4* groups = roots + S.n_roots;
     const float4* leaves = groups + S.n_groups;
@@ -256,10 +279,10 @@ __device__ __forceinline__ bool analytic_nearest_impl(const DevScene& S, D3 ro, 
     return degenerate;
 }
 template <bool COUNT>
-__device__ __forceinline__ bool analytic_nearest(const DevScene& S, const Staged& st, D3 ro, D3 rd, double min_t,
-                                                 double max_t, double& best, int& winner, DevCounters& c) {
-    if (st.smem) return analytic_nearest_impl<COUNT, true>(S, ro, rd, min_t, max_t, best, winner, c);
-    return analytic_nearest_impl<COUNT, false>(S, ro, rd, min_t, max_t, best, winner, c);
+__device__ __forceinline__ bool analytic_nearest(const DevScene& S, const Staged& st, const CullRay& cr, D3 ro, D3 rd,
+                                                 double min_t, double max_t, double& best, int& winner, DevCounters& c) {
+    if (st.smem) return analytic_nearest_impl<COUNT, true>(S, cr, ro, rd, min_t, max_t, best, winner, c);
+    return analytic_nearest_impl<COUNT, false>(S, cr, ro, rd, min_t, max_t, best, winner, c);
 }
 
 // does marched shape number k (position in S.march_index) have to be marched for this ray, given the
@@ -281,9 +304,11 @@ __device__ __forceinline__ bool march_needed(const DevScene& S, const double* m,
 
 // step 2 for one marched shape.  Returns true when the ray turned out degenerate.
 template <bool COUNT>
-__device__ __forceinline__ bool march_shape_update(const DevScene& S, const double* s_inv, int k, D3 ro, D3 rd,
-                                                   double min_t, double max_t, double& best, int& winner,
+__device__ __forceinline__ bool march_shape_update(const DevScene& S, const CullRay& cr, const double* s_inv, int k,
+                                                   D3 ro, D3 rd, double min_t, double max_t, double& best, int& winner,
                                                    DevCounters& c) {
+    if (COUNT) c.cull_tests++;
+    if (!cull_pass(cr, S.march_cull[k])) return false;  // the line misses the marching bound: None
     const int i = S.march_index[k];
     const double* q = S.params + RT_SHAPE_PARAMS * i;
     D3 o, d;
@@ -314,9 +339,10 @@ __device__ __forceinline__ void nearest_hit_fast(const DevScene& S, const Staged
                                                  double max_t, double& best_t, int& best_i, DevCounters& c) {
     double best;
     int winner;
-    bool degenerate = analytic_nearest<COUNT>(S, st, ro, rd, min_t, max_t, best, winner, c);
+    const CullRay cr = make_cull_ray(ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
+    bool degenerate = analytic_nearest<COUNT>(S, st, cr, ro, rd, min_t, max_t, best, winner, c);
     for (int k = 0; k < S.n_march && !degenerate; k++)
-        degenerate = march_shape_update<COUNT>(S, S.inv, k, ro, rd, min_t, max_t, best, winner, c);
+        degenerate = march_shape_update<COUNT>(S, cr, S.inv, k, ro, rd, min_t, max_t, best, winner, c);
     if (degenerate) {
         nearest_hit_brute<COUNT>(S, ro, rd, min_t, max_t, best_t, best_i, c);
         return;

@@ -17,6 +17,55 @@ from . import api
 from ._ffi import Camera
 
 
+def owned_pixel_coords(width: int, height: int, tile: int, world: int, shard: int):
+    """Host mirror of ShardMap::pixel_of (csrc/rt_core.cu): the pixels shard `shard` owns, in its
+    tile-packed "owned order" (tile k -> shard k % world, tiles row-major, row-major inside a tile, border
+    tiles padded to tile*tile).  Returns (x, y, valid) int arrays of length rt_shard_float4_count."""
+    if world == 1:   # whole image: one "tile" per row, owned order == x + y*width
+        tw, th = width, 1
+    else:
+        tw = th = tile
+    tiles_x, tiles_y = (width + tw - 1) // tw, (height + th - 1) // th
+    ks = np.arange(shard, tiles_x * tiles_y, world)
+    tx, ty = ks % tiles_x, ks // tiles_x
+    r = np.arange(tw * th)
+    x = (tx[:, None] * tw + r[None, :] % tw).reshape(-1)
+    y = (ty[:, None] * th + r[None, :] // tw).reshape(-1)
+    return x, y, (x < width) & (y < height)
+
+
+def exchange_to_rank0(dist, mine, counts, rank: int, world: int, bufs=None):
+    """The one exchange of a frame: every rank's tile-packed float4 accumulator to rank 0 (grouped
+    send/recv: shard sizes can differ by one tile, so this is not dist.gather).  Returns the list of the
+    `world` shard tensors on rank 0, None elsewhere.  Backend-agnostic (NCCL on GPUs, gloo in the CPU tests)."""
+    import torch
+    if world == 1:
+        return [mine]
+    ops = []
+    if rank == 0:
+        if bufs is None or [b.shape[0] for b in bufs] != list(counts):
+            bufs = [torch.empty((c, 4), dtype=torch.float32, device=mine.device) for c in counts]
+        bufs[0].copy_(mine)
+        for s in range(1, world):
+            ops.append(dist.P2POp(dist.irecv, bufs[s], s))
+    else:
+        ops.append(dist.P2POp(dist.isend, mine, 0))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return bufs if rank == 0 else None
+
+
+def assemble_host(shards, width: int, height: int, tile: int, world: int) -> np.ndarray:
+    """numpy restatement of k_assemble: gathered tile-packed (n, 4) shards -> (h, w, 3) mean radiance"""
+    frame = np.zeros((height, width, 3), dtype=np.float64)
+    for s, buf in enumerate(shards):
+        b = np.asarray(buf, dtype=np.float64)
+        x, y, ok = owned_pixel_coords(width, height, tile, world, s)
+        frame[y[ok], x[ok]] = b[ok, :3] / b[ok, 3:4]
+    return frame
+
+
 class DistributedRenderer:
     """Renderer-trait-shaped front end for N ranks.  Every rank constructs it with the same scene and
     calls render(); rank 0 returns the full frame (numpy, h x w x 3 float64), the others None."""
@@ -46,28 +95,13 @@ class DistributedRenderer:
         api.render_start(self.dev_scene, camera, p)
         ptr, n = api.render_device_result(self.dev_scene)   # waits for this shard's kernels
         mine = torch.as_tensor(api.DevicePointer(ptr, (n, 4), "<f4", owner=self), device=f"cuda:{self.device}")
-        if self.world == 1:
-            shards = [mine]
-        else:
-            counts = [api.shard_float4_count(p, s) for s in range(self.world)]
-            if self.rank == 0:
-                if self._gather_bufs is None or [b.shape[0] for b in self._gather_bufs] != counts:
-                    self._gather_bufs = [torch.empty((c, 4), dtype=torch.float32, device=mine.device) for c in counts]
-                shards = self._gather_bufs
-            # one exchange per frame: every rank's tile-packed accumulator to rank 0 over NVLink.
-            # Shard sizes can differ by one tile, so this is grouped send/recv rather than dist.gather.
-            ops = []
-            if self.rank == 0:
-                shards[0].copy_(mine)
-                for s in range(1, self.world):
-                    ops.append(dist.P2POp(dist.irecv, shards[s], s))
-            else:
-                ops.append(dist.P2POp(dist.isend, mine, 0))
-            if ops:
-                for req in dist.batch_isend_irecv(ops):
-                    req.wait()
-            if self.rank != 0:
-                return None
+        counts = [api.shard_float4_count(p, s) for s in range(self.world)]
+        # one exchange per frame: every rank's tile-packed accumulator to rank 0 over NVLink
+        shards = exchange_to_rank0(dist, mine, counts, self.rank, self.world, self._gather_bufs)
+        if shards is None:
+            return None
+        if self.world > 1:
+            self._gather_bufs = shards
         if self._frame is None or tuple(self._frame.shape) != (height, width, 3):
             self._frame = torch.empty((height, width, 3), dtype=torch.float64, device=mine.device)
         api.assemble_frame(self.dev_scene, self._params(width, height, samples_number, 0),

@@ -1,0 +1,74 @@
+"""Host logic of the N > 1 path on CPU: world size 2, gloo backend.
+
+The pixels themselves need a GPU (tests/test_gpu_render.py::test_sharded_render_assembles_to_the_unsharded_frame
+renders the shards on one device); what runs here is everything around them -- which tiles a rank owns
+(host mirror of ShardMap::pixel_of, checked against the C ABI's rt_shard_float4_count), the single
+rank-0 exchange with unequal shard sizes (the same function the NCCL path calls), and the de-interleave
+(numpy restatement of k_assemble)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from rs_pathtracing_b200 import api
+from rs_pathtracing_b200.distributed import assemble_host, exchange_to_rank0, owned_pixel_coords
+
+
+def _pixel_value(x, y):
+    return np.stack([x * 1.0 + 0.25, y * 2.0 + 0.5, (x * 7 + y * 13) % 101 + 1.0], axis=-1)
+
+
+def _worker(rank, world, port, width, height, tile, spp, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x, y, ok = owned_pixel_coords(width, height, tile, world, rank)
+        p = api.render_params(width, height, spp, 8, 0, world, rank, tile=tile)
+        counts = [api.shard_float4_count(p, s) for s in range(world)]
+        assert len(x) == counts[rank]
+        mine = np.zeros((counts[rank], 4), dtype=np.float32)   # (sum rgb, samples); padding stays 0
+        mine[ok, :3] = (_pixel_value(x[ok], y[ok]) * spp).astype(np.float32)
+        mine[ok, 3] = spp
+        shards = exchange_to_rank0(dist, torch.from_numpy(mine), counts, rank, world)
+        if rank == 0:
+            frame = assemble_host([t.numpy() for t in shards], width, height, tile, world)
+            np.save(out_path, frame)
+        else:
+            assert shards is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("width,height,tile", [(96, 64, 32), (100, 70, 32), (33, 17, 8)])
+def test_two_rank_gather_and_assemble(tmp_path, width, height, tile):
+    world, spp = 2, 4
+    out = str(tmp_path / "frame.npy")
+    mp.spawn(_worker, args=(world, _free_port(), width, height, tile, spp, out), nprocs=world, join=True)
+    frame = np.load(out)
+    yy, xx = np.mgrid[0:height, 0:width]
+    want = _pixel_value(xx, yy).astype(np.float32).astype(np.float64)   # float accumulator, exact for these values
+    assert np.array_equal(frame, want)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_owned_pixels_partition_the_image(world):
+    width, height, tile = 70, 45, 16
+    seen = np.zeros((height, width), dtype=np.int32)
+    for s in range(world):
+        x, y, ok = owned_pixel_coords(width, height, tile, world, s)
+        p = api.render_params(width, height, 1, 8, 0, world, s, tile=tile)
+        assert len(x) == api.shard_float4_count(p, s)
+        np.add.at(seen, (y[ok], x[ok]), 1)
+    assert (seen == 1).all()
