@@ -1045,6 +1045,22 @@ struct Batch {
     cudaEvent_t done;
 };
 
+// One set of path-state buffers + the stream its kernels run on.  Batches alternate between
+// RT_MAX_LANES lanes so that the tail of one batch's kernels (a few long marches, the thin deep bounce
+// levels) overlaps with the other batch's kernels instead of leaving SMs idle.
+#define RT_MAX_LANES 3
+struct PathLane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    PathQueue q[2]{};
+    HitQueue hq{};
+    float4* d_radiance = nullptr;
+    uint32_t* d_counts = nullptr;
+    MarchRec* d_march_state = nullptr;
+    std::vector<void*> qallocs;
+    uint64_t path_capacity = 0;
+};
+
 struct rt_scene {
     int device = 0;
     int n_sm = 0;
@@ -1094,6 +1110,10 @@ struct rt_scene {
     float4* d_accum = nullptr;
     rt_vec3* d_frame = nullptr;    // owned order
     uint64_t frame_capacity = 0;
+    // the fields q, hq, d_radiance, d_counts, d_march_state, qallocs, path_capacity and `stream` above are
+    // the BOUND lane's (bind_lane swaps them); lanes[0].stream is the main stream
+    PathLane lanes[RT_MAX_LANES];
+    int n_lanes = 2, cur_lane = 0;
     std::vector<Batch> batches;
     size_t delivered = 0;          // batches already copied to the caller
     cudaEvent_t ev_frame_start = nullptr, ev_frame_stop = nullptr;
@@ -1186,6 +1206,13 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
     if (cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&sc->copy_stream, cudaStreamNonBlocking) != cudaSuccess)
         return bail(fail(RT_ERR_CUDA, "cudaStreamCreate failed"));
+    sc->lanes[0].stream = sc->stream;
+    for (int l = 1; l < RT_MAX_LANES; l++) {
+        if (cudaStreamCreateWithFlags(&sc->lanes[l].stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&sc->lanes[l].done, cudaEventDisableTiming) != cudaSuccess)
+            return bail(fail(RT_ERR_CUDA, "cudaStreamCreate failed"));
+    }
+    sc->n_lanes = (int)std::min<size_t>(std::max<size_t>(env_size("RT_B200_LANES", 2), 1), RT_MAX_LANES);
     cudaEventCreate(&sc->ev_a);
     cudaEventCreate(&sc->ev_b);
     cudaEventCreate(&sc->ev_frame_start);
@@ -1297,15 +1324,36 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
     return RT_OK;
 }
 
-static void free_render_buffers(rt_scene* sc) {
+// make lane i the one the launch code sees (sc->stream, sc->q, ...)
+static void bind_lane(rt_scene* sc, int i) {
+    if (i == sc->cur_lane) return;
+    PathLane& a = sc->lanes[sc->cur_lane];
+    a.stream = sc->stream; a.q[0] = sc->q[0]; a.q[1] = sc->q[1]; a.hq = sc->hq; a.d_radiance = sc->d_radiance;
+    a.d_counts = sc->d_counts; a.d_march_state = sc->d_march_state; a.qallocs.swap(sc->qallocs);
+    a.path_capacity = sc->path_capacity;
+    PathLane& b = sc->lanes[i];
+    sc->stream = b.stream; sc->q[0] = b.q[0]; sc->q[1] = b.q[1]; sc->hq = b.hq; sc->d_radiance = b.d_radiance;
+    sc->d_counts = b.d_counts; sc->d_march_state = b.d_march_state; sc->qallocs.swap(b.qallocs);
+    sc->path_capacity = b.path_capacity;
+    sc->cur_lane = i;
+}
+
+static void free_lane_buffers(rt_scene* sc) {  // of the bound lane
     for (void* p : sc->qallocs) cudaFree(p);
     sc->qallocs.clear();
     cudaFree(sc->d_radiance); sc->d_radiance = nullptr;
     cudaFree(sc->d_counts); sc->d_counts = nullptr;
     cudaFree(sc->d_march_state); sc->d_march_state = nullptr;
+    sc->path_capacity = 0;
+}
+
+static void free_render_buffers(rt_scene* sc) {
+    for (int l = RT_MAX_LANES - 1; l >= 0; l--) {
+        bind_lane(sc, l);
+        free_lane_buffers(sc);
+    }
     cudaFree(sc->d_accum); sc->d_accum = nullptr;
     cudaFree(sc->d_frame); sc->d_frame = nullptr;
-    sc->path_capacity = 0;
     sc->frame_capacity = 0;
     for (Batch& b : sc->batches) cudaEventDestroy(b.done);
     sc->batches.clear();
@@ -1314,8 +1362,15 @@ static void free_render_buffers(rt_scene* sc) {
 void rt_scene_destroy(rt_scene* sc) {
     if (!sc) return;
     cudaSetDevice(sc->device);
-    if (sc->stream) cudaStreamSynchronize(sc->stream);
+    bind_lane(sc, 0);
+    for (int l = 0; l < RT_MAX_LANES; l++)
+        if (sc->lanes[l].stream) cudaStreamSynchronize(l == 0 ? sc->stream : sc->lanes[l].stream);
     free_render_buffers(sc);
+    bind_lane(sc, 0);
+    for (int l = 1; l < RT_MAX_LANES; l++) {
+        if (sc->lanes[l].stream) cudaStreamDestroy(sc->lanes[l].stream);
+        if (sc->lanes[l].done) cudaEventDestroy(sc->lanes[l].done);
+    }
     for (void* p : sc->allocs) cudaFree(p);
     cudaFree(sc->d_counters);
     for (cudaEvent_t e : sc->ev_pool) cudaEventDestroy(e);
@@ -1565,7 +1620,7 @@ static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long 
 }
 
 static int ensure_path_buffers(rt_scene* sc, uint64_t need_paths) {
-    if (sc->path_capacity >= need_paths) return RT_OK;
+    if (sc->path_capacity >= need_paths) return RT_OK;  // (of the bound lane)
     for (void* p : sc->qallocs) cudaFree(p);
     sc->qallocs.clear();
     cudaFree(sc->d_radiance); sc->d_radiance = nullptr;
@@ -1609,9 +1664,22 @@ int rt_render_start(rt_scene* sc, const rt_camera* cam, const rt_render_params* 
     const uint32_t spp = p->samples_number;
     uint64_t cap_paths = env_size("RT_B200_BATCH_PATHS", (size_t)1 << 22);
     uint64_t px_per_batch = std::max<uint64_t>(1, cap_paths / spp);
+    // batches alternate between lanes (streams); per-kernel timing wants the launches back to back
+    int lanes_used = sc->ktiming ? 1 : sc->n_lanes;
+    if (lanes_used > 1) {  // a frame of one batch is split when each part still fills the GPU
+        uint64_t split = (std::max<uint64_t>(sc->owned_pixels, 1) + lanes_used - 1) / lanes_used;
+        if (split * spp >= ((uint64_t)1 << 20)) px_per_batch = std::min(px_per_batch, split);
+    }
     px_per_batch = std::min<uint64_t>(px_per_batch, std::max<uint64_t>(sc->owned_pixels, 1));
     if (px_per_batch * spp > 0xFFFFFFF0ull) return fail(RT_ERR_INVALID, "samples_number too large for one batch");
-    int rc = ensure_path_buffers(sc, px_per_batch * spp);
+    const uint64_t n_batches = (sc->owned_pixels + px_per_batch - 1) / px_per_batch;
+    lanes_used = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)lanes_used, n_batches));
+    int rc = RT_OK;
+    for (int l = 0; l < lanes_used && rc == RT_OK; l++) {
+        bind_lane(sc, l);
+        rc = ensure_path_buffers(sc, px_per_batch * spp);
+    }
+    bind_lane(sc, 0);
     if (rc != RT_OK) return rc;
     if (sc->frame_capacity < sc->owned_pixels) {
         cudaFree(sc->d_accum); cudaFree(sc->d_frame);
@@ -1628,29 +1696,43 @@ int rt_render_start(rt_scene* sc, const rt_camera* cam, const rt_render_params* 
 
     RayCasterDev rcd = make_raycaster(*cam, p->image);
     uint32_t k0 = (uint32_t)p->seed, k1 = (uint32_t)(p->seed >> 32);
-    CU(cudaEventRecord(sc->ev_frame_start, sc->stream));
-    for (uint64_t first = 0; first < sc->owned_pixels; first += px_per_batch) {
-        uint32_t npx = (uint32_t)std::min<uint64_t>(px_per_batch, sc->owned_pixels - first);
-        CU(cudaMemsetAsync(sc->d_counts, 0, RT_CNT_WORDS * sizeof(uint32_t), sc->stream));
-        {
-            KernelSpan span(sc, RT_KCLASS_RAYGEN);
-            k_raygen<<<sc->grid, 256, 0, sc->stream>>>(rcd, sc->map, first, npx, spp, k0, k1, sc->q[0], sc->d_counts, sc->d_radiance);
+    auto enqueue = [&]() -> int {
+        CU(cudaEventRecord(sc->ev_frame_start, sc->stream));  // lane 0 = the main stream
+        for (int l = 1; l < lanes_used; l++) CU(cudaStreamWaitEvent(sc->lanes[l].stream, sc->ev_frame_start, 0));
+        uint64_t batch_no = 0;
+        for (uint64_t first = 0; first < sc->owned_pixels; first += px_per_batch, batch_no++) {
+            bind_lane(sc, (int)(batch_no % (uint64_t)lanes_used));
+            uint32_t npx = (uint32_t)std::min<uint64_t>(px_per_batch, sc->owned_pixels - first);
+            CU(cudaMemsetAsync(sc->d_counts, 0, RT_CNT_WORDS * sizeof(uint32_t), sc->stream));
+            {
+                KernelSpan span(sc, RT_KCLASS_RAYGEN);
+                k_raygen<<<sc->grid, 256, 0, sc->stream>>>(rcd, sc->map, first, npx, spp, k0, k1, sc->q[0], sc->d_counts, sc->d_radiance);
+            }
+            launch_bounces(sc, p->max_depth, first, spp, p->seed);
+            {
+                KernelSpan span(sc, RT_KCLASS_RESOLVE);
+                k_resolve<<<(npx + 255) / 256, 256, 0, sc->stream>>>(sc->d_radiance, npx, spp, first, sc->d_accum, sc->d_frame);
+            }
+            Batch b;
+            b.first_owned = first;
+            b.n_pixels = npx;
+            CU(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
+            CU(cudaEventRecord(b.done, sc->stream));
+            sc->batches.push_back(b);
+            sc->paths += (uint64_t)npx * spp;
         }
-        launch_bounces(sc, p->max_depth, first, spp, p->seed);
-        {
-            KernelSpan span(sc, RT_KCLASS_RESOLVE);
-            k_resolve<<<(npx + 255) / 256, 256, 0, sc->stream>>>(sc->d_radiance, npx, spp, first, sc->d_accum, sc->d_frame);
+        bind_lane(sc, 0);
+        for (int l = 1; l < lanes_used; l++) {  // the main stream ends the frame after every lane
+            CU(cudaEventRecord(sc->lanes[l].done, sc->lanes[l].stream));
+            CU(cudaStreamWaitEvent(sc->stream, sc->lanes[l].done, 0));
         }
-        Batch b;
-        b.first_owned = first;
-        b.n_pixels = npx;
-        CU(cudaEventCreateWithFlags(&b.done, cudaEventDisableTiming));
-        CU(cudaEventRecord(b.done, sc->stream));
-        sc->batches.push_back(b);
-        sc->paths += (uint64_t)npx * spp;
-    }
-    CU(cudaEventRecord(sc->ev_frame_stop, sc->stream));
-    CU(cudaGetLastError());
+        CU(cudaEventRecord(sc->ev_frame_stop, sc->stream));
+        CU(cudaGetLastError());
+        return RT_OK;
+    };
+    rc = enqueue();
+    bind_lane(sc, 0);
+    if (rc != RT_OK) return rc;
     sc->rendering = true;
     sc->frame_complete = false;
     return RT_OK;
