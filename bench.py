@@ -119,7 +119,21 @@ def cpu_reference_run(steps: int, warmup: int, sample=None):
             "n_paths": n_paths}
 
 
+def emit(line: dict) -> None:
+    """the ONE JSON line, on the real stdout"""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    # libraries (NCCL's version banner, torch warnings) must not share stdout with the JSON line: keep a
+    # private duplicate of fd 1 for it and point fd 1 at stderr for everybody else
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -145,7 +159,7 @@ def main():
                                  "sample": r["sample"]},
                 "e2e": {"value": r["mpaths"], "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     import numpy as np
@@ -315,7 +329,7 @@ def main():
                     "d2h_bytes_per_step": d2h, "scene_upload_ms_once": scene_upload_ms},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         }
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
