@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 2
+#define RT_B200_ABI_VERSION 3
 
 typedef enum rt_status {
     RT_OK = 0,
@@ -105,12 +105,13 @@ typedef struct rt_material {
     double scalar;
 } rt_material;
 
-/* Texture implementations, src/world/texture.rs:10-117 (NoiseTexture is out of scope) */
+/* Texture implementations, src/world/texture.rs:10-117 */
 enum {
     RT_TEX_SOLID = 0,      /* color                                                   */
     RT_TEX_CHECKER = 1,    /* color = multipliers (x,y,z); odd/even texture indices   */
     RT_TEX_UV_CHECKER = 2, /* color.x/.y = multipliers .0/.1; odd/even                */
-    RT_TEX_IMAGE = 3       /* image = index into images[]                             */
+    RT_TEX_IMAGE = 3,      /* image = index into images[]                             */
+    RT_TEX_NOISE = 4       /* NoiseTexture (texture.rs:54-68): image = index into noise[], color.x = scale */
 };
 typedef struct rt_texture {
     uint32_t kind;
@@ -120,6 +121,14 @@ typedef struct rt_texture {
     rt_vec3 color;
 } rt_texture;
 #define RT_TEX_MAX_DEPTH 8
+
+/* algebra::noise::Perlin (src/algebra/noise.rs:7-15): the tables Perlin::new draws from thread_rng
+ * (:24-41) -- three permutations of 0..255 and 256 vectors with components in [-1, 1).  `ranfloat`
+ * and `cartesian` are not used by noise() / turb() and are not carried. */
+typedef struct rt_perlin {
+    uint32_t perm_x[256], perm_y[256], perm_z[256];
+    rt_vec3 ranvec[256];
+} rt_perlin;
 
 /* image::RgbaImage, row-major, 4 bytes per texel, row 0 = top (src/world/texture.rs:98-117) */
 typedef struct rt_image {
@@ -141,6 +150,8 @@ typedef struct rt_scene_desc {
     const rt_texture* textures;
     uint32_t n_images;
     const rt_image* images;
+    uint32_t n_noise;
+    const rt_perlin* noise;     /* [n_noise] Perlin tables of the NoiseTextures                 */
 } rt_scene_desc;
 
 typedef struct rt_scene rt_scene;   /* opaque: the device-resident scene + renderer state */

@@ -183,6 +183,7 @@ bool scene_from_desc(const rt_scene_desc* d, Scene* out) {
         out->images[i].rgba.assign(d->images[i].rgba,
                                    d->images[i].rgba + (size_t)4 * d->images[i].width * d->images[i].height);
     }
+    out->noise.assign(d->noise, d->noise + (d->noise ? d->n_noise : 0));
     return true;
 }
 
@@ -708,6 +709,45 @@ V3 random_unit(PathRng& r) { return normalize(random_in_unit_sphere(r)); }  // :
 // ---------------------------------------------------------------------------------------------
 // textures / materials
 // ---------------------------------------------------------------------------------------------
+// Perlin::noise — src/algebra/noise.rs:43-73
+double perlin_noise(const rt_perlin& pn, V3 p) {
+    auto as_i32 = [](double v) -> int32_t {  // Rust `as i32`: saturating, NaN -> 0
+        if (std::isnan(v)) return 0;
+        if (v <= -2147483648.0) return INT32_MIN;
+        if (v >= 2147483647.0) return INT32_MAX;
+        return (int32_t)v;
+    };
+    int32_t x = as_i32(std::floor(p.x)), y = as_i32(std::floor(p.y)), z = as_i32(std::floor(p.z));
+    double u = p.x - std::floor(p.x), v = p.y - std::floor(p.y), w = p.z - std::floor(p.z);
+    double u2 = u * u * (3.0 - 2.0 * u);
+    double v2 = v * v * (3.0 - 2.0 * v);
+    double w2 = w * w * (3.0 - 2.0 * w);
+    double acc = 0.0;  // Iterator::sum::<f64>() folds from 0.0
+    for (int i = 0; i < 2; i++)          // multi_cartesian_product of three 0..2 ranges: last one fastest
+        for (int j = 0; j < 2; j++)
+            for (int k = 0; k < 2; k++) {
+                uint32_t ix = (uint32_t)(i + (int64_t)x) & 255u, iy = (uint32_t)(j + (int64_t)y) & 255u,
+                         iz = (uint32_t)(k + (int64_t)z) & 255u;
+                const rt_vec3& c = pn.ranvec[pn.perm_x[ix] ^ pn.perm_y[iy] ^ pn.perm_z[iz]];
+                double fi = (double)i, fj = (double)j, fk = (double)k;
+                double dotp = c.x * (u - fi) + c.y * (v - fj) + c.z * (w - fk);
+                double term = (fi * u2 + (double)(1 - i) * (1.0 - u2)) * (fj * v2 + (double)(1 - j) * (1.0 - v2)) *
+                              (fk * w2 + (double)(1 - k) * (1.0 - w2)) * dotp;
+                acc = acc + term;
+            }
+    return acc;
+}
+// Perlin::turb — :75-86.  `self.noise(&p)`: the scan never uses temp_p, every octave samples p itself.
+double perlin_turb(const rt_perlin& pn, V3 p, int depth) {
+    double weight = 1.0, acc = 0.0;
+    for (int i = 0; i < depth; i++) {
+        double ret = weight * perlin_noise(pn, p);
+        weight *= 0.5;
+        acc = acc + ret;
+    }
+    return std::fabs(acc);
+}
+
 V3 texture_value(const Scene& sc, uint32_t tex, double u, double v, V3 p) {
     for (int depth = 0; depth <= RT_TEX_MAX_DEPTH; depth++) {
         const rt_texture& t = sc.textures[tex];
@@ -739,6 +779,10 @@ V3 texture_value(const Scene& sc, uint32_t tex, double u, double v, V3 p) {
                 const uint8_t* px = &im.rgba[((size_t)y * im.w + x) * 4];
                 double color_scale = 1.0 / 255.0;
                 return v3((double)px[0] * color_scale, (double)px[1] * color_scale, (double)px[2] * color_scale);
+            }
+            case RT_TEX_NOISE: {  // texture.rs:61-67
+                double k = 0.5 * (1.0 + std::sin(t.color.x * p.z + 10.0 * perlin_turb(sc.noise[t.image], p, 7)));
+                return v3(k * 1.0, k * 1.0, k * 1.0);
             }
             default:
                 return v3(0.0, 0.0, 0.0);

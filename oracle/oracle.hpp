@@ -137,6 +137,7 @@ struct Scene {
     std::vector<rt_texture> textures;
     struct Image { uint32_t w, h; std::vector<uint8_t> rgba; };
     std::vector<Image> images;
+    std::vector<rt_perlin> noise;  // algebra::noise::Perlin tables
     std::vector<BvhNode> bvh;    // built on demand by build_bvh
     int bvh_root = -1;
 };
@@ -152,6 +153,10 @@ bool collection_ray_intersect(const Scene& sc, const Ray& ray, double min_t, dou
                               Counters* c);
 // BvhNode::ray_hit — shapes/mod.rs:628-651 (what Scene::new really builds, world/mod.rs:35)
 bool bvh_ray_hit(const Scene& sc, const Ray& ray, double min_t, double max_t, Hit* hit, Counters* c);
+
+// Perlin::noise / turb — src/algebra/noise.rs:43-86
+double perlin_noise(const rt_perlin& pn, V3 p);
+double perlin_turb(const rt_perlin& pn, V3 p, int depth);
 
 // implicit surfaces — ray_marching.rs:134-520
 double surface_func(const double* p8, V3 p);

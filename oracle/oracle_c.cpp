@@ -221,4 +221,8 @@ uint32_t orc_hardware_threads(void) {
     return n ? n : 1;
 }
 
+// ---- Perlin noise (src/algebra/noise.rs) ---------------------------------------------------------
+double orc_perlin_noise(const rt_perlin* pn, rt_vec3 p) { return perlin_noise(*pn, fr(p)); }
+double orc_perlin_turb(const rt_perlin* pn, rt_vec3 p, int depth) { return perlin_turb(*pn, fr(p), depth); }
+
 }  // extern "C"

@@ -77,6 +77,10 @@ def lib() -> C.CDLL:
     L.orc_pixel_sample_colors.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]
     L.orc_hardware_threads.restype = C.c_uint32
+    L.orc_perlin_noise.argtypes = [C.c_void_p, Vec3]
+    L.orc_perlin_noise.restype = C.c_double
+    L.orc_perlin_turb.argtypes = [C.c_void_p, Vec3, C.c_int]
+    L.orc_perlin_turb.restype = C.c_double
     _lib = L
     return L
 
@@ -150,6 +154,15 @@ def philox_stream(seed, pixel, sample, event, n) -> np.ndarray:
     out = np.empty(n)
     lib().orc_philox_stream(seed, pixel, sample, event, n, _p(out))
     return out
+
+
+def perlin_noise(table, p) -> float:
+    """Perlin::noise (src/algebra/noise.rs:43-73) on an rt_perlin table (ctypes struct)"""
+    return lib().orc_perlin_noise(C.addressof(table), Vec3(*map(float, p)))
+
+
+def perlin_turb(table, p, depth=7) -> float:
+    return lib().orc_perlin_turb(C.addressof(table), Vec3(*map(float, p)), depth)
 
 
 class OracleScene:

@@ -16,7 +16,7 @@ RT_ISECT_BRUTE, RT_ISECT_FAST, RT_ISECT_VERIFY = 0, 1, 2
 RT_SHAPE_SPHERE, RT_SHAPE_CUBE, RT_SHAPE_RECTANGLE, RT_SHAPE_MARCH = 0, 1, 2, 3
 RT_SURF_HEART, RT_SURF_SINE, RT_SURF_STAR, RT_SURF_DUPIN, RT_SURF_HUNTS, RT_SURF_CUSHION = range(6)
 RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT_EMPTY = range(5)
-RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_UV_CHECKER, RT_TEX_IMAGE = range(4)
+RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_UV_CHECKER, RT_TEX_IMAGE, RT_TEX_NOISE = range(5)
 RT_SHAPE_PARAMS = 8
 
 
@@ -56,6 +56,11 @@ class Image(C.Structure):
     _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("rgba", C.POINTER(C.c_uint8))]
 
 
+class Perlin(C.Structure):
+    _fields_ = [("perm_x", C.c_uint32 * 256), ("perm_y", C.c_uint32 * 256), ("perm_z", C.c_uint32 * 256),
+                ("ranvec", Vec3 * 256)]
+
+
 class SceneDesc(C.Structure):
     _fields_ = [
         ("n_shapes", C.c_uint32),
@@ -71,6 +76,8 @@ class SceneDesc(C.Structure):
         ("textures", C.POINTER(Texture)),
         ("n_images", C.c_uint32),
         ("images", C.POINTER(Image)),
+        ("n_noise", C.c_uint32),
+        ("noise", C.POINTER(Perlin)),
     ]
 
 

@@ -195,6 +195,8 @@ rt_scene_desc FlatScene::desc() const {
     d.textures = textures.data();
     d.n_images = (uint32_t)images.size();
     d.images = images.data();
+    d.n_noise = (uint32_t)noise.size();
+    d.noise = noise.data();
     return d;
 }
 
@@ -251,9 +253,60 @@ bool load_ppm(const std::string& path, uint32_t* w, uint32_t* h, std::vector<uin
     return true;
 }
 
+// xoshiro256** seeded through splitmix64: the reproducible stand-in for rand::thread_rng()
+struct HostRng {
+    uint64_t s[4];
+    explicit HostRng(uint64_t seed) {
+        uint64_t x = seed;
+        for (int i = 0; i < 4; i++) {
+            uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+            s[i] = z ^ (z >> 31);
+        }
+    }
+    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    uint64_t next_u64() {
+        uint64_t result = rotl(s[1] * 5, 7) * 9;
+        uint64_t t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
+        s[2] ^= t;
+        s[3] = rotl(s[3], 45);
+        return result;
+    }
+    double gen() {  // rng.gen::<f64>(): 53 random bits scaled to [0,1)
+        return (double)(next_u64() >> 11) * (1.0 / 9007199254740992.0);
+    }
+};
+
+// Perlin::new, src/algebra/noise.rs:24-41.  The reference shuffles with thread_rng (unreproducible); the
+// tables here come from the scene seed: Fisher-Yates like SliceRandom::shuffle (i from the top, j uniform
+// in 0..=i), ranvec = Vector3d::random(-1.0, 1.0) = min + (max - min) * gen() per component.
+rt_perlin make_perlin(uint64_t seed) {
+    HostRng rng(seed ^ 0x5045524C494E0001ull);
+    rt_perlin pn;
+    uint32_t* perms[3] = {pn.perm_x, pn.perm_y, pn.perm_z};
+    for (int a = 0; a < 3; a++) {
+        for (uint32_t i = 0; i < 256; i++) perms[a][i] = i;
+        for (uint32_t i = 255; i > 0; i--) {
+            uint32_t j = (uint32_t)(rng.next_u64() % (uint64_t)(i + 1));
+            std::swap(perms[a][i], perms[a][j]);
+        }
+    }
+    for (int i = 0; i < 256; i++) (void)rng.gen();  // ranfloat (drawn, never used by noise / turb)
+    for (int i = 0; i < 256; i++) {
+        double x = -1.0 + (1.0 - -1.0) * rng.gen();
+        double y = -1.0 + (1.0 - -1.0) * rng.gen();
+        double z = -1.0 + (1.0 - -1.0) * rng.gen();
+        pn.ranvec[i] = rt_vec3{x, y, z};
+    }
+    return pn;
+}
+
 struct Builder {
     FlatScene& fs;
     std::map<std::string, uint32_t> material_by_name;
+    uint64_t seed = 1;
     explicit Builder(FlatScene& f) : fs(f) {}
 
     uint32_t add_solid(const Vector3d& c) {
@@ -309,8 +362,11 @@ struct Builder {
             im.rgba = nullptr;  // fixed up after all images are stored (vector may reallocate)
             fs.images.push_back(im);
             t.image = (uint32_t)fs.images.size() - 1;
-        } else if (type == "NoiseTexture") {
-            throw std::runtime_error("NoiseTexture is outside the accelerated hot path (SURVEY §8f)");
+        } else if (type == "NoiseTexture") {  // texture.rs:54-68; `noise` is #[serde(skip)] -> Perlin::default()
+            t.kind = RT_TEX_NOISE;
+            t.color = rt_vec3{v.at("scale").as_number(), 0.0, 0.0};
+            fs.noise.push_back(make_perlin(seed + 0x9E37ull * (uint64_t)fs.noise.size()));
+            t.image = (uint32_t)fs.noise.size() - 1;
         } else {
             throw std::runtime_error("unknown variant `" + type + "` for Texture");
         }
@@ -419,29 +475,6 @@ struct Builder {
     }
 };
 
-// xoshiro256** seeded through splitmix64: the reproducible stand-in for rand::thread_rng()
-struct HostRng {
-    uint64_t s[4];
-    explicit HostRng(uint64_t seed) {
-        uint64_t x = seed;
-        for (int i = 0; i < 4; i++) {
-            uint64_t z = (x += 0x9E3779B97F4A7C15ull);
-            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-            z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-            s[i] = z ^ (z >> 31);
-        }
-    }
-    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
-    double gen() {  // rng.gen::<f64>(): 53 random bits scaled to [0,1)
-        uint64_t result = rotl(s[1] * 5, 7) * 9;
-        uint64_t t = s[1] << 17;
-        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
-        s[2] ^= t;
-        s[3] = rotl(s[3], 45);
-        return (double)(result >> 11) * (1.0 / 9007199254740992.0);
-    }
-};
-
 // json_models.rs:50-133
 void add_random_spheres(Builder& b, uint64_t seed) {
     HostRng rng(seed);
@@ -497,6 +530,7 @@ std::shared_ptr<Scene> Scene::from_json(const std::string& data, uint64_t seed, 
     sc->background_ = parse_vec3(root->at("background"));
 
     Builder b(sc->flat_);
+    b.seed = seed;
     const Value& mats = root->at("materials");
     if (mats.kind != Value::Object) throw std::runtime_error("materials: expected a map");
     for (auto& kv : mats.obj) b.material_by_name[kv.first] = b.add_material(kv.first, *kv.second);

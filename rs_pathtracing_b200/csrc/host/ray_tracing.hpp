@@ -122,6 +122,7 @@ struct FlatScene {
     std::vector<rt_texture> textures;
     std::vector<std::vector<uint8_t>> image_data;
     std::vector<rt_image> images;
+    std::vector<rt_perlin> noise;
     std::vector<std::string> shape_names, material_names;
     rt_scene_desc desc() const;
 };

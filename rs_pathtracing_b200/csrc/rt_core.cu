@@ -358,8 +358,11 @@ struct HitQueue {
 #define RT_CNT_HEAD (3 * RT_MAX_LEVELS)              // + kind * RT_MAX_LEVELS
 #define RT_CNT_WORDS (9 * RT_MAX_LEVELS)
 
+#ifndef RT_EXTEND_MIN_BLOCKS
+#define RT_EXTEND_MIN_BLOCKS 3
+#endif
 template <bool COUNT>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, RT_EXTEND_MIN_BLOCKS)
 k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ count_in, HitQueue hq,
          uint32_t* march_count, uint32_t* replay_count, DevCounters* g_counters) {
     Staged st = stage_scene(S, use_smem);
@@ -1173,7 +1176,8 @@ static int validate_desc(const rt_scene_desc* d) {
     }
     for (uint32_t i = 0; i < d->n_textures; i++) {
         const rt_texture& t = d->textures[i];
-        if (t.kind > RT_TEX_IMAGE) return fail(RT_ERR_INVALID, "scene description: unknown texture kind");
+        if (t.kind > RT_TEX_NOISE) return fail(RT_ERR_INVALID, "scene description: unknown texture kind");
+        if (t.kind == RT_TEX_NOISE && (t.image >= d->n_noise || !d->noise)) return fail(RT_ERR_INVALID, "scene description: noise index out of range");
         if ((t.kind == RT_TEX_CHECKER || t.kind == RT_TEX_UV_CHECKER) && (t.odd >= d->n_textures || t.even >= d->n_textures))
             return fail(RT_ERR_INVALID, "scene description: child texture index out of range");
         if (t.kind == RT_TEX_IMAGE && t.image >= d->n_images) return fail(RT_ERR_INVALID, "scene description: image index out of range");
@@ -1235,6 +1239,7 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
         if ((rc = upload(sc, d->images[i].rgba, (size_t)4 * imgs[i].width * imgs[i].height, &imgs[i].rgba)) != RT_OK) return bail(rc);
     }
     if ((rc = upload(sc, imgs.data(), imgs.size(), &sc->ds.images)) != RT_OK) return bail(rc);
+    if ((rc = upload(sc, d->noise, (size_t)d->n_noise, &sc->ds.noise)) != RT_OK) return bail(rc);
     std::vector<int> march;
     for (uint32_t i = 0; i < n; i++)
         if (d->kind[i] == RT_SHAPE_MARCH) march.push_back((int)i);
@@ -1662,7 +1667,7 @@ int rt_render_start(rt_scene* sc, const rt_camera* cam, const rt_render_params* 
     sc->owned_pixels = owned_tiles(sc->map) * sc->map.tile_pixels();
 
     const uint32_t spp = p->samples_number;
-    uint64_t cap_paths = env_size("RT_B200_BATCH_PATHS", (size_t)1 << 22);
+    uint64_t cap_paths = env_size("RT_B200_BATCH_PATHS", (size_t)1 << 23);
     uint64_t px_per_batch = std::max<uint64_t>(1, cap_paths / spp);
     // batches alternate between lanes (streams); per-kernel timing wants the launches back to back
     int lanes_used = sc->ktiming ? 1 : sc->n_lanes;

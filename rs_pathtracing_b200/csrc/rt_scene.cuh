@@ -25,6 +25,7 @@ struct DevScene {
     const rt_material* materials;
     const rt_texture* textures;
     const DevImage* images;
+    const rt_perlin* noise;
     // indices of the RT_SHAPE_MARCH shapes (they are few; kernels that split marching out of the
     // analytic loop walk this list)
     int n_march;
@@ -355,6 +356,45 @@ __device__ __forceinline__ void nearest_hit_fast(const DevScene& S, const Staged
 // ------------------------------------------------------------------------------------------------
 // textures — src/world/texture.rs:17-116
 // ------------------------------------------------------------------------------------------------
+// Perlin::noise, src/algebra/noise.rs:43-73: gradient noise over the unit cell of p, corners in
+// multi_cartesian_product order (last index fastest), terms summed in that order from 0.0
+__device__ inline double perlin_noise(const rt_perlin& pn, D3 p) {
+    const double fx = floor(p.x), fy = floor(p.y), fz = floor(p.z);
+    auto as_i32 = [](double v) -> int {  // `as i32`: saturating, NaN -> 0
+        if (v != v) return 0;
+        if (v <= -2147483648.0) return (int)0x80000000;
+        if (v >= 2147483647.0) return 2147483647;
+        return (int)v;
+    };
+    const unsigned x = (unsigned)as_i32(fx), y = (unsigned)as_i32(fy), z = (unsigned)as_i32(fz);
+    const double u = p.x - fx, v = p.y - fy, w = p.z - fz;
+    const double u2 = u * u * (3.0 - 2.0 * u);
+    const double v2 = v * v * (3.0 - 2.0 * v);
+    const double w2 = w * w * (3.0 - 2.0 * w);
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int d0 = (k >> 2) & 1, d1 = (k >> 1) & 1, d2 = k & 1;
+        const rt_vec3 c = pn.ranvec[pn.perm_x[(d0 + x) & 255u] ^ pn.perm_y[(d1 + y) & 255u] ^ pn.perm_z[(d2 + z) & 255u]];
+        const double fi = (double)d0, fj = (double)d1, fk = (double)d2;
+        const double dotp = c.x * (u - fi) + c.y * (v - fj) + c.z * (w - fk);
+        sum = sum + (fi * u2 + (double)(1 - d0) * (1.0 - u2)) * (fj * v2 + (double)(1 - d1) * (1.0 - v2)) *
+                        (fk * w2 + (double)(1 - d2) * (1.0 - w2)) * dotp;
+    }
+    return sum;
+}
+// Perlin::turb, :75-86.  The reference's scan evaluates noise(&p) -- the ORIGINAL point, not the doubled
+// temp_p -- at every octave, so the result is |sum_i 2^-i noise(p)| with the sum's own roundings.
+__device__ inline double perlin_turb(const rt_perlin& pn, D3 p, int depth) {
+    const double n = perlin_noise(pn, p);
+    double sum = 0.0, weight = 1.0;
+    for (int i = 0; i < depth; i++) {
+        sum = sum + weight * n;
+        weight *= 0.5;
+    }
+    return fabs(sum);
+}
+
 __device__ inline D3 texture_value(const DevScene& S, uint32_t tex, double u, double v, D3 p) {
     const double PI = 3.14159265358979323846264338327950288;
     for (int depth = 0; depth <= RT_TEX_MAX_DEPTH; depth++) {
@@ -380,6 +420,9 @@ __device__ inline D3 texture_value(const DevScene& S, uint32_t tex, double u, do
             const uint8_t* px = im.rgba + ((size_t)y * im.width + x) * 4;
             double color_scale = 1.0 / 255.0;
             return mk((double)px[0] * color_scale, (double)px[1] * color_scale, (double)px[2] * color_scale);
+        } else if (t.kind == RT_TEX_NOISE) {  // NoiseTexture::value, :61-67
+            const double k = 0.5 * (1.0 + sin(t.color.x * p.z + 10.0 * perlin_turb(S.noise[t.image], p, 7)));
+            return mk(k * 1.0, k * 1.0, k * 1.0);
         } else {
             return mk(0.0, 0.0, 0.0);
         }

@@ -265,7 +265,7 @@ def grazing_rays(sc, n_shapes, seed):
 
 
 @pytest.mark.parametrize("name", ["spheres.json", "cornell_box.json", "detached_materials.json", "dupin.json",
-                                  "cube_test.json"])
+                                  "cube_test.json", "light_source.json"])
 def test_cull_is_conservative_on_fixture_scenes(name):
     """RT_ISECT_VERIFY: FAST == BRUTE on every ray and no culled (ray, shape) pair hits in the exact test"""
     sc = rt.Scene.from_file(scene_path(name), random_spheres_seed=1)

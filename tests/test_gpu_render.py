@@ -37,6 +37,7 @@ SAME_PATH_TOL = 2e-6
     ("detached_materials.json", 64, 36, 4, 8),
     ("dupin.json", 64, 36, 4, 8),
     ("cube_test.json", 48, 48, 4, 50),
+    ("light_source.json", 64, 36, 4, 8),     # NoiseTexture (Perlin turbulence) on the big sphere and the ground
 ])
 def test_same_paths_as_oracle(name, w, h, spp, depth):
     sc = rt.Scene.from_file(scene_path(name), random_spheres_seed=1)

@@ -29,7 +29,7 @@ def test_core_exports_every_declared_symbol():
     assert names == set(_ffi.CORE_SYMBOLS), names ^ set(_ffi.CORE_SYMBOLS)
     for n in names:
         assert hasattr(lib, n)
-    assert lib.rt_abi_version() == 2
+    assert lib.rt_abi_version() == 3
 
 
 def test_host_exports_every_declared_symbol():
@@ -43,11 +43,12 @@ def test_host_exports_every_declared_symbol():
 def test_pod_layouts():
     assert C.sizeof(_ffi.Vec3) == 24 and C.sizeof(_ffi.Ray) == 48 and C.sizeof(_ffi.Camera) == 112
     assert C.sizeof(_ffi.Material) == 16 and C.sizeof(_ffi.Texture) == 40 and C.sizeof(_ffi.RenderParams) == 40
+    assert C.sizeof(_ffi.Perlin) == 3 * 1024 + 256 * 24 and C.sizeof(_ffi.SceneDesc) == 120
 
 
 @pytest.mark.parametrize("name,json_shapes", [("spheres.json", 5), ("cornell_box.json", 9),
                                                ("detached_materials.json", 5), ("dupin.json", 3),
-                                               ("cube_test.json", 3), ("empty.json", 0)])
+                                               ("cube_test.json", 3), ("empty.json", 0), ("light_source.json", 3)])
 def test_scene_loads_and_adds_random_spheres(name, json_shapes):
     bare = rt.Scene.from_file(scene_path(name), add_random_spheres=False)
     assert bare.shape_count == json_shapes

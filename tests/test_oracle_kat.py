@@ -132,3 +132,34 @@ def test_surface_gradients_are_derivatives():
             comps = faithful.get(k, [])
             assert np.allclose(g[comps], num[comps], rtol=1e-5, atol=1e-5), (k, g, num)
             assert np.isfinite(g).all()
+
+
+def test_perlin_noise_properties():
+    """src/algebra/noise.rs:43-86 holds no test; properties of the restatement: the noise vanishes on the
+    integer lattice (every corner weight multiplies (u-i, v-j, w-k) . c with the matching corner at 0),
+    is continuous across cell faces, is bounded by sqrt(3) * max|c| and turb is |sum 2^-i noise(p)| of the
+    ORIGINAL point (the reference never uses its doubled temp_p)."""
+    import rs_pathtracing_b200 as rt
+    from conftest import scene_path
+    sc = rt.Scene.from_file(scene_path("light_source.json"), random_spheres_seed=1)
+    d = sc.desc()
+    assert d.n_noise == 1
+    tab = d.noise[0]
+    for name in ("perm_x", "perm_y", "perm_z"):
+        assert sorted(getattr(tab, name)) == list(range(256))        # a permutation (SliceRandom::shuffle)
+    rv = np.array([[v.x, v.y, v.z] for v in tab.ranvec])
+    assert rv.min() >= -1.0 and rv.max() < 1.0 and rv.std() > 0.4        # Vector3d::random(-1, 1)
+    rng = np.random.default_rng(2)
+    for p in rng.integers(-300, 300, (50, 3)):
+        assert po.perlin_noise(tab, p) == 0.0
+    for p in rng.uniform(-40, 40, (200, 3)):
+        n = po.perlin_noise(tab, p)
+        assert abs(n) <= 3.0 ** 0.5 * np.abs(rv).max()
+        q = p.copy()
+        q[0] = np.floor(p[0])                       # a cell face: approach from both sides
+        lo, hi = po.perlin_noise(tab, q - [1e-9, 0, 0]), po.perlin_noise(tab, q + [1e-9, 0, 0])
+        assert abs(lo - hi) < 1e-6
+        acc, w = 0.0, 1.0
+        for _ in range(7):
+            acc, w = acc + w * n, w * 0.5
+        assert po.perlin_turb(tab, p, 7) == abs(acc)

@@ -28,7 +28,8 @@ import rs_pathtracing_b200 as rt  # host mirror only: scene loading / flattening
 from oracle import pyoracle as po
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-SCENES = ["spheres.json", "cornell_box.json", "detached_materials.json", "dupin.json", "cube_test.json"]
+SCENES = ["spheres.json", "cornell_box.json", "detached_materials.json", "dupin.json", "cube_test.json",
+          "light_source.json"]
 N_RAYS = 2048
 
 KAT = {
@@ -77,7 +78,8 @@ def main():
                             n_shapes=np.int64(sc.shape_count))
         print(tag, "shapes", sc.shape_count, "hits", int((want["index"] >= 0).sum()), "of", len(rays))
     for name, w, h, spp, depth in [("spheres.json", 48, 36, 4, 8), ("cornell_box.json", 32, 32, 4, 8),
-                                   ("detached_materials.json", 48, 27, 4, 8), ("dupin.json", 48, 27, 4, 8)]:
+                                   ("detached_materials.json", 48, 27, 4, 8), ("dupin.json", 48, 27, 4, 8),
+                                   ("light_source.json", 48, 27, 4, 8)]:
         sc = rt.Scene.from_file(os.path.join(ROOT, "scenes", name), 1)
         osc = po.OracleScene(sc.desc())
         frame, info = osc.render(sc.camera(), w, h, spp, depth, seed=11, rng="philox")
