@@ -75,7 +75,8 @@ def nvcc_path() -> str:
 
 def build_core(force: bool = False) -> str:
     if force or _stale(CORE_SO, CORE_SOURCES + CORE_HEADERS + [os.path.abspath(__file__)]):
-        _run([nvcc_path(), *NVCC_FLAGS, "-o", CORE_SO, *CORE_SOURCES], "build_core.log")
+        extra = os.environ.get("RT_B200_NVCC_EXTRA", "").split()   # tuning experiments, e.g. -DRT_MARCH_MIN_BLOCKS=5
+        _run([nvcc_path(), *NVCC_FLAGS, *extra, "-o", CORE_SO, *CORE_SOURCES], "build_core.log")
     return CORE_SO
 
 

@@ -364,7 +364,7 @@ struct HitQueue {
 template <bool COUNT>
 __global__ void __launch_bounds__(256, RT_EXTEND_MIN_BLOCKS)
 k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ count_in, HitQueue hq,
-         uint32_t* march_count, uint32_t* replay_count, DevCounters* g_counters) {
+         uint32_t* march_count, uint32_t* replay_count, DevCounters* g_counters, bool any_hit_suffices) {
     Staged st = stage_scene(S, use_smem);
     DevCounters c = {};
     const uint32_t n = *count_in;
@@ -380,7 +380,9 @@ k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
             int winner;
             const CullRay cr = make_cull_ray(ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
             degenerate = analytic_nearest<COUNT>(S, st, cr, ro, rd, 0.001, INFINITY, best, winner, c);
-            if (!degenerate) {
+            // depth == 0 (renderer/mod.rs:26-27): a hit is black whatever it is, so a ray that already hit an
+            // analytic shape needs no marching at the last level
+            if (!degenerate && !(any_hit_suffices && winner >= 0)) {
                 for (int k = 0; k < S.n_march; k++) {
                     if (!cull_pass(cr, S.march_cull[k])) continue;  // the line misses the marching bound
                     const int si = S.march_index[k];
@@ -1570,9 +1572,9 @@ static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long 
         {
             KernelSpan span(sc, RT_KCLASS_EXTEND);
             if (sc->counters_on)
-                k_extend<true><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, rcount, sc->d_counters);
+                k_extend<true><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, rcount, sc->d_counters, level == max_depth);
             else
-                k_extend<false><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, rcount, sc->d_counters);
+                k_extend<false><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, rcount, sc->d_counters, level == max_depth);
         }
         if (sc->ds.n_march > 0) {
             KernelSpan span(sc, RT_KCLASS_MARCH);

@@ -121,14 +121,13 @@ __device__ __forceinline__ double advance_exact(double a, double s, long long m)
         if (take > 0) {
             a = __longlong_as_double(up ? bits + take * D : bits - take * D);
             m -= take;
+            if (m == 0) return a;  // the common case: the whole jump in one binade
         }
         // next to the binade edge (the margin above leaves 2-3 steps): literal steps carry it across
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            if (m > 0) {
-                a = a + s;
-                m--;
-            }
+#pragma unroll 1
+        for (int e = 0; e < 4 && m > 0; e++) {
+            a = a + s;
+            m--;
         }
     }
     return a;
