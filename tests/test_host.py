@@ -228,3 +228,19 @@ def test_march_region_bounds_dominate_sampled_derivatives():
         assert worst2 <= H * (1 + 1e-6) + 1e-6, (k, worst2, H)
         assert worst1 <= G * (1 + 1e-6) + 1e-6, (k, worst1, G)
         assert worst2 > H / 200 and worst1 > G / 200, (k, worst1, G, worst2, H)   # and not absurdly loose
+
+
+def test_rust_sys_crate_covers_the_abi():
+    """rust/ray_tracing_b200-sys/src/lib.rs (uncompiled: no Rust toolchain here) must declare every symbol
+    of include/rt_b200.h, the ABI version the header states, and mirror rt_stats / rt_scene_desc field
+    for field."""
+    src = open(os.path.join(ROOT, "rust", "ray_tracing_b200-sys", "src", "lib.rs")).read()
+    hdr = open(os.path.join(ROOT, "include", "rt_b200.h")).read()
+    for name in _declared("rt_b200.h"):
+        assert re.search(r"\bpub fn %s\(" % name, src), name
+    version = re.search(r"#define RT_B200_ABI_VERSION (\d+)", hdr).group(1)
+    assert f"RT_B200_ABI_VERSION: c_int = {version};" in src
+    for struct, cls in (("rt_stats", _ffi.Stats), ("rt_scene_desc", _ffi.SceneDesc)):
+        body = re.search(r"pub struct %s \{(.*?)\}" % struct, src, re.S).group(1)
+        rust_fields = re.findall(r"pub (\w+):", body)
+        assert rust_fields == [f[0] for f in cls._fields_], struct
