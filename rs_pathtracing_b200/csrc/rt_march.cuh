@@ -46,90 +46,105 @@
 namespace rt {
 
 // ---- (1) exact multi-step advance ---------------------------------------------------------------
-// returns the value `a` holds after m iterations of `a = a + s` in IEEE double arithmetic
-__device__ __forceinline__ double advance_exact(double a, double s, long long m) {
+// advance_iter: one unit of progress (m > 0 on entry): a bounded literal walk near zero, or one binade --
+// as many regular steps as provably stay inside it plus the few literal steps that cross its edge.
+// advance_exact loops over it; k_march's cooperative advance interleaves it with other lanes' work.
+__device__ __forceinline__ void advance_iter(double& a, const double s, long long& m) {
     const long long MANT = 0x000fffffffffffffLL;
-    if (s == 0.0) return m > 0 ? a + s : a;
-    const long long sb = __double_as_longlong(fabs(s));
-    const int sexp = (int)(sb >> 52);
-    const long long Ms = (sb & MANT) | (1LL << 52);
-    const bool s_neg = s < 0.0;
+    if (s == 0.0) {
+        a = a + s;
+        m = 0;
+        return;
+    }
     // Near zero (|a| < 32 |s|) a binade holds fewer than 32 steps: walking it literally (one DADD per step)
     // is cheaper than the per-binade bookkeeping below, and an accumulator that changes sign would
     // otherwise pay that bookkeeping for every binade between |s| and its starting magnitude, twice.
     const double near = 32.0 * fabs(s);
-    while (m > 0) {
-        if (fabs(a) < near) {
-            // (literal steps are exact wherever they are taken: overshooting the zone by up to 3 of them is
-            // harmless, so the test runs once per 4 steps)
-            while (m >= 4 && fabs(a) < near) {
-                a = a + s;
-                a = a + s;
-                a = a + s;
-                a = a + s;
-                m -= 4;
-            }
+    if (fabs(a) < near) {
+        // (literal steps are exact wherever they are taken: overshooting the zone by up to 3 of them is
+        // harmless, so the test runs once per 4 steps)
+#pragma unroll 1
+        for (int c = 0; c < 4 && m >= 4 && fabs(a) < near; c++) {
+            a = a + s;
+            a = a + s;
+            a = a + s;
+            a = a + s;
+            m -= 4;
+        }
+        if (m < 4) {
             while (m > 0 && fabs(a) < near) {
                 a = a + s;
                 m--;
             }
-            continue;
         }
-        const long long bits = __double_as_longlong(a);
-        const int exp = (int)((bits >> 52) & 0x7ff);
-        const long long mant = bits & MANT;
-        const bool a_neg = bits < 0;
-        const int k = exp - sexp;           // ulp(a) = 2^k ulp(s):  s / ulp(a) = Ms / 2^k
-        const bool up = (a_neg == s_neg);   // the magnitude grows
-        // literal step wherever the regular-progression argument does not apply: zero / subnormal /
-        // non-finite operands, a step comparable to the value itself, or the bottom of a binade
-        // approached from above (the grid below it is finer)
-        bool literal = exp == 0 || exp == 0x7ff || sexp == 0 || sexp == 0x7ff || k < 1 || (!up && mant == 0);
-        long long D = 0;
-        if (!literal && k <= 54) {
-            const long long S = Ms >> k;
-            const long long rem = Ms & ((1LL << k) - 1);
-            const long long half = 1LL << (k - 1);
-            if (rem > half) D = S + 1;
-            else if (rem < half) D = S;
-            else if (mant & 1) literal = true;   // exact tie from an odd mantissa: one literal step makes it even
-            else D = S + (S & 1);                // exact tie from an even mantissa: round-half-even lands on even again
-        }                                        // k > 54: |s| < ulp(a)/4, the sum rounds back to a (D = 0)
-        if (literal) {
-            a = a + s;
-            m--;
-            continue;
-        }
-        if (D == 0) return a;  // a + s == a for every remaining step
-        // steps that provably stay inside this binade (going down, the landing mantissa must stay >= 1):
-        // take <= num / D - 2, in integer arithmetic (64-bit int <-> double conversions and a double
-        // division per binade used to dominate the marcher)
-        const unsigned long long num = (unsigned long long)(up ? (MANT - mant) : (mant - 1));
-        const unsigned long long Du = (unsigned long long)D, mu = (unsigned long long)m;
-        const unsigned long long lo = mu * Du;
-        long long take;
-        if (__umul64hi(mu, Du) == 0 && lo <= num && num - lo >= 2 * Du) {
-            take = m;  // the whole jump stays inside the binade (the common case)
-        } else {
-            // floor(num / D) - 2 from a float quotient rounded down at every stage (a smaller take is
-            // always safe: the remaining steps are simply handled by the next iteration)
-            const float qf = __fdiv_rd(__ull2float_rd(num), __ull2float_ru(Du));
-            long long room = (long long)qf - 2;
-            if (room < 0) room = 0;
-            take = room < m ? room : m;
-        }
-        if (take > 0) {
-            a = __longlong_as_double(up ? bits + take * D : bits - take * D);
-            m -= take;
-            if (m == 0) return a;  // the common case: the whole jump in one binade
-        }
-        // next to the binade edge (the margin above leaves 2-3 steps): literal steps carry it across
-#pragma unroll 1
-        for (int e = 0; e < 4 && m > 0; e++) {
-            a = a + s;
-            m--;
-        }
+        return;
     }
+    const long long sb = __double_as_longlong(fabs(s));
+    const int sexp = (int)(sb >> 52);
+    const long long Ms = (sb & MANT) | (1LL << 52);
+    const bool s_neg = s < 0.0;
+    const long long bits = __double_as_longlong(a);
+    const int exp = (int)((bits >> 52) & 0x7ff);
+    const long long mant = bits & MANT;
+    const bool a_neg = bits < 0;
+    const int k = exp - sexp;           // ulp(a) = 2^k ulp(s):  s / ulp(a) = Ms / 2^k
+    const bool up = (a_neg == s_neg);   // the magnitude grows
+    // literal step wherever the regular-progression argument does not apply: zero / subnormal /
+    // non-finite operands, a step comparable to the value itself, or the bottom of a binade
+    // approached from above (the grid below it is finer)
+    bool literal = exp == 0 || exp == 0x7ff || sexp == 0 || sexp == 0x7ff || k < 1 || (!up && mant == 0);
+    long long D = 0;
+    if (!literal && k <= 54) {
+        const long long S = Ms >> k;
+        const long long rem = Ms & ((1LL << k) - 1);
+        const long long half = 1LL << (k - 1);
+        if (rem > half) D = S + 1;
+        else if (rem < half) D = S;
+        else if (mant & 1) literal = true;   // exact tie from an odd mantissa: one literal step makes it even
+        else D = S + (S & 1);                // exact tie from an even mantissa: round-half-even lands on even again
+    }                                        // k > 54: |s| < ulp(a)/4, the sum rounds back to a (D = 0)
+    if (literal) {
+        a = a + s;
+        m--;
+        return;
+    }
+    if (D == 0) {  // a + s == a for every remaining step
+        m = 0;
+        return;
+    }
+    // steps that provably stay inside this binade (going down, the landing mantissa must stay >= 1):
+    // take <= num / D - 2, in integer arithmetic (64-bit int <-> double conversions and a double
+    // division per binade used to dominate the marcher)
+    const unsigned long long num = (unsigned long long)(up ? (MANT - mant) : (mant - 1));
+    const unsigned long long Du = (unsigned long long)D, mu = (unsigned long long)m;
+    const unsigned long long lo = mu * Du;
+    long long take;
+    if (__umul64hi(mu, Du) == 0 && lo <= num && num - lo >= 2 * Du) {
+        take = m;  // the whole jump stays inside the binade (the common case)
+    } else {
+        // floor(num / D) - 2 from a float quotient rounded down at every stage (a smaller take is
+        // always safe: the remaining steps are simply handled by the next iteration)
+        const float qf = __fdiv_rd(__ull2float_rd(num), __ull2float_ru(Du));
+        long long room = (long long)qf - 2;
+        if (room < 0) room = 0;
+        take = room < m ? room : m;
+    }
+    if (take > 0) {
+        a = __longlong_as_double(up ? bits + take * D : bits - take * D);
+        m -= take;
+        if (m == 0) return;  // the common case: the whole jump in one binade
+    }
+    // next to the binade edge (the margin above leaves 2-3 steps): literal steps carry it across
+#pragma unroll 1
+    for (int e = 0; e < 4 && m > 0; e++) {
+        a = a + s;
+        m--;
+    }
+}
+
+// returns the value `a` holds after m iterations of `a = a + s` in IEEE double arithmetic
+__device__ __forceinline__ double advance_exact(double a, double s, long long m) {
+    while (m > 0) advance_iter(a, s, m);
     return a;
 }
 
@@ -247,6 +262,9 @@ __device__ __forceinline__ void expand_ray(const double* q, D3 p, D3 d, double t
 }
 
 #define RT_MARCH_MIN_JUMP 8
+#ifndef RT_MARCH_LAND_COOLDOWN
+#define RT_MARCH_LAND_COOLDOWN 6
+#endif
 enum { RT_MARCH_MORE = 0, RT_MARCH_DONE = 1, RT_MARCH_MISS = 2 };
 enum { RT_PHASE_END = 0, RT_PHASE_ATTEMPT = 1, RT_PHASE_LITERAL = 2 };
 
@@ -319,10 +337,51 @@ struct Marcher {
     //   [advance t, p by m steps exactly]
     //   attempt_land():  the reference's `r = next` at the landing sample + the model self-check
     struct Plan {
-        double s[DEG + 1];  // Taylor shift of the model to the current sample
-        double M;           // the uncertainty band of this jump
+        double s[DEG + 1];  // the model shifted to the sample + `shift`: g(tau + shift + x) = sum s[k] x^k (x signed)
+        double M;           // the uncertainty band of this jump (of its last stage)
+        // state of the hop loop (plan_begin / plan_hop / plan_end)
+        double shift;       // signed displacement of the expansion point of s[] from the current sample
+        double sig, g, dg, span, abs_step, dir, span_limit, base;
+        float B2;
+        int hop, stage;
+        bool newton_limited;  // this stage's span was cut by the Newton-distance rule, not by the range limit
+        bool more;            // stopped at the stage limit, not at the |g| = M boundary: attempt again after landing
     };
-    __device__ __forceinline__ long long attempt_plan(Plan& pl) {
+#define RT_MARCH_MAX_STAGES 6
+    // plan_begin + plan_hop until it returns false + plan_end == attempt_plan (the hop loop is resumable so that
+    // a kernel can interleave it with other work).
+    //
+    // The hops are planned in STAGES.  A stage bounds |g''| over its whole span, so from far away the bound
+    // is loose and the hops stall (or the span, limited to twice the Newton distance, ends) well before the
+    // |g| = M boundary.  Re-planning from the point reached needs no exact advance -- only a Taylor shift
+    // of the model (21 FMAs) and a new, tighter bound -- so it is done right here; the accumulators are
+    // advanced once, by the total.  (It used to take a landing + a fresh attempt: 2.9 attempts per ray at
+    // level 0, 1.4 of them failing.)  M grows from stage to stage with the number of steps the jump may then
+    // cover; the stretch proven by an earlier stage only needed the smaller M of that stage.
+    __device__ __forceinline__ void plan_stage(Plan& pl) {
+        const double remaining = fmax(pl.span_limit - fabs(pl.shift), 0.0);
+        // do not look further than twice the Newton distance to the next root: the |g''| bound grows with the span
+        const double span = fmin(remaining, (2.0 * fabs(pl.s[0]) / fabs(pl.s[1]) + 32.0 * pl.abs_step));  // fmin ignores a NaN quotient
+        pl.newton_limited = span < remaining;
+        const double m_max = (fabs(pl.shift) + span) / pl.abs_step + 4.0;
+        pl.M = pl.base + m_max * P.drift1;
+        // furthest sigma in [0, span] such that the whole stretch is provably inside {|g| >= M, same sign}:
+        // hops of length 2b / (|g'| + sqrt(g'^2 + 2 B2 b)), b = |g| - M, B2 >= max |g''| over the span.
+        // The hop length is a lower bound, so it is computed in FP32 (rounded toward safety, shortened 1 %).
+        double b2 = 0.0, pw = 1.0;
+#pragma unroll
+        for (int k = 2; k <= DEG; k++) {
+            b2 += (double)(k * (k - 1)) * fabs(pl.s[k]) * pw;
+            pw *= span;
+        }
+        pl.B2 = __double2float_ru(b2 * (1.0 + 1e-9));
+        pl.sig = 0.0;
+        pl.g = pl.s[0];
+        pl.dg = pl.s[1];
+        pl.span = span;
+        pl.hop = 0;
+    }
+    __device__ __forceinline__ void plan_begin(Plan& pl) {
         if (!have_poly) {
             // expand around the current sample (the first one); covers every later sample of the ray
             double tau_hi = (end - t) + 4.0 * step0;
@@ -344,64 +403,87 @@ struct Marcher {
         // the range checks must not fire on skipped samples: stay 2 steps inside [start, end] and the model
         double tau_lim = (dir > 0.0 ? end : start) - P.t0 - dir * 2.0 * abs_step;
         tau_lim = fmin(fmax(tau_lim, 0.0), P.tau_hi);
-        // do not look further than twice the Newton distance to the next root: M grows with the span
-        double span = fmax((tau_lim - tau) * dir, 0.0);
-        span = fmin(span, (2.0 * fabs(s[0]) / fabs(s[1]) + 32.0 * abs_step));  // fmin ignores a NaN quotient
-        const double m_max = span / abs_step + 4.0;
-        // M for this jump: measured displacement now + the steps the jump may cover
+        pl.span_limit = fmax((tau_lim - tau) * dir, 0.0);
+        // the part of M that does not depend on the length of the jump: the displacement of the sample
+        // against the model line, measured now, and the evaluation / model rounding
         const double ex = p.x - fma(tau, d.x, P.p0.x), ey = p.y - fma(tau, d.y, P.p0.y),
                      ez = p.z - fma(tau, d.z, P.p0.z);
-        const double M = RT_MARCH_SAFETY * G * (fabs(ex) + fabs(ey) + fabs(ez)) + m_max * P.drift1 + P.err0;
-        pl.M = M;
-        // furthest sigma in [0, span] such that the whole stretch is provably inside {|g| >= M, same sign}:
-        // hops of length 2b / (|g'| + sqrt(g'^2 + 2 B2 b)), b = |g| - M, B2 >= max |g''| over the span.
-        // The hop length is a lower bound, so it is computed in FP32 (rounded toward safety, shortened 1 %).
-        double b2 = 0.0, pw = 1.0;
-#pragma unroll
-        for (int k = 2; k <= DEG; k++) {
-            b2 += (double)(k * (k - 1)) * fabs(s[k]) * pw;
-            pw *= span;
+        pl.base = RT_MARCH_SAFETY * G * (fabs(ex) + fabs(ey) + fabs(ez)) + P.err0;
+        pl.abs_step = abs_step;
+        pl.dir = dir;
+        pl.shift = 0.0;
+        pl.stage = 0;
+        pl.more = false;
+        plan_stage(pl);
+    }
+    // the stage ended short of the |g| = M boundary: re-plan from the point reached, if that may help
+    __device__ __forceinline__ bool plan_next_stage(Plan& pl, bool progressed) {
+        if (!progressed) return false;
+        if (pl.stage + 1 >= RT_MARCH_MAX_STAGES) {
+            pl.more = true;
+            return false;
         }
-        const float B2 = __double2float_ru(b2 * (1.0 + 1e-9));
-        double sig = 0.0, g = s[0], dg = s[1];
-        for (int hop = 0; hop < 32; hop++) {
-            if (PROF) prof[3]++;
-            const double b = fabs(g) - M;
-            if (!(b > 0.0)) break;
-            const float bf = __double2float_rd(b);
-            const float af = __double2float_ru(fabs(dg));
-            const float den = af + sqrtf(fmaf(af, af, 2.0f * B2 * bf));
-            const double dt = (double)(0.99f * (2.0f * bf / den));
-            const double ns = sig + dt;
-            if (ns >= span) {
-                sig = span;
-                break;
-            }
-            if (!(dt > abs_step)) break;
-            sig = ns;
-            const double x = dir * sig;
-            double v = s[DEG], dv = 0.0;
+        const double x = pl.dir * pl.sig;
 #pragma unroll
-            for (int k = DEG - 1; k >= 0; k--) {
-                dv = fma(dv, x, v);
-                v = fma(v, x, s[k]);
-            }
-            g = v;
-            dg = dv;
+        for (int i = 0; i < DEG; i++)
+#pragma unroll
+            for (int j = DEG - 1; j >= i; j--) pl.s[j] = fma(x, pl.s[j + 1], pl.s[j]);
+        pl.shift += x;
+        pl.stage++;
+        plan_stage(pl);
+        return true;
+    }
+    // one hop; false when the planning is over
+    __device__ __forceinline__ bool plan_hop(Plan& pl) {
+        if (pl.hop >= 32) return plan_next_stage(pl, pl.sig > 0.0);
+        pl.hop++;
+        if (PROF) prof[3]++;
+        const double b = fabs(pl.g) - pl.M;
+        if (!(b > 0.0)) return false;  // at the boundary of the uncertainty band: the jump ends here
+        const float bf = __double2float_rd(b);
+        const float af = __double2float_ru(fabs(pl.dg));
+        const float den = af + sqrtf(fmaf(af, af, 2.0f * pl.B2 * bf));
+        const double dt = (double)(0.99f * (2.0f * bf / den));
+        const double ns = pl.sig + dt;
+        if (ns >= pl.span) {
+            pl.sig = pl.span;
+            if (pl.newton_limited) return plan_next_stage(pl, pl.sig > 0.0);
+            return false;  // the range limit
         }
-        const double mf = sig / abs_step * (1.0 - 1e-9) - 2.0;
+        if (!(dt > pl.abs_step)) return plan_next_stage(pl, pl.sig > 8.0 * pl.abs_step);  // stalled: loose |g''| bound?
+        pl.sig = ns;
+        const double x = pl.dir * pl.sig;
+        double v = pl.s[DEG], dv = 0.0;
+#pragma unroll
+        for (int k = DEG - 1; k >= 0; k--) {
+            dv = fma(dv, x, v);
+            v = fma(v, x, pl.s[k]);
+        }
+        pl.g = v;
+        pl.dg = dv;
+        return true;
+    }
+    // the number of iterations that can be skipped (0: none, cooldown is set)
+    __device__ __forceinline__ long long plan_end(const Plan& pl) {
+        const double mf = (fabs(pl.shift) + pl.sig) / pl.abs_step * (1.0 - 1e-9) - 2.0;
         if (mf >= (double)RT_MARCH_MIN_JUMP) return (long long)fmin(mf, 1.0e15);
         // inside the |g| < M zone or next to a range limit: plain steps, retry later
         cooldown = backoff;
         backoff = min(backoff * 2, 64);
         return 0;
     }
+    __device__ __forceinline__ long long attempt_plan(Plan& pl) {
+        plan_begin(pl);
+        while (plan_hop(pl)) {
+        }
+        return plan_end(pl);
+    }
     // nt / np: t and p after m more iterations (advance_exact of t by step and of p by sd)
     __device__ __forceinline__ void attempt_land(const Plan& pl, double nt, D3 np) {
         const double land = surface_func<KIND>(q, np);  // the reference's `r = next` at the landing sample
         n++;
         if (PROF) prof[2]++;
-        const double x = nt - t;
+        const double x = (nt - t) - pl.shift;  // s[] is centred `shift` past the sample the jump started from
         double gp = pl.s[DEG];
 #pragma unroll
         for (int k = DEG - 1; k >= 0; k--) gp = fma(gp, x, pl.s[k]);
@@ -412,6 +494,10 @@ struct Marcher {
             p = np;
             r = land;
             backoff = 4;
+            // A jump that ran up to the |g| = M boundary (or to the range limit) has nothing left to skip: the
+            // next event is a few literal steps away.  Attempting again right away failed 4 times per ray
+            // (half of all attempts, each a full plan); only a jump cut short by the span / hop limit retries.
+            cooldown = pl.more ? 0 : RT_MARCH_LAND_COOLDOWN;
             return;
         }
         skip_ok = false;  // the model does not describe this ray: finish it with the plain loop
