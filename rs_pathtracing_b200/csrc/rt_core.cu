@@ -435,7 +435,11 @@ __device__ __forceinline__ void coop_advance(unsigned jumping, long long mj, dou
     for (int base = 0; base < tasks; base += 32) {
         const int task = base + lane;
         const bool active = task < tasks;
-        const int src = active ? (int)__fns(jumping, 0, (task >> 2) + 1) : lane;
+        // the lane that owns this task: the (task / 4)-th set bit of `jumping` (strip the lower ones;
+        // __fns is a long software loop)
+        unsigned rem = jumping;
+        for (int i = 0; i < (task >> 2) && rem; i++) rem &= rem - 1;
+        const int src = (active && rem) ? __ffs(rem) - 1 : lane;
         const int comp = task & 3;
         const double a0 = __shfl_sync(FULL, t, src), a1 = __shfl_sync(FULL, p.x, src), a2 = __shfl_sync(FULL, p.y, src),
                      a3 = __shfl_sync(FULL, p.z, src);
