@@ -249,7 +249,9 @@ __device__ __forceinline__ bool analytic_nearest_impl(const DevScene& S, const C
         while (mask) {
             const int j = __ffs(mask) - 1;
             mask &= mask - 1;
-            analytic_test<COUNT>(S, __ldg(flat_ids + f0 + j), ro, rd, min_t, best, winner, degenerate, c);
+            // (a NaN ray passes every pre-test, the padding entries' too: their id is -1)
+            const int id = __ldg(flat_ids + f0 + j);
+            if (id >= 0) analytic_test<COUNT>(S, id, ro, rd, min_t, best, winner, degenerate, c);
         }
     }
     if (COUNT) c.cull_tests += S.n_flat_real + S.n_roots;
@@ -273,7 +275,8 @@ __device__ __forceinline__ bool analytic_nearest_impl(const DevScene& S, const C
             while (mask) {
                 const int j = __ffs(mask) - 1;
                 mask &= mask - 1;
-                analytic_test<COUNT>(S, __ldg(S.cids + RT_CULL_GROUP * g + j), ro, rd, min_t, best, winner, degenerate, c);
+                const int id = __ldg(S.cids + RT_CULL_GROUP * g + j);
+                if (id >= 0) analytic_test<COUNT>(S, id, ro, rd, min_t, best, winner, degenerate, c);
             }
         }
     }

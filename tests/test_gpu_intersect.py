@@ -362,6 +362,11 @@ def test_cull_tree_sizes(n_spheres, spread, offset):
     o[::3] = rng.uniform(-1.5 * spread, 1.5 * spread, (2000, 3))   # a third of the rays start near the world origin
     tgt = rng.uniform(-spread, spread, (6000, 3)) + off
     rays = rt.make_rays(o, tgt - o)
+    # rays no pre-test can judge (NaN / zero / infinite components pass every ball test, padding entries
+    # included): they must come out like the literal loop's
+    odd = np.array([[0, 0, 0, math.nan, 0, 1], [1, 2, 3, 0, 0, 0], [math.nan, 0, 0, 0, 0, 1],
+                    [0, 0, 0, math.inf, 0, 0], [math.inf, 1, 1, 0, 1, 0]], dtype=np.float64)
+    rays = np.concatenate([rays, odd + np.concatenate([off, [0, 0, 0]])])
     want = check_parity(sc, rays)
     assert (want["index"] >= 0).mean() > (0.3 if offset == 0.0 else 0.05)
     sc.reset_stats()
