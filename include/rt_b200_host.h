@@ -60,6 +60,11 @@ int rth_renderer_start_rendering(rth_renderer* r, const rt_camera* camera, rt_im
 int rth_renderer_render_step(rth_renderer* r, rt_vec3* buffer, uint64_t buffer_len, int* done);
 int rth_renderer_stop_rendering(rth_renderer* r);
 
+
+/* image::save_buffer(path, &frame, w, h, ColorType::Rgba8) of the bins (src/bin/main_raylib.rs:64-75,
+ * src/bin/main.rs:72-83): writes an 8-bit RGBA PNG (stored deflate blocks; no external library). */
+int rth_save_png(const char* path, const uint8_t* rgba, uint32_t width, uint32_t height);
+
 #ifdef __cplusplus
 }
 #endif

@@ -174,6 +174,7 @@ HOST_SYMBOLS = {
     "rth_renderer_start_rendering": (C.c_int, [C.c_void_p, C.POINTER(Camera), ImageParams, C.c_uint32]),
     "rth_renderer_render_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]),
     "rth_renderer_stop_rendering": (C.c_int, [C.c_void_p]),
+    "rth_save_png": (C.c_int, [C.c_char_p, C.c_void_p, C.c_uint32, C.c_uint32]),
 }
 
 

@@ -250,6 +250,15 @@ def tonemap_rgba8(scene: Scene, frame: np.ndarray, device: int = 0) -> np.ndarra
     return out.reshape(frame.shape[:-1] + (4,))
 
 
+def save_png(path: str, rgba: np.ndarray) -> None:
+    """image::save_buffer of the bins (main_raylib.rs:64-75): (h, w, 4) uint8 -> PNG"""
+    rgba = np.ascontiguousarray(rgba, dtype=np.uint8)
+    if rgba.ndim != 3 or rgba.shape[2] != 4:
+        raise ValueError("rgba must have shape (h, w, 4)")
+    _check(_ffi.host().rth_save_png(path.encode(), rgba.ctypes.data_as(C.c_void_p), rgba.shape[1], rgba.shape[0]),
+           host=True)
+
+
 def measure_peaks(device: int = 0):
     a, b = C.c_double(), C.c_double()
     _check(_ffi.core().rt_measure_peaks(device, C.byref(a), C.byref(b)))

@@ -4,6 +4,9 @@
 #include <stdexcept>
 #include <string>
 
+#include <algorithm>
+#include <cstdio>
+#include <vector>
 #include "../../../include/rt_b200_host.h"
 #include "ray_tracing.hpp"
 
@@ -115,6 +118,70 @@ int rth_renderer_render_step(rth_renderer* r, rt_vec3* buffer, uint64_t len, int
 int rth_renderer_stop_rendering(rth_renderer* r) {
     if (!r) { g_err = "null argument"; return RT_ERR_INVALID; }
     return guarded([&] { r->r->stop_rendering(); });
+}
+
+// ---- PNG output ------------------------------------------------------------------------------
+static uint32_t crc32_update(uint32_t crc, const uint8_t* p, size_t n) {
+    static uint32_t table[256];
+    static bool init = false;
+    if (!init) {
+        for (uint32_t i = 0; i < 256; i++) {
+            uint32_t c = i;
+            for (int k = 0; k < 8; k++) c = (c & 1) ? 0xEDB88320u ^ (c >> 1) : c >> 1;
+            table[i] = c;
+        }
+        init = true;
+    }
+    for (size_t i = 0; i < n; i++) crc = table[(crc ^ p[i]) & 0xff] ^ (crc >> 8);
+    return crc;
+}
+static void put_be32(std::vector<uint8_t>& v, uint32_t x) {
+    v.push_back((uint8_t)(x >> 24)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x);
+}
+static void png_chunk(std::vector<uint8_t>& out, const char* type, const std::vector<uint8_t>& data) {
+    put_be32(out, (uint32_t)data.size());
+    size_t at = out.size();
+    out.insert(out.end(), type, type + 4);
+    out.insert(out.end(), data.begin(), data.end());
+    put_be32(out, crc32_update(0xFFFFFFFFu, out.data() + at, out.size() - at) ^ 0xFFFFFFFFu);
+}
+
+int rth_save_png(const char* path, const uint8_t* rgba, uint32_t width, uint32_t height) {
+    if (!path || !rgba || width == 0 || height == 0) { g_err = "null or empty argument"; return RT_ERR_INVALID; }
+    return guarded([&] {
+        // raw scanlines: filter byte 0 + width * 4 bytes
+        std::vector<uint8_t> raw;
+        raw.reserve((size_t)height * ((size_t)width * 4 + 1));
+        for (uint32_t y = 0; y < height; y++) {
+            raw.push_back(0);
+            raw.insert(raw.end(), rgba + (size_t)y * width * 4, rgba + (size_t)(y + 1) * width * 4);
+        }
+        // zlib stream of stored (uncompressed) deflate blocks
+        std::vector<uint8_t> z = {0x78, 0x01};
+        uint32_t a = 1, b = 0;  // Adler-32
+        for (size_t i = 0; i < raw.size(); i++) { a = (a + raw[i]) % 65521u; b = (b + a) % 65521u; }
+        for (size_t off = 0; off < raw.size(); off += 65535) {
+            size_t n = std::min<size_t>(65535, raw.size() - off);
+            z.push_back(off + n >= raw.size() ? 1 : 0);
+            z.push_back((uint8_t)(n & 0xff)); z.push_back((uint8_t)(n >> 8));
+            z.push_back((uint8_t)(~n & 0xff)); z.push_back((uint8_t)((~n >> 8) & 0xff));
+            z.insert(z.end(), raw.begin() + off, raw.begin() + off + n);
+        }
+        put_be32(z, (b << 16) | a);
+        std::vector<uint8_t> out = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+        std::vector<uint8_t> ihdr;
+        put_be32(ihdr, width);
+        put_be32(ihdr, height);
+        ihdr.insert(ihdr.end(), {8, 6, 0, 0, 0});  // 8 bit, RGBA, deflate, no filter, no interlace
+        png_chunk(out, "IHDR", ihdr);
+        png_chunk(out, "IDAT", z);
+        png_chunk(out, "IEND", {});
+        FILE* f = fopen(path, "wb");
+        if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+        size_t w = fwrite(out.data(), 1, out.size(), f);
+        fclose(f);
+        if (w != out.size()) throw std::runtime_error(std::string("short write to ") + path);
+    });
 }
 
 }  // extern "C"

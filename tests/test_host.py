@@ -244,3 +244,18 @@ def test_rust_sys_crate_covers_the_abi():
         body = re.search(r"pub struct %s \{(.*?)\}" % struct, src, re.S).group(1)
         rust_fields = re.findall(r"pub (\w+):", body)
         assert rust_fields == [f[0] for f in cls._fields_], struct
+
+
+def test_save_png_round_trips(tmp_path):
+    """rth_save_png (image::save_buffer of the bins): a valid PNG that decodes to the same RGBA bytes"""
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(0)
+    for w, h in ((7, 5), (300, 260)):          # 300*260*4 + 260 > 65535: several stored deflate blocks
+        rgba = rng.integers(0, 256, (h, w, 4), dtype=np.uint8)
+        path = str(tmp_path / f"t{w}.png")
+        rt.save_png(path, rgba)
+        with Image.open(path) as im:
+            assert im.mode == "RGBA" and im.size == (w, h)
+            assert np.array_equal(np.asarray(im), rgba)
+    with pytest.raises(rt.RtError):
+        rt.save_png(str(tmp_path / "no_such_dir" / "x.png"), rgba)

@@ -166,6 +166,7 @@ stress. cfg 5 (8.5 G paths) streams through the same 2 x 1.6 GB of path state as
 | `{cid}_source_hotspots.txt` | per-source-line instruction / sample shares of the three kernels |
 | `ncu_traffic.json` | DRAM bytes per launch from that capture (read by `bench.py` for `roofline.traffic`) |
 | `{cid}_configs_1gpu.md` | the five configurations |
+| `{cid}_render_*.jpg` | `tools/render.py` output (GpuRenderer -> rt_tonemap_rgba8 -> rth_save_png), 512x384, 256 spp, depth 50, as JPEG previews |
 | `r1a_*` ... `r1v_*` | earlier captures of this round (fused k_bounce; first wavefront split; cull tree; before / after the march work) |
 """
 open(os.path.join(P, "README.md"), "w").write(readme)
