@@ -297,6 +297,17 @@ int rt_set_kernel_timing(rt_scene* scene, int enabled);
  * region.  Exposed so that tests can check them against sampled derivatives; needs no device. */
 int rt_march_region_bounds(const double* params8, double* grad_bound, double* hess_bound);
 
+/* Host-only self-check of the conservative cull tree k_extend walks (csrc/rt_cull.cuh): builds the tree for
+ * `desc` exactly like rt_scene_create and verifies, in FP64, that every group ball encloses the balls of
+ * its leaves and every root ball the balls of its groups, with the slack the proof in rt_cull.cuh needs.
+ * Outputs: n_roots, n_groups (padded), n_tree (shapes under the tree), n_flat (shapes tested one by one),
+ * worst = the largest (member reach - node radius) / node radius found.  The node radius is read back from
+ * the FP32 table entry, which costs ~1e-8 relative; the entry itself carries a 1e-4 relative margin for the
+ * FP32 roundings (the factor 1.0101 instead of 1.01), so worst <= 1e-7 means every node encloses its members.
+ * Needs no device. */
+int rt_cull_tree_check(const rt_scene_desc* desc, uint32_t* n_roots, uint32_t* n_groups, uint32_t* n_tree,
+                       uint32_t* n_flat, double* worst);
+
 /* FP64 / FP32 FMA micro-benchmarks used as roofline denominators (TFLOP/s, FMA = 2 flop). */
 int rt_measure_peaks(int device, double* fp64_tflops, double* fp32_tflops);
 

@@ -1993,6 +1993,55 @@ int rt_march_region_bounds(const double* params8, double* grad_bound, double* he
     return RT_OK;
 }
 
+int rt_cull_tree_check(const rt_scene_desc* d, uint32_t* n_roots, uint32_t* n_groups, uint32_t* n_tree,
+                       uint32_t* n_flat, double* worst) {
+    int rc = validate_desc(d);
+    if (rc != RT_OK) return rc;
+    if (!n_roots || !n_groups || !n_tree || !n_flat || !worst) return fail(RT_ERR_INVALID, "null argument");
+    const int n = (int)d->n_shapes;
+    CullTree ct = cull_build(d->inverse, d->kind, n, false, false);
+    *n_roots = (uint32_t)ct.n_roots;
+    *n_groups = (uint32_t)ct.n_groups;
+    *n_flat = (uint32_t)ct.n_flat_real;
+    const float4* roots = ct.table.data();
+    const float4* grp = roots + ct.n_roots;
+    // radius a node entry stands for: A = 1.0101 (s R + sqrt(3B)(|c| + R))^2  ->  R
+    auto node_radius = [](float4 e) {
+        const double cn = sqrt((double)e.x * e.x + (double)e.y * e.y + (double)e.z * e.z);
+        const double x = sqrt((double)e.w / 1.0101);
+        return (x - sqrt(3.0 * RT_CULL_B) * cn) / (sqrt(1.1) + sqrt(3.0 * RT_CULL_B));
+    };
+    double w = -INFINITY;
+    uint32_t in_tree = 0;
+    std::vector<double> group_reach_c(3 * (size_t)ct.n_groups, 0.0), group_r((size_t)ct.n_groups, -1.0);
+    for (int i = 0; i < n; i++) {
+        const int g = ct.group_of[i];
+        if (g < 0) continue;
+        in_tree++;
+        if (g >= ct.n_groups || !isfinite(grp[g].w)) return fail(RT_ERR_STATE, "cull tree: shape in a padding group");
+        // the shape's true world ball, from its own transform (not from the table entry)
+        double r;
+        const float4 leaf = cull_entry(d->inverse + (size_t)12 * i, d->kind[i], &r);
+        const double* m = d->direct + (size_t)12 * i;   // centre = direct * origin
+        const double c[3] = {m[3], m[7], m[11]};
+        (void)leaf;
+        const double gr = node_radius(grp[g]);
+        const double dx = c[0] - grp[g].x, dy = c[1] - grp[g].y, dz = c[2] - grp[g].z;
+        w = fmax(w, (sqrt(dx * dx + dy * dy + dz * dz) + r - gr) / gr);
+        group_r[g] = gr;
+        const float4 rt_ = roots[g / RT_CULL_ROOT_FANOUT];
+        const double rr = node_radius(rt_);
+        const double ex = grp[g].x - rt_.x, ey = grp[g].y - rt_.y, ez = grp[g].z - rt_.z;
+        w = fmax(w, (sqrt(ex * ex + ey * ey + ez * ez) + ct.group_radius[g] - rr) / rr);
+        // and the leaf directly under the root
+        const double fx = c[0] - rt_.x, fy = c[1] - rt_.y, fz = c[2] - rt_.z;
+        w = fmax(w, (sqrt(fx * fx + fy * fy + fz * fz) + r - rr) / rr);
+    }
+    *n_tree = in_tree;
+    *worst = in_tree ? w : 0.0;
+    return RT_OK;
+}
+
 int rt_measure_peaks(int device, double* fp64_tflops, double* fp32_tflops) {
     int ndev = rt_device_count();
     if (ndev == 0) return fail(RT_ERR_NO_DEVICE, "no CUDA device");

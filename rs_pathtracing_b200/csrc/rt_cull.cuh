@@ -139,11 +139,13 @@ struct CullTree {
     std::vector<int> group_of;  // [n_shapes] group of a shape, -1 = flat list, -2 = not in the analytic loop
     std::vector<float4> leaf;   // [n_shapes] the shape's own entry (RT_ISECT_VERIFY)
     int n_roots = 0, n_groups = 0, n_flat = 0, n_flat_real = 0;
+    std::vector<double> group_radius;  // [groups built] the FP64 radius each group entry was made from (rt_cull_tree_check)
 };
 
 struct CullBall {
     double c[3], r;
 };
+
 
 // ball around member balls, FP32-representable centre
 inline CullBall cull_enclose(const std::vector<CullBall>& m) {
@@ -264,6 +266,7 @@ inline CullTree cull_build(const double* inverse, const uint8_t* kind, int n, bo
         }
         gball[g] = cull_enclose(m);
         grp[g] = cull_node_entry(gball[g]);
+        t.group_radius.push_back(gball[g].r);
     }
     for (int r = 0; r < t.n_roots; r++) {
         std::vector<CullBall> m;

@@ -259,3 +259,48 @@ def test_save_png_round_trips(tmp_path):
             assert np.array_equal(np.asarray(im), rgba)
     with pytest.raises(rt.RtError):
         rt.save_png(str(tmp_path / "no_such_dir" / "x.png"), rgba)
+
+
+@pytest.mark.parametrize("name", ["spheres.json", "cornell_box.json", "detached_materials.json", "dupin.json",
+                                  "light_source.json"])
+def test_cull_tree_nodes_enclose_their_members(name):
+    """host-side invariant of the conservative cull tree (csrc/rt_cull.cuh): with the centre taken from the
+    shape's own direct transform and the radius from its inverse, every leaf ball lies inside its group
+    ball and inside its root ball, every group ball inside its root ball (FP64, no device needed)"""
+    sc = rt.Scene.from_file(scene_path(name), random_spheres_seed=1)
+    d = sc.desc()
+    roots, groups, tree, flat = (C.c_uint32() for _ in range(4))
+    worst = C.c_double()
+    rc = _ffi.core().rt_cull_tree_check(C.byref(d), C.byref(roots), C.byref(groups), C.byref(tree), C.byref(flat),
+                                       C.byref(worst))
+    assert rc == 0
+    kinds = sc.shape_kinds()
+    assert tree.value + flat.value == int((kinds != _ffi.RT_SHAPE_MARCH).sum())
+    assert tree.value >= 470 and roots.value == 1 and groups.value % 8 == 0 and groups.value * 16 >= tree.value
+    assert flat.value <= 12                      # Rectangles, cubes next to them, the ground / sun spheres
+    assert worst.value <= 1e-7, worst.value      # relative reach of a member beyond its node's radius (header)
+
+
+def test_cull_tree_invariant_on_a_large_random_scene():
+    """several roots (> 512 shapes under the tree), rotated / anisotropic shapes, a cluster far from the origin"""
+    import json
+    rng = np.random.default_rng(11)
+    shapes = []
+    for k in range(1400):
+        c = rng.uniform(-20, 20, 3) + (np.array([3e5, -1e5, 2e5]) if k % 5 == 0 else 0.0)
+        r = float(rng.uniform(0.05, 0.5))
+        shapes.append({"type": "Cube" if k % 3 == 0 else "Sphere", "name": f"s{k}", "material": "M",
+                       "transform": {"translate": c.tolist(), "rotate": rng.uniform(-90, 90, 3).tolist(),
+                                     "scale": [r, r * float(rng.uniform(0.6, 1.6)), r * float(rng.uniform(0.6, 1.6))]}})
+    scene = {"camera": {"position": [0, 0, -10], "direction": [0, 0, 1], "up": [0, 1, 0], "fov": 40.0, "focal_length": 1.0},
+             "background": [0, 0, 0],
+             "materials": {"M": {"type": "Lambertian", "albedo": {"type": "SolidColor", "color": [0.9, 0.1, 0.1]}}},
+             "shapes": shapes}
+    sc = rt.Scene.from_json(json.dumps(scene), add_random_spheres=False)
+    d = sc.desc()
+    roots, groups, tree, flat = (C.c_uint32() for _ in range(4))
+    worst = C.c_double()
+    assert _ffi.core().rt_cull_tree_check(C.byref(d), C.byref(roots), C.byref(groups), C.byref(tree), C.byref(flat),
+                                         C.byref(worst)) == 0
+    assert tree.value + flat.value == 1400 and tree.value > 1300 and roots.value >= 3
+    assert worst.value <= 1e-7, worst.value
