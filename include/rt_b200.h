@@ -297,6 +297,11 @@ int rt_set_kernel_timing(rt_scene* scene, int enabled);
  * region.  Exposed so that tests can check them against sampled derivatives; needs no device. */
 int rt_march_region_bounds(const double* params8, double* grad_bound, double* hess_bound);
 
+/* Host-only build of the marcher's exact multi-step advance (csrc/rt_march.cuh, advance_exact): *out = the
+ * double `a` holds after m iterations of `a = a + s` (IEEE round-to-nearest-even), computed in
+ * O(binades crossed) like on the device.  Exposed so that CPU tests can compare it with the literal loop. */
+int rt_advance_exact(double a, double s, int64_t m, double* out);
+
 /* Host-only self-check of the conservative cull tree k_extend walks (csrc/rt_cull.cuh): builds the tree for
  * `desc` exactly like rt_scene_create and verifies, in FP64, that every group ball encloses the balls of
  * its leaves and every root ball the balls of its groups, with the slack the proof in rt_cull.cuh needs.

@@ -1993,6 +1993,12 @@ int rt_march_region_bounds(const double* params8, double* grad_bound, double* he
     return RT_OK;
 }
 
+int rt_advance_exact(double a, double s, int64_t m, double* out) {
+    if (!out) return fail(RT_ERR_INVALID, "null argument");
+    *out = advance_exact(a, s, (long long)m);
+    return RT_OK;
+}
+
 int rt_cull_tree_check(const rt_scene_desc* d, uint32_t* n_roots, uint32_t* n_groups, uint32_t* n_tree,
                        uint32_t* n_flat, double* worst) {
     int rc = validate_desc(d);

@@ -41,6 +41,8 @@
 // ray while the other lanes of the warp keep marching.
 // tests/test_gpu_intersect.py compares t bit-exactly with the oracle for all six surfaces.
 #pragma once
+#include <cstring>
+
 #include "rt_math.cuh"
 
 namespace rt {
@@ -49,7 +51,44 @@ namespace rt {
 // advance_iter: one unit of progress (m > 0 on entry): a bounded literal walk near zero, or one binade --
 // as many regular steps as provably stay inside it plus the few literal steps that cross its edge.
 // advance_exact loops over it; k_march's cooperative advance interleaves it with other lanes' work.
-__device__ __forceinline__ void advance_iter(double& a, const double s, long long& m) {
+// (host + device: the host build backs rt_advance_exact, which the CPU tests compare with the literal loop)
+__host__ __device__ __forceinline__ long long adv_bits(double x) {
+#ifdef __CUDA_ARCH__
+    return __double_as_longlong(x);
+#else
+    long long r;
+    memcpy(&r, &x, sizeof r);
+    return r;
+#endif
+}
+__host__ __device__ __forceinline__ double adv_from_bits(long long b) {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double(b);
+#else
+    double r;
+    memcpy(&r, &b, sizeof r);
+    return r;
+#endif
+}
+// a lower bound of num / D, at least 3 below it unless it is tiny (any smaller value is safe)
+__host__ __device__ __forceinline__ long long adv_room(unsigned long long num, unsigned long long D) {
+#ifdef __CUDA_ARCH__
+    // num rounded down, D rounded up, the fast division's <= 2 ulp (2.4e-7) more than covered by the factor
+    // 1 - 1e-6.  (__fdiv_rd is a subroutine call with a long slow path: 6 % of k_march's instructions.)
+    const float qf = __fdividef(__ull2float_rd(num), __ull2float_ru(D)) * 0.999999f;
+    return (long long)qf - 3;
+#else
+    return (long long)((double)num / (double)D * 0.999998) - 3;
+#endif
+}
+__host__ __device__ __forceinline__ bool adv_mul_fits(unsigned long long a, unsigned long long b) {
+#ifdef __CUDA_ARCH__
+    return __umul64hi(a, b) == 0;
+#else
+    return (unsigned long long)(((unsigned __int128)a * b) >> 64) == 0;
+#endif
+}
+__host__ __device__ __forceinline__ void advance_iter(double& a, const double s, long long& m) {
     const long long MANT = 0x000fffffffffffffLL;
     if (s == 0.0) {
         a = a + s;
@@ -79,11 +118,11 @@ __device__ __forceinline__ void advance_iter(double& a, const double s, long lon
         }
         return;
     }
-    const long long sb = __double_as_longlong(fabs(s));
+    const long long sb = adv_bits(fabs(s));
     const int sexp = (int)(sb >> 52);
     const long long Ms = (sb & MANT) | (1LL << 52);
     const bool s_neg = s < 0.0;
-    const long long bits = __double_as_longlong(a);
+    const long long bits = adv_bits(a);
     const int exp = (int)((bits >> 52) & 0x7ff);
     const long long mant = bits & MANT;
     const bool a_neg = bits < 0;
@@ -119,20 +158,17 @@ __device__ __forceinline__ void advance_iter(double& a, const double s, long lon
     const unsigned long long Du = (unsigned long long)D, mu = (unsigned long long)m;
     const unsigned long long lo = mu * Du;
     long long take;
-    if (__umul64hi(mu, Du) == 0 && lo <= num && num - lo >= 2 * Du) {
+    if (adv_mul_fits(mu, Du) && lo <= num && num - lo >= 2 * Du) {
         take = m;  // the whole jump stays inside the binade (the common case)
     } else {
-        // at most floor(num / D) - 2 from a float quotient pushed down at every stage (a smaller take is
-        // always safe: the remaining steps are simply handled by the next iteration): num rounded down, D
-        // rounded up, the fast division's <= 2 ulp (2.4e-7) more than covered by the factor 1 - 1e-6.
-        // (__fdiv_rd is a subroutine call with a long slow path: 6 % of k_march's instructions.)
-        const float qf = __fdividef(__ull2float_rd(num), __ull2float_ru(Du)) * 0.999999f;
-        long long room = (long long)qf - 3;
+        // at most floor(num / D) - 2 from a quotient pushed down at every stage (a smaller take is always
+        // safe: the remaining steps are simply handled by the next iteration)
+        long long room = adv_room(num, Du);
         if (room < 0) room = 0;
         take = room < m ? room : m;
     }
     if (take > 0) {
-        a = __longlong_as_double(up ? bits + take * D : bits - take * D);
+        a = adv_from_bits(up ? bits + take * D : bits - take * D);
         m -= take;
         if (m == 0) return;  // the common case: the whole jump in one binade
     }
@@ -145,7 +181,7 @@ __device__ __forceinline__ void advance_iter(double& a, const double s, long lon
 }
 
 // returns the value `a` holds after m iterations of `a = a + s` in IEEE double arithmetic
-__device__ __forceinline__ double advance_exact(double a, double s, long long m) {
+__host__ __device__ __forceinline__ double advance_exact(double a, double s, long long m) {
     while (m > 0) advance_iter(a, s, m);
     return a;
 }
