@@ -208,3 +208,20 @@ def test_work_counters_match_oracle():
     assert 0 < st.shape_tests < c["shape_tests"] // 4
     assert 0 < st.march_steps < c["march_steps"]
     assert st.kernel_launches > 0
+
+
+@pytest.mark.parametrize("name", ["spheres.json", "cornell_box.json", "dupin.json"])
+def test_alternative_schedules_give_the_same_frame(monkeypatch, name):
+    """the marching result does not depend on how the work is scheduled: the block-local wavefront marcher
+    (RT_B200_MARCH_V2, an experiment kept off by default), the fused k_bounce (RT_B200_FUSED_BOUNCE) and
+    other k_march voting thresholds reproduce the default frame bit for bit"""
+    w, h, spp, depth, seed = 96, 72, 4, 8, 21
+    sc = rt.Scene.from_file(scene_path(name), random_spheres_seed=1)
+    ref = gpu_frame(sc, sc.camera(), w, h, spp, depth, seed)
+    for var, val in (("RT_B200_MARCH_V2", "1"), ("RT_B200_FUSED_BOUNCE", "1"), ("RT_B200_MARCH_TUNE", "2,30,3"),
+                     ("RT_B200_NO_CULL_TREE", "1"), ("RT_B200_NO_MARCH_SKIP", "1")):
+        monkeypatch.setenv(var, val)
+        alt = rt.Scene.from_file(scene_path(name), random_spheres_seed=1)
+        got = gpu_frame(alt, alt.camera(), w, h, spp, depth, seed)
+        monkeypatch.delenv(var)
+        assert np.array_equal(got, ref), var
