@@ -313,6 +313,12 @@ int rt_advance_exact(double a, double s, int64_t m, double* out);
 int rt_cull_tree_check(const rt_scene_desc* desc, uint32_t* n_roots, uint32_t* n_groups, uint32_t* n_tree,
                        uint32_t* n_flat, double* worst);
 
+/* Host-only emulation of the cull decisions k_extend takes (same FP32 operations, each rounded once): for every
+ * ray, reached[r * n_shapes + i] = 1 when shape i would be handed to its exact test -- flat-list entry passed,
+ * or root, group and leaf balls all passed, or (ray-marched shape) the ball around its marching bound passed --
+ * and 0 when it is skipped.  CPU tests check "the oracle's test hits shape i  =>  reached" pair by pair. */
+int rt_cull_reached(const rt_scene_desc* desc, const rt_ray* rays, uint64_t n_rays, uint8_t* reached);
+
 /* FP64 / FP32 FMA micro-benchmarks used as roofline denominators (TFLOP/s, FMA = 2 flop). */
 int rt_measure_peaks(int device, double* fp64_tflops, double* fp32_tflops);
 

@@ -420,6 +420,10 @@ static bool sphere_intersect(const Shape& s, const Ray& ray, double min_t, doubl
     return true;
 }
 
+bool march_intersect_bound(const Shape& s, const Ray& local, double* start, double* end) {
+    return intersect_bound(s.p, local.origin, local.direction, start, end);
+}
+
 static bool march_intersect(const Shape& s, const Ray& ray, double min_t, double max_t, ObjHit* h,
                             Counters* c) {
     // ray_marching.rs:20-74

@@ -154,6 +154,9 @@ bool collection_ray_intersect(const Scene& sc, const Ray& ray, double min_t, dou
 // BvhNode::ray_hit — shapes/mod.rs:628-651 (what Scene::new really builds, world/mod.rs:35)
 bool bvh_ray_hit(const Scene& sc, const Ray& ray, double min_t, double max_t, Hit* hit, Counters* c);
 
+// ShapeFunction::intersect_bound of a ray-marched shape on an object-space ray (ray_marching.rs:135-145, 213-225)
+bool march_intersect_bound(const Shape& s, const Ray& local, double* start, double* end);
+
 // Perlin::noise / turb — src/algebra/noise.rs:43-86
 double perlin_noise(const rt_perlin& pn, V3 p);
 double perlin_turb(const rt_perlin& pn, V3 p, int depth);

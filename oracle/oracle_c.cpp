@@ -221,6 +221,29 @@ uint32_t orc_hardware_threads(void) {
     return n ? n : 1;
 }
 
+// ---- per-shape hits of one ray: Shape::ray_hit for EVERY shape with max_t = +inf (no shrinking), so that
+// tests can check the GPU core's conservative culling pair by pair.  hits[i] = 1 when shape i returns Some.
+// A ray-marched shape counts as hit as soon as its bound is entered (intersect_bound returns Some): that is
+// the decision the pre-test in front of it must never contradict.
+void orc_shape_hits(const Scene* sc, const rt_ray* ray, double min_t, uint8_t* hits) {
+    Ray r;
+    r.origin = fr(ray->origin);
+    r.direction = fr(ray->direction);
+    for (size_t i = 0; i < sc->shapes.size(); i++) {
+        const Shape& s = sc->shapes[i];
+        if (s.kind == RT_SHAPE_MARCH) {
+            Ray local;
+            local.origin = transform_point(s.inverse, r.origin);
+            local.direction = transform_vector(s.inverse, r.direction);
+            double start, end;
+            hits[i] = march_intersect_bound(s, local, &start, &end) ? 1 : 0;
+        } else {
+            Hit h;
+            hits[i] = shape_ray_hit(s, (int)i, r, min_t, INFINITY, &h, nullptr) ? 1 : 0;
+        }
+    }
+}
+
 // ---- Perlin noise (src/algebra/noise.rs) ---------------------------------------------------------
 double orc_perlin_noise(const rt_perlin* pn, rt_vec3 p) { return perlin_noise(*pn, fr(p)); }
 double orc_perlin_turb(const rt_perlin* pn, rt_vec3 p, int depth) { return perlin_turb(*pn, fr(p), depth); }

@@ -77,6 +77,7 @@ def lib() -> C.CDLL:
     L.orc_pixel_sample_colors.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]
     L.orc_hardware_threads.restype = C.c_uint32
+    L.orc_shape_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
     L.orc_perlin_noise.argtypes = [C.c_void_p, Vec3]
     L.orc_perlin_noise.restype = C.c_double
     L.orc_perlin_turb.argtypes = [C.c_void_p, Vec3, C.c_int]
@@ -222,6 +223,13 @@ class OracleScene:
             info["counters"] = dict(zip(["segments", "shape_tests", "march_steps", "march_rays", "aabb_tests"],
                                         [int(x) for x in cnt]))
         return buf, info
+
+    def shape_hits(self, ray, n_shapes: int, min_t=0.001) -> np.ndarray:
+        """Shape::ray_hit of EVERY shape for one ray with max_t = +inf (a marched shape: its bound); uint8[n_shapes]"""
+        ray = np.ascontiguousarray(ray, dtype=np.float64).reshape(6)
+        out = np.zeros(n_shapes, np.uint8)
+        lib().orc_shape_hits(self._h, ray.ctypes.data_as(C.c_void_p), min_t, out.ctypes.data_as(C.c_void_p))
+        return out
 
     def trace_pixel_samples(self, rays: np.ndarray, depth, seed=0, pixel_index=0, use_bvh=False):
         rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)

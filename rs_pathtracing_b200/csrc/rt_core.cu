@@ -2048,6 +2048,51 @@ int rt_cull_tree_check(const rt_scene_desc* d, uint32_t* n_roots, uint32_t* n_gr
     return RT_OK;
 }
 
+int rt_cull_reached(const rt_scene_desc* d, const rt_ray* rays, uint64_t n_rays, uint8_t* reached) {
+    int rc = validate_desc(d);
+    if (rc != RT_OK) return rc;
+    if ((n_rays && !rays) || !reached) return fail(RT_ERR_INVALID, "null argument");
+    const int n = (int)d->n_shapes;
+    const CullTree ct = cull_build(d->inverse, d->kind, n, false, false);
+    std::vector<std::pair<int, float4>> march;  // (shape, ball around its marching bound), like rt_scene_create
+    for (int i = 0; i < n; i++) {
+        if (d->kind[i] != RT_SHAPE_MARCH) continue;
+        const double* q = d->params + (size_t)i * RT_SHAPE_PARAMS;
+        double radius[3] = {q[7], q[7], q[7]};
+        if ((int)q[0] == RT_SURF_HEART) { radius[0] = 1.45; radius[1] = 1.45 / 2.05; radius[2] = 1.45; }
+        march.push_back({i, cull_entry_march_bound(d->inverse + (size_t)12 * i, radius)});
+    }
+    const float4* roots = ct.table.data();
+    const float4* groups = roots + ct.n_roots;
+    const float4* leaves = groups + ct.n_groups;
+    const float4* flat = leaves + (size_t)RT_CULL_GROUP * ct.n_groups;
+    const int* leaf_ids = ct.ids.data();
+    const int* flat_ids = leaf_ids + (size_t)RT_CULL_GROUP * ct.n_groups;
+    for (uint64_t r = 0; r < n_rays; r++) {
+        uint8_t* out = reached + r * (uint64_t)n;
+        memset(out, 0, (size_t)n);
+        const rt_ray& ray = rays[r];
+        const CullRay cr = make_cull_ray(ray.origin.x, ray.origin.y, ray.origin.z, ray.direction.x, ray.direction.y,
+                                         ray.direction.z);
+        for (int j = 0; j < ct.n_flat; j++)
+            if (flat_ids[j] >= 0 && cull_pass(cr, flat[j])) out[flat_ids[j]] = 1;
+        for (int rt_i = 0; rt_i < ct.n_roots; rt_i++) {
+            if (!cull_pass_node(cr, roots[rt_i])) continue;
+            const int g0 = RT_CULL_ROOT_FANOUT * rt_i, g1 = std::min(g0 + RT_CULL_ROOT_FANOUT, ct.n_groups);
+            for (int g = g0; g < g1; g++) {
+                if (!cull_pass_node(cr, groups[g])) continue;
+                for (int j = 0; j < RT_CULL_GROUP; j++) {
+                    const int id = leaf_ids[(size_t)RT_CULL_GROUP * g + j];
+                    if (id >= 0 && cull_pass(cr, leaves[(size_t)RT_CULL_GROUP * g + j])) out[id] = 1;
+                }
+            }
+        }
+        for (auto& m : march)
+            if (cull_pass(cr, m.second)) out[m.first] = 1;
+    }
+    return RT_OK;
+}
+
 int rt_measure_peaks(int device, double* fp64_tflops, double* fp32_tflops) {
     int ndev = rt_device_count();
     if (ndev == 0) return fail(RT_ERR_NO_DEVICE, "no CUDA device");

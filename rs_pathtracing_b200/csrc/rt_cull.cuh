@@ -287,34 +287,55 @@ struct CullRay {
     float ox, oy, oz, dx, dy, dz, rhs0, rhs1;  // rhs0 = 3B|o|^2 (leaf tests), rhs1 = 101 * 3B|o|^2 (node tests)
 };
 
-__device__ __forceinline__ CullRay make_cull_ray(double ox, double oy, double oz, double dx, double dy, double dz) {
+// FP32 operations of the pre-test, each rounded once (no contraction, no flush-to-zero): the _rn intrinsics on
+// the device, the IEEE operations of the host compiler (-ffp-contract=off) in the host build that backs
+// rt_cull_reached -- the same bits either way.
+#ifdef __CUDA_ARCH__
+#define RT_CF_FMA(a, b, c) __fmaf_rn(a, b, c)
+#define RT_CF_MUL(a, b) __fmul_rn(a, b)
+#define RT_CF_ADD(a, b) __fadd_rn(a, b)
+#define RT_CF_SUB(a, b) __fsub_rn(a, b)
+#define RT_CF_DIV(a, b) __fdiv_rn(a, b)
+#define RT_CF_SQRT(a) __fsqrt_rn(a)
+#define RT_CF_D2F(a) __double2float_rn(a)
+#else
+#define RT_CF_FMA(a, b, c) fmaf(a, b, c)
+#define RT_CF_MUL(a, b) ((float)(a) * (float)(b))
+#define RT_CF_ADD(a, b) ((float)(a) + (float)(b))
+#define RT_CF_SUB(a, b) ((float)(a) - (float)(b))
+#define RT_CF_DIV(a, b) ((float)(a) / (float)(b))
+#define RT_CF_SQRT(a) sqrtf(a)
+#define RT_CF_D2F(a) ((float)(a))
+#endif
+
+__host__ __device__ __forceinline__ CullRay make_cull_ray(double ox, double oy, double oz, double dx, double dy, double dz) {
     CullRay r;
-    r.ox = __double2float_rn(ox);
-    r.oy = __double2float_rn(oy);
-    r.oz = __double2float_rn(oz);
-    float x = __double2float_rn(dx), y = __double2float_rn(dy), z = __double2float_rn(dz);
-    float s = __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)));
-    float inv = __fdiv_rn(1.0f, __fsqrt_rn(s));
+    r.ox = RT_CF_D2F(ox);
+    r.oy = RT_CF_D2F(oy);
+    r.oz = RT_CF_D2F(oz);
+    float x = RT_CF_D2F(dx), y = RT_CF_D2F(dy), z = RT_CF_D2F(dz);
+    float s = RT_CF_FMA(z, z, RT_CF_FMA(y, y, RT_CF_MUL(x, x)));
+    float inv = RT_CF_DIV(1.0f, RT_CF_SQRT(s));
     if (!(s > 1e-30f && s < 1e30f)) inv = NAN;  // zero / denormal / huge / NaN direction: nothing is culled
-    r.dx = __fmul_rn(x, inv);
-    r.dy = __fmul_rn(y, inv);
-    r.dz = __fmul_rn(z, inv);
-    float oo = __fmaf_rn(r.oz, r.oz, __fmaf_rn(r.oy, r.oy, __fmul_rn(r.ox, r.ox)));
-    r.rhs0 = __fmul_rn((float)(3.0 * RT_CULL_B), oo);
-    r.rhs1 = __fmul_rn((float)(RT_CULL_NODE_RAY * 3.0 * RT_CULL_B * (1.0 + 1e-6)), oo);
+    r.dx = RT_CF_MUL(x, inv);
+    r.dy = RT_CF_MUL(y, inv);
+    r.dz = RT_CF_MUL(z, inv);
+    float oo = RT_CF_FMA(r.oz, r.oz, RT_CF_FMA(r.oy, r.oy, RT_CF_MUL(r.ox, r.ox)));
+    r.rhs0 = RT_CF_MUL((float)(3.0 * RT_CULL_B), oo);
+    r.rhs1 = RT_CF_MUL((float)(RT_CULL_NODE_RAY * 3.0 * RT_CULL_B * (1.0 + 1e-6)), oo);
     return r;
 }
 
 // true: the exact test must run.  s = (C, A) from cull_entry.
-__device__ __forceinline__ bool cull_pass(const CullRay& r, float4 s, float ray_rhs) {
-    float ocx = __fsub_rn(s.x, r.ox), ocy = __fsub_rn(s.y, r.oy), ocz = __fsub_rn(s.z, r.oz);
-    float b = __fmaf_rn(ocz, r.dz, __fmaf_rn(ocy, r.dy, __fmul_rn(ocx, r.dx)));
-    float px = __fmaf_rn(-b, r.dx, ocx), py = __fmaf_rn(-b, r.dy, ocy), pz = __fmaf_rn(-b, r.dz, ocz);
-    float p2 = __fmaf_rn(pz, pz, __fmaf_rn(py, py, __fmul_rn(px, px)));
-    float rhs = __fadd_rn(s.w, ray_rhs);
+__host__ __device__ __forceinline__ bool cull_pass(const CullRay& r, float4 s, float ray_rhs) {
+    float ocx = RT_CF_SUB(s.x, r.ox), ocy = RT_CF_SUB(s.y, r.oy), ocz = RT_CF_SUB(s.z, r.oz);
+    float b = RT_CF_FMA(ocz, r.dz, RT_CF_FMA(ocy, r.dy, RT_CF_MUL(ocx, r.dx)));
+    float px = RT_CF_FMA(-b, r.dx, ocx), py = RT_CF_FMA(-b, r.dy, ocy), pz = RT_CF_FMA(-b, r.dz, ocz);
+    float p2 = RT_CF_FMA(pz, pz, RT_CF_FMA(py, py, RT_CF_MUL(px, px)));
+    float rhs = RT_CF_ADD(s.w, ray_rhs);
     return !(p2 > rhs);
 }
-__device__ __forceinline__ bool cull_pass(const CullRay& r, float4 s) { return cull_pass(r, s, r.rhs0); }
-__device__ __forceinline__ bool cull_pass_node(const CullRay& r, float4 s) { return cull_pass(r, s, r.rhs1); }
+__host__ __device__ __forceinline__ bool cull_pass(const CullRay& r, float4 s) { return cull_pass(r, s, r.rhs0); }
+__host__ __device__ __forceinline__ bool cull_pass_node(const CullRay& r, float4 s) { return cull_pass(r, s, r.rhs1); }
 
 }  // namespace rt
