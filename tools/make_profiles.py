@@ -51,7 +51,7 @@ scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 acc = collections.defaultdict(list)
 metrics = collections.defaultdict(lambda: collections.defaultdict(list))
 want = {"smsp__thread_inst_executed_per_inst_executed.ratio": "lanes", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active": "fp64",
-        "sm__warps_active.avg.pct_of_peak_sustained_active": "occ", "smsp__issue_active.avg.pct": "issue",
+        "sm__warps_active.avg.pct_of_peak_sustained_active": "occ", "sm__inst_issued.avg.pct_of_peak_sustained_active": "issue",
         "launch__registers_per_thread": "regs", "gpu__time_duration.sum": "dur"}
 for r in rows[2:]:
     name = r[ik].split("<")[0].replace("void ", "")
@@ -120,7 +120,8 @@ command (`{cid}_launches_bench_cornell1024x256.csv`, first 400 launches, `--metr
   = {ex['fp32_pretest_tflops']:.2f} TFLOP/s FP32 ({ex['fp32_frac'] * 100:.1f} % of {ex['fp32_peak_tflops']:.1f}) + {ex['fp64_exact_tflops']:.2f} TFLOP/s FP64 ({ex['fp64_frac'] * 100:.1f} % of peak,
   i.e. {ex['fp64_frac'] * 200:.0f} % of the no-FMA ceiling);
 * ncu (`{cid}_ncu_full_extend_march_shade_cornell1024x4.md`, bounce levels 0 / 1 / 2): FP64 pipe {rng('k_extend', 'fp64')} % busy,
-  {rng('k_extend', 'lanes', '{:.1f}')} of 32 lanes active per instruction, achieved occupancy {rng('k_extend', 'occ')} %
+  {rng('k_extend', 'lanes', '{:.1f}')} of 32 lanes active per instruction (warp execution efficiency), SM issue slots
+  {rng('k_extend', 'issue')} % busy, achieved occupancy {rng('k_extend', 'occ')} %
   ({rng('k_extend', 'regs')} registers), stalls dominated by fixed-latency FP64 dependencies (`wait`) and L1/L2 loads
   of the 96 B inverse rows (`long_scoreboard`): the kernel is latency-bound, not issue-bound -- removing 29 % of
   its instructions (Rectangle fast path, marching-bound pre-cull) did not change its time, nor did 4 CTAs / SM;
@@ -131,8 +132,9 @@ command (`{cid}_launches_bench_cornell1024x256.csv`, first 400 launches, `--metr
 ## `k_march` (largest share)
 
 `{cid}_source_hotspots.txt` (per-source-line warp instructions and stall samples from the same capture,
-`tools/ncu_source_hotspots.py`). ncu, levels 0 / 1 / 2: {rng('k_march', 'lanes', '{:.1f}')} of 32 lanes active, FP64 pipe
-{rng('k_march', 'fp64')} %, 16 warps / SM (128 registers). Work per marched ray on this scene (`rt_stats.march_prof`):
+`tools/ncu_source_hotspots.py`). ncu, levels 0 / 1 / 2: {rng('k_march', 'lanes', '{:.1f}')} of 32 lanes active, SM issue slots
+{rng('k_march', 'issue')} % busy, FP64 pipe {rng('k_march', 'fp64')} %, 16 warps / SM (128 registers).  `k_shade`: {rng('k_shade', 'lanes', '{:.1f}')}
+lanes, issue {rng('k_shade', 'issue')} %, FP64 pipe {rng('k_shade', 'fp64')} %. Work per marched ray on this scene (`rt_stats.march_prof`):
 6.3 literal steps at level 0 + 12.8 at the refinement levels, 2.0 exact jumps, 16 hops of the skip bound.
 What was tried, with the measured effect on cornell 1024x1024x4 (k_march ms per 4 Mi paths):
 

@@ -9,7 +9,9 @@ WANT = [
     ("launch__shared_mem_per_block_dynamic", "dyn smem/block"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
     ("smsp__thread_inst_executed_per_inst_executed.ratio", "active threads / warp instr (of 32)"),
-    ("smsp__issue_active.avg.pct", "SM issue-slot utilisation %"),
+    ("sm__inst_issued.avg.pct_of_peak_sustained_active", "SM issue-slot utilisation % (inst issued, of peak)"),
+    ("sm__inst_executed.avg.per_cycle_active", "IPC (warp instructions / active cycle / SM)"),
+    ("smsp__warps_eligible.avg.per_cycle_active", "eligible warps / scheduler / cycle"),
     ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "FP64 pipe % of peak"),
     ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA (FP32) pipe % of peak"),
     ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe % of peak"),
