@@ -302,6 +302,12 @@ int rt_march_region_bounds(const double* params8, double* grad_bound, double* he
  * O(binades crossed) like on the device.  Exposed so that CPU tests can compare it with the literal loop. */
 int rt_advance_exact(double a, double s, int64_t m, double* out);
 
+/* Host-only build of the device's vector / scalar division (csrc/rt_math.cuh, div3_exact): the three quotients
+ * a[k] / s from one correctly rounded reciprocal and two FMA correction steps each.  q[3n] receives, for every
+ * triple a[3i..3i+2] and divisor s[i], what the device computes; CPU tests compare it bit for bit with the IEEE
+ * divisions the reference performs (Vector3d / f64, src/algebra/mod.rs:299-317).  Needs no device. */
+int rt_div3_exact(const double* a, const double* s, uint64_t n, double* q);
+
 /* Host-only self-check of the conservative cull tree k_extend walks (csrc/rt_cull.cuh): builds the tree for
  * `desc` exactly like rt_scene_create and verifies, in FP64, that every group ball encloses the balls of
  * its leaves and every root ball the balls of its groups, with the slack the proof in rt_cull.cuh needs.

@@ -101,6 +101,10 @@ __device__ __forceinline__ Staged stage_scene(const DevScene& S, bool use_smem) 
     float4* s_tab = reinterpret_cast<float4*>(rt_smem_raw);
     const int n = S.ctab_entries();
     for (int k = threadIdx.x; k < n; k += blockDim.x) s_tab[k] = S.ctab[k];
+    // the flat list's shape records (rt_scene.cuh, FlatRec) behind the table, 16 B at a time
+    const float4* frec = reinterpret_cast<const float4*>(S.frec);
+    const int nf = S.n_frec * (RT_FLAT_REC * 8 / 16);
+    for (int k = threadIdx.x; k < nf; k += blockDim.x) s_tab[n + k] = frec[k];
     __syncthreads();
     return Staged{true};
 }
@@ -924,43 +928,52 @@ k_shade(DevScene S, PathQueue in, const uint32_t* __restrict__ count_in, HitQueu
     const uint32_t n = *count_in;
     const uint32_t n_round = (n + 31u) & ~31u;
     const uint32_t stride = gridDim.x * blockDim.x;
+    // random_in_unit_sphere is drawn by the whole warp for its rejected lanes (coop_random_in_unit_sphere)
+    __shared__ uint4 s_ball_id[256];
+    uint4* const s_id = s_ball_id + (threadIdx.x & ~31u);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        bool alive = false;
+        bool alive = false, shading = false, need_ball = false;
         D3 no = mk(0, 0, 0), nd = mk(0, 0, 0), nb = mk(0, 0, 0);
+        D3 rd = mk(0, 0, 0), beta = mk(0, 0, 0), L = mk(0.0, 0.0, 0.0);
         uint32_t pid = 0;
+        HitRec h;
+        PathRng rng;
+        rng.k0 = k0; rng.k1 = k1;
+        rng.pixel = 0; rng.sample = 0;
+        rng.begin_event(level + 1);
         if (i < n) {
-            D3 rd = mk(in.dx[i], in.dy[i], in.dz[i]);
-            D3 beta = mk(in.bx[i], in.by[i], in.bz[i]);
+            rd = mk(in.dx[i], in.dy[i], in.dz[i]);
+            beta = mk(in.bx[i], in.by[i], in.bz[i]);
             pid = in.pid[i];
             const int bi = hq.index[i];
-            D3 L = mk(0.0, 0.0, 0.0);
             if (bi < 0) {
                 L = hadamard(beta, sky(rd));  // renderer/mod.rs:41-43
             } else if (level == max_depth) {
                 // depth == 0: black (:26-27)
             } else {
                 D3 ro = mk(in.ox[i], in.oy[i], in.oz[i]);
-                HitRec h;
                 finalize_hit(S, bi, hq.t[i], ro, rd, h);
                 uint32_t pl = pid / spp, s = pid % spp, x, y;
                 map.pixel_of(first_owned + pl, x, y);
-                PathRng rng;
-                rng.k0 = k0; rng.k1 = k1;
                 rng.pixel = x + y * map.width;
                 rng.sample = s;
-                rng.begin_event(level + 1);
-                D3 ndir, atten;
-                if (scatter_or_emit(S, h, rd, rng, ndir, atten)) {  // :29-32
-                    alive = true;
-                    no = h.point;
-                    nd = ndir;
-                    nb = hadamard(beta, atten);
-                } else {
-                    L = hadamard(beta, atten);  // :34-36
-                }
+                shading = true;
+                need_ball = material_needs_ball(S.materials[S.material[bi]]);
             }
-            if (!alive) radiance[pid] = make_float4((float)L.x, (float)L.y, (float)L.z, 1.0f);
         }
+        const D3 ball = coop_random_in_unit_sphere(need_ball, rng.pixel, rng.sample, level + 1, k0, k1, s_id);
+        if (shading) {
+            D3 ndir, atten;
+            if (scatter_or_emit(S, h, rd, rng, ndir, atten, &ball)) {  // :29-32
+                alive = true;
+                no = h.point;
+                nd = ndir;
+                nb = hadamard(beta, atten);
+            } else {
+                L = hadamard(beta, atten);  // :34-36
+            }
+        }
+        if (i < n && !alive) radiance[pid] = make_float4((float)L.x, (float)L.y, (float)L.z, 1.0f);
         uint32_t slot = queue_append(alive, count_out);
         if (alive) {
             out.ox[slot] = no.x; out.oy[slot] = no.y; out.oz[slot] = no.z;
@@ -1296,9 +1309,27 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
         if ((rc = upload(sc, ct.ids.data(), ct.ids.size(), &sc->ds.cids)) != RT_OK) return bail(rc);
         if ((rc = upload(sc, ct.leaf.data(), ct.leaf.size(), &sc->ds.cull)) != RT_OK) return bail(rc);
         if ((rc = upload(sc, ct.group_of.data(), ct.group_of.size(), &sc->ds.cull_group)) != RT_OK) return bail(rc);
+        // the flat list's shapes as self-contained records (rt_scene.cuh, FlatRec): inverse rows, Rectangle
+        // bounds, index and kind side by side, so that the exact test of flat entry j starts from one address
+        // known in advance instead of the chain cids[j] -> kind[id] -> inv[12 id] of dependent loads
+        sc->ds.n_frec = 0;
+        sc->ds.frec = nullptr;
+        if (ct.n_flat_real > 0 && ct.n_flat_real <= RT_FLAT_REC_MAX && !getenv("RT_B200_NO_FLAT_REC")) {
+            std::vector<double> frec((size_t)RT_FLAT_REC * ct.n_flat_real, 0.0);
+            for (int k = 0; k < ct.n_flat_real; k++) {
+                const int id = ct.ids[(size_t)RT_CULL_GROUP * ct.n_groups + k];
+                double* r = frec.data() + (size_t)RT_FLAT_REC * k;
+                for (int j = 0; j < 12; j++) r[j] = d->inverse[(size_t)12 * id + j];
+                for (int j = 0; j < 4; j++) r[12 + j] = d->params[(size_t)RT_SHAPE_PARAMS * id + j];
+                const int tag[2] = {id, (int)d->kind[id]};
+                memcpy(r + 16, tag, sizeof tag);
+            }
+            if ((rc = upload(sc, frec.data(), frec.size(), &sc->ds.frec)) != RT_OK) return bail(rc);
+            sc->ds.n_frec = ct.n_flat_real;
+        }
     }
-    // shared-memory staging: 16 B per table entry
-    sc->smem_bytes = (size_t)sc->ds.ctab_entries() * sizeof(float4);
+    // shared-memory staging: 16 B per table entry + the flat list's records
+    sc->smem_bytes = (size_t)sc->ds.ctab_entries() * sizeof(float4) + (size_t)sc->ds.n_frec * RT_FLAT_REC * sizeof(double);
     sc->use_smem = n > 0 && sc->smem_bytes > 0 && sc->smem_bytes <= sc->smem_optin;
     if (!sc->use_smem) sc->smem_bytes = 0;
     if (sc->smem_bytes > 48 * 1024) {
@@ -1996,6 +2027,12 @@ int rt_march_region_bounds(const double* params8, double* grad_bound, double* he
 int rt_advance_exact(double a, double s, int64_t m, double* out) {
     if (!out) return fail(RT_ERR_INVALID, "null argument");
     *out = advance_exact(a, s, (long long)m);
+    return RT_OK;
+}
+
+int rt_div3_exact(const double* a, const double* s, uint64_t n, double* q) {
+    if (!a || !s || !q) return fail(RT_ERR_INVALID, "null argument");
+    for (uint64_t i = 0; i < n; i++) div3_exact(a[3 * i], a[3 * i + 1], a[3 * i + 2], s[i], q[3 * i], q[3 * i + 1], q[3 * i + 2]);
     return RT_OK;
 }
 

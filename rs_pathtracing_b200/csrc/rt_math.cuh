@@ -7,7 +7,9 @@
 // Citations are file:line into dkarpushkin/rs-pathtracing.
 #pragma once
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/rt_b200.h"
 
@@ -23,7 +25,57 @@ __device__ __forceinline__ D3 operator-(D3 a, D3 b) { return {a.x - b.x, a.y - b
 __device__ __forceinline__ D3 operator-(D3 a) { return {-a.x, -a.y, -a.z}; }
 __device__ __forceinline__ D3 operator*(D3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
 __device__ __forceinline__ D3 operator*(double s, D3 a) { return {a.x * s, a.y * s, a.z * s}; }
-__device__ __forceinline__ D3 operator/(D3 a, double s) { return {a.x / s, a.y / s, a.z / s}; }
+// Vector / scalar (mod.rs:299-317: three IEEE divisions by the same divisor).  nvcc's inline division takes a
+// ~100-instruction slow path whenever the numerator is zero -- two components of every axis-aligned wall normal
+// -- which made `normalize` a quarter of k_shade.  div3_exact returns the same three correctly rounded
+// quotients from ONE correctly rounded reciprocal y = RN(1 / s) (Markstein: with r = a - s q computed exactly
+// by an FMA, q' = RN(q + r y) is RN(a / s) as soon as q is within one ulp of a / s; the first correction makes
+// q = RN(a y) faithful, the second one correctly rounded).  The FMAs are explicit, so -fmad=false does not
+// touch them.  Operands outside [2^-500, 2^500] (where r or q could leave the normal range) and s <= 0 take the
+// plain divisions; a zero numerator keeps its sign (s > 0).  Host build: rt_div3_exact, tests/test_div3_exact.py.
+__host__ __device__ __forceinline__ int fp_exponent_field(double v) {
+#ifdef __CUDA_ARCH__
+    return (__double2hiint(v) >> 20) & 0x7ff;
+#else
+    unsigned long long b;
+    memcpy(&b, &v, sizeof b);
+    return (int)((b >> 52) & 0x7ff);
+#endif
+}
+__host__ __device__ __forceinline__ bool div3_operand_ok(double v) {
+    return (unsigned)(fp_exponent_field(v) - 523) <= 1000u || v == 0.0;
+}
+__host__ __device__ __forceinline__ double quotient_by_rcp(double a, double s, double y) {
+    double q = a * y;
+    double r = fma(-s, q, a);
+    q = fma(r, y, q);
+    r = fma(-s, q, a);
+    q = fma(r, y, q);
+    return a == 0.0 ? a : q;
+}
+__host__ __device__ __forceinline__ void div3_exact(double ax, double ay, double az, double s, double& qx, double& qy,
+                                                    double& qz) {
+    if (s > 0.0 && (unsigned)(fp_exponent_field(s) - 523) <= 1000u && div3_operand_ok(ax) && div3_operand_ok(ay) &&
+        div3_operand_ok(az)) {
+#ifdef __CUDA_ARCH__
+        const double y = __drcp_rn(s);
+#else
+        const double y = 1.0 / s;
+#endif
+        qx = quotient_by_rcp(ax, s, y);
+        qy = quotient_by_rcp(ay, s, y);
+        qz = quotient_by_rcp(az, s, y);
+        return;
+    }
+    qx = ax / s;
+    qy = ay / s;
+    qz = az / s;
+}
+__device__ __forceinline__ D3 operator/(D3 a, double s) {
+    D3 q;
+    div3_exact(a.x, a.y, a.z, s, q.x, q.y, q.z);
+    return q;
+}
 // `*` between vectors is the dot product: (x*x' + y*y') + z*z'   (mod.rs:319-349)
 __device__ __forceinline__ double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ D3 hadamard(D3 a, D3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }  // product, :135-141
@@ -389,5 +441,79 @@ __device__ __forceinline__ D3 random_in_unit_sphere(PathRng& r) {
     }
 }
 __device__ __forceinline__ D3 random_unit(PathRng& r) { return normalize(random_in_unit_sphere(r)); }  // :86-88
+
+// Try number k of random_in_unit_sphere on a fresh event stream, computed out of sequence: the candidate is
+// doubles 3k, 3k+1, 3k+2 of the stream (blocks 3k/2 and 3k/2 + 1), mapped by random_range(-1, 1) -- the very
+// values the sequential loop above would draw in its iteration k.
+__device__ __forceinline__ D3 ball_try(uint32_t pixel, uint32_t sample, uint32_t event, uint32_t k, uint32_t k0,
+                                       uint32_t k1) {
+    const uint32_t i0 = 3u * k, b0 = i0 >> 1;
+    uint32_t A[4], B[4];
+    philox4x32_10(pixel, sample, event, b0, k0, k1, A);
+    philox4x32_10(pixel, sample, event, b0 + 1u, k0, k1, B);
+    const unsigned long long a_lo = ((unsigned long long)A[1] << 32) | A[0], a_hi = ((unsigned long long)A[3] << 32) | A[2];
+    const unsigned long long b_lo = ((unsigned long long)B[1] << 32) | B[0], b_hi = ((unsigned long long)B[3] << 32) | B[2];
+    const bool odd = (i0 & 1u) != 0u;
+    const unsigned long long w0 = odd ? a_hi : a_lo, w1 = odd ? b_lo : a_hi, w2 = odd ? b_hi : b_lo;
+    const double S53 = 1.0 / 9007199254740992.0;
+    const double u0 = (double)(w0 >> 11) * S53, u1 = (double)(w1 >> 11) * S53, u2 = (double)(w2 >> 11) * S53;
+    return mk(-1.0 + (1.0 - -1.0) * u0, -1.0 + (1.0 - -1.0) * u1, -1.0 + (1.0 - -1.0) * u2);
+}
+
+// random_in_unit_sphere for a whole warp.  The sequential rejection loop keeps a warp busy for its slowest lane
+// (5.7 rounds on average for 32 lanes that need 1.9 tries each: a third of the lanes active, 38 % of k_shade's
+// instructions).  Here every lane first evaluates its own try 0; after that ALL lanes work for the lanes still
+// rejected -- with nr of them left, lane j evaluates try (next + j % T) of the (j / T)-th rejected lane,
+// T = 32 / nr -- and each owner takes its first accepted candidate.  Same tries, same order of preference, same
+// arithmetic: the result is the sequential loop's, bit for bit.  Must be called by all 32 lanes;
+// s_id: 32 uint4 of shared memory private to the warp.  `event`, k0, k1 are warp-uniform.
+__device__ __forceinline__ D3 coop_random_in_unit_sphere(bool need, uint32_t pixel, uint32_t sample, uint32_t event,
+                                                         uint32_t k0, uint32_t k1, uint4* s_id) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    D3 v = mk(0.0, 0.0, 0.0);
+    bool pending = need;
+    if (need) {
+        v = ball_try(pixel, sample, event, 0u, k0, k1);
+        pending = !(dot(v, v) <= 1.0);
+    }
+    uint32_t next_try = 1u;
+    unsigned rej = __ballot_sync(FULL, pending);
+    while (rej) {
+        const int nr = __popc(rej);
+        const int T = 32 / nr;  // helpers per rejected lane
+        const int rank = __popc(rej & ((1u << lane) - 1u));
+        if (pending) s_id[rank] = make_uint4(pixel, sample, next_try, 0u);
+        __syncwarp();
+        const int orank = lane / T, off = lane - orank * T;
+        D3 w = mk(0.0, 0.0, 0.0);
+        bool acc = false;
+        if (orank < nr) {
+            const uint4 id = s_id[orank];
+            w = ball_try(id.x, id.y, event, id.z + (uint32_t)off, k0, k1);
+            acc = dot(w, w) <= 1.0;
+        }
+        const unsigned accm = __ballot_sync(FULL, acc);
+        __syncwarp();  // the reads of s_id are done before the next round overwrites it
+        int src = lane;
+        bool got = false;
+        if (pending) {
+            const unsigned mine = (accm >> (rank * T)) & (T == 32 ? FULL : ((1u << T) - 1u));
+            if (mine) {
+                src = rank * T + __ffs(mine) - 1;
+                got = true;
+            } else {
+                next_try += (uint32_t)T;
+            }
+        }
+        const double x = __shfl_sync(FULL, w.x, src), y = __shfl_sync(FULL, w.y, src), z = __shfl_sync(FULL, w.z, src);
+        if (got) {
+            v = mk(x, y, z);
+            pending = false;
+        }
+        rej = __ballot_sync(FULL, pending);
+    }
+    return v;
+}
 
 }  // namespace rt

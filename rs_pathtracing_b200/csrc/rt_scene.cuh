@@ -42,7 +42,14 @@ struct DevScene {
     const float4* cull;
     const int* cull_group;
     __host__ __device__ int ctab_entries() const { return n_roots + n_groups + RT_CULL_GROUP * n_groups + n_flat; }
+    // FlatRec: one record of RT_FLAT_REC doubles per flat-list entry, in flat-list order -- [0..11] inverse rows,
+    // [12..15] params 0..3 (Rectangle bounds), [16] = {int shape index, int kind}, [17] padding (144 B, 16-byte
+    // aligned).  n_frec = n_flat_real, or 0 when the flat list is too long to be worth staging.
+    int n_frec;
+    const double* frec;
 };
+#define RT_FLAT_REC 18
+#define RT_FLAT_REC_MAX 64
 
 // optional work counters (rt_stats); enabled per launch by a template flag
 struct DevCounters {
@@ -173,12 +180,18 @@ struct Staged {
     bool smem;
 };
 
-// one exact candidate test of analytic shape i (kind != MARCH) against the current best
-template <bool COUNT>
-__device__ __forceinline__ void analytic_test(const DevScene& S, int i, D3 ro, D3 rd, double min_t, double& best,
-                                              int& winner, bool& degenerate, DevCounters& c) {
-    const int kind = S.kind[i];
-    const double2* mp = reinterpret_cast<const double2*>(S.inv + 12 * i);  // rows are 96 B, 16-byte aligned
+// one exact candidate test of analytic shape i (kind != MARCH) against the current best.  mp: the shape's
+// inverse rows, q: its params; NC = read them through the non-coherent path (global arrays) or with plain
+// loads (records staged in shared memory)
+template <bool NC>
+__device__ __forceinline__ double2 ld2(const double2* p) {
+    if (NC) return __ldg(p);
+    return *p;
+}
+template <bool COUNT, bool NC>
+__device__ __forceinline__ void analytic_test_at(int i, int kind, const double2* mp, const double* q, D3 ro, D3 rd,
+                                                 double min_t, double& best, int& winner, bool& degenerate,
+                                                 DevCounters& c) {
     if (COUNT) c.shape_tests++;
     double t;
     bool ok;
@@ -186,7 +199,7 @@ __device__ __forceinline__ void analytic_test(const DevScene& S, int i, D3 ro, D
         // Rectangle::ray_intersect (shapes/mod.rs:181-190) needs only o.z, d.z to reject most rays: row 2 of the
         // inverse first, the other rows when x = -o.z / d.z is in range (same operations, same order as
         // xf_point / xf_vector + rect_candidate, so the same bits).
-        const double2 r20 = __ldg(mp + 4), r21 = __ldg(mp + 5);
+        const double2 r20 = ld2<NC>(mp + 4), r21 = ld2<NC>(mp + 5);
         const double oz = ro.x * r20.x + ro.y * r20.y + ro.z * r21.x + r21.y;
         const double dz = rd.x * r20.x + rd.y * r20.y + rd.z * r21.x;
         // o.z and d.z finite, non-zero and of the same sign: x = -o.z / d.z is negative (or -0), below min_t > 0
@@ -194,12 +207,11 @@ __device__ __forceinline__ void analytic_test(const DevScene& S, int i, D3 ro, D
         if (min_t > 0.0 && sgn > 0.0 && sgn < INFINITY) return;
         const double x = -oz / dz;
         if (x < min_t || x > best) return;
-        const double2 r00 = __ldg(mp), r01 = __ldg(mp + 1), r10 = __ldg(mp + 2), r11 = __ldg(mp + 3);
+        const double2 r00 = ld2<NC>(mp), r01 = ld2<NC>(mp + 1), r10 = ld2<NC>(mp + 2), r11 = ld2<NC>(mp + 3);
         const double ox = ro.x * r00.x + ro.y * r00.y + ro.z * r01.x + r01.y;
         const double oy = ro.x * r10.x + ro.y * r10.y + ro.z * r11.x + r11.y;
         const double dx = rd.x * r00.x + rd.y * r00.y + rd.z * r01.x;
         const double dy = rd.x * r10.x + rd.y * r10.y + rd.z * r11.x;
-        const double* q = S.params + RT_SHAPE_PARAMS * i;
         const double px = ox + dx * x, py = oy + dy * x;
         if (px < q[0] || px > q[2] || py < q[1] || py > q[3]) return;
         t = x;
@@ -208,7 +220,7 @@ __device__ __forceinline__ void analytic_test(const DevScene& S, int i, D3 ro, D
         double m[12];
 #pragma unroll
         for (int k = 0; k < 6; k++) {
-            double2 v = __ldg(mp + k);
+            double2 v = ld2<NC>(mp + k);
             m[2 * k] = v.x;
             m[2 * k + 1] = v.y;
         }
@@ -226,6 +238,12 @@ __device__ __forceinline__ void analytic_test(const DevScene& S, int i, D3 ro, D
         }
     }
 }
+template <bool COUNT>
+__device__ __forceinline__ void analytic_test(const DevScene& S, int i, D3 ro, D3 rd, double min_t, double& best,
+                                              int& winner, bool& degenerate, DevCounters& c) {
+    analytic_test_at<COUNT, true>(i, S.kind[i], reinterpret_cast<const double2*>(S.inv + 12 * i),  // rows are 96 B
+                                  S.params + RT_SHAPE_PARAMS * i, ro, rd, min_t, best, winner, degenerate, c);
+}
 
 // step 1.  Returns true when the ray is degenerate.  FP32 culling first (rt_cull.cuh): the flat list,
 // then roots -> groups -> leaves of the tree; each lane runs the exact test on its own survivors.
@@ -240,6 +258,21 @@ __device__ __forceinline__ bool analytic_nearest_impl(const DevScene& S, const C
     const float4* leaves = groups + S.n_groups;
     const float4* flat = leaves + RT_CULL_GROUP * S.n_groups;
     const int* flat_ids = S.cids + RT_CULL_GROUP * S.n_groups;
+    if (S.n_frec > 0) {
+        // the flat list through its records: entry j's exact test reads frec[j] (staged behind the table), and
+        // an entry that is never culled (w = +inf: Rectangles, ill-conditioned transforms) skips the pre-test,
+        // whose answer is known -- the same decisions as the loop below
+        const double* frec = SMEM ? reinterpret_cast<const double*>(rt_smem_raw + sizeof(float4) * S.ctab_entries())
+                                  : S.frec;
+        for (int j = 0; j < S.n_frec; j++) {
+            const float4 e = flat[j];
+            if (e.w != INFINITY && !cull_pass(cr, e)) continue;
+            const double* r = frec + RT_FLAT_REC * j;
+            const int2 tag = *reinterpret_cast<const int2*>(r + 16);
+            if (SMEM) analytic_test_at<COUNT, false>(tag.x, tag.y, reinterpret_cast<const double2*>(r), r + 12, ro, rd, min_t, best, winner, degenerate, c);
+            else analytic_test_at<COUNT, true>(tag.x, tag.y, reinterpret_cast<const double2*>(r), r + 12, ro, rd, min_t, best, winner, degenerate, c);
+        }
+    } else
     for (int f0 = 0; f0 < S.n_flat; f0 += 32) {
         const int nf = min(32, S.n_flat - f0);  // a multiple of 8
         uint32_t mask = 0;
@@ -445,12 +478,17 @@ __device__ __forceinline__ double reflectance(double cosine, double ref_index) {
 
 // Material::scatter (src/world/material.rs:42-115).  Returns false when the material does not
 // scatter (DiffuseLight, EmptyMaterial); then `atten` holds Material::emitted (:123-127).
+// `ball`: random_in_unit_sphere drawn beforehand at the start of the event's stream (k_shade samples it
+// warp-cooperatively, material_needs_ball says for which lanes), or nullptr to draw it here.
+__device__ __forceinline__ bool material_needs_ball(const rt_material& m) {
+    return m.kind == RT_MAT_LAMBERTIAN || (m.kind == RT_MAT_METAL && m.scalar != 0.0);
+}
 __device__ inline bool scatter_or_emit(const DevScene& S, const HitRec& h, D3 rd, PathRng& rng, D3& new_dir,
-                                       D3& atten) {
+                                       D3& atten, const D3* ball = nullptr) {
     const rt_material m = S.materials[S.material[h.shape]];
     switch (m.kind) {
         case RT_MAT_LAMBERTIAN: {  // :42-53
-            D3 direction = h.normal + random_unit(rng);
+            D3 direction = h.normal + (ball ? normalize(*ball) : random_unit(rng));
             if (approx_zero(direction.x) && approx_zero(direction.y) && approx_zero(direction.z)) direction = h.normal;
             new_dir = normalize(direction);  // Ray::new, ray.rs:12-17
             atten = texture_value(S, m.texture, h.u, h.v, h.point);
@@ -458,7 +496,8 @@ __device__ inline bool scatter_or_emit(const DevScene& S, const HitRec& h, D3 rd
         }
         case RT_MAT_METAL: {  // :64-75
             D3 reflected = reflect(rd, h.normal);
-            D3 direction = (m.scalar == 0.0) ? reflected : reflected + m.scalar * random_in_unit_sphere(rng);
+            D3 direction = (m.scalar == 0.0) ? reflected
+                                             : reflected + m.scalar * (ball ? *ball : random_in_unit_sphere(rng));
             new_dir = normalize(direction);
             atten = texture_value(S, m.texture, h.u, h.v, h.point);
             return true;
