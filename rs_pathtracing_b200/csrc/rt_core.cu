@@ -952,13 +952,14 @@ k_shade(DevScene S, PathQueue in, const uint32_t* __restrict__ count_in, HitQueu
                 // depth == 0: black (:26-27)
             } else {
                 D3 ro = mk(in.ox[i], in.oy[i], in.oz[i]);
-                finalize_hit(S, bi, hq.t[i], ro, rd, h);
+                const rt_material mat = S.materials[S.material[bi]];
+                finalize_hit(S, bi, hq.t[i], ro, rd, h, material_reads_uv(S, mat));
                 uint32_t pl = pid / spp, s = pid % spp, x, y;
                 map.pixel_of(first_owned + pl, x, y);
                 rng.pixel = x + y * map.width;
                 rng.sample = s;
                 shading = true;
-                need_ball = material_needs_ball(S.materials[S.material[bi]]);
+                need_ball = material_needs_ball(mat);
             }
         }
         const D3 ball = coop_random_in_unit_sphere(need_ball, rng.pixel, rng.sample, level + 1, k0, k1, s_id);

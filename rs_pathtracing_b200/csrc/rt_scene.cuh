@@ -71,7 +71,9 @@ struct HitRec {  // RayHit, src/world/ray.rs:21-29
 // Rebuild the winner's RayHit from (shape, t, ray): Shape::ray_hit_transformed
 // (src/world/shapes/mod.rs:112-124) around the tail of each ray_intersect and RayHit::new /
 // set_normal (src/world/ray.rs:32-64).
-__device__ inline void finalize_hit(const DevScene& S, int i, double t, D3 ro, D3 rd, HitRec& h) {
+// want_uv = false: the caller knows (u, v) will not be read (material_reads_uv) -- the Sphere's acos / atan2 and the
+// Rectangle's two divisions are skipped and u = v = 0.
+__device__ inline void finalize_hit(const DevScene& S, int i, double t, D3 ro, D3 rd, HitRec& h, bool want_uv = true) {
     const double* inv = S.inv + 12 * i;
     const double* q = S.params + RT_SHAPE_PARAMS * i;
     const double PI = 3.14159265358979323846264338327950288;
@@ -83,10 +85,12 @@ __device__ inline void finalize_hit(const DevScene& S, int i, double t, D3 ro, D
     switch (S.kind[i]) {
         case RT_SHAPE_SPHERE: {  // shapes/mod.rs:358-373
             n = (S.flags[i] & RT_SHAPE_FLAG_INVERSE_NORMAL) ? -p : p;
-            double theta = acos(-p.y);
-            double phi = atan2(-p.z, p.x) + PI;
-            u = phi / (2.0 * PI);
-            v = theta / PI;
+            if (want_uv) {
+                double theta = acos(-p.y);
+                double phi = atan2(-p.z, p.x) + PI;
+                u = phi / (2.0 * PI);
+                v = theta / PI;
+            }
             break;
         }
         case RT_SHAPE_CUBE: {  // :263-283
@@ -99,8 +103,10 @@ __device__ inline void finalize_hit(const DevScene& S, int i, double t, D3 ro, D
         }
         case RT_SHAPE_RECTANGLE: {  // :191-201
             n = mk(0.0, 0.0, 1.0);
-            u = (p.x - q[0]) / (q[2] - q[0]);
-            v = (p.y - q[1]) / (q[3] - q[1]);
+            if (want_uv) {
+                u = (p.x - q[0]) / (q[2] - q[0]);
+                v = (p.y - q[1]) / (q[3] - q[1]);
+            }
             break;
         }
         default: {  // RT_SHAPE_MARCH, ray_marching.rs:59-61
@@ -480,6 +486,12 @@ __device__ __forceinline__ double reflectance(double cosine, double ref_index) {
 // scatter (DiffuseLight, EmptyMaterial); then `atten` holds Material::emitted (:123-127).
 // `ball`: random_in_unit_sphere drawn beforehand at the start of the event's stream (k_shade samples it
 // warp-cooperatively, material_needs_ball says for which lanes), or nullptr to draw it here.
+// Only texture lookups read the hit's (u, v), and a SolidColor root never does (texture.rs:17-24); Dielectric
+// and EmptyMaterial have no texture at all.
+__device__ __forceinline__ bool material_reads_uv(const DevScene& S, const rt_material& m) {
+    if (m.kind == RT_MAT_DIELECTRIC || m.kind == RT_MAT_EMPTY) return false;
+    return S.textures[m.texture].kind != RT_TEX_SOLID;
+}
 __device__ __forceinline__ bool material_needs_ball(const rt_material& m) {
     return m.kind == RT_MAT_LAMBERTIAN || (m.kind == RT_MAT_METAL && m.scalar != 0.0);
 }
