@@ -430,20 +430,23 @@ __device__ __noinline__ void replay_brute(const DevScene& S, const PathQueue& in
 // four advances in a row while the others wait.  Must be called by the whole warp (convergent).
 template <class CoWork>
 __device__ __forceinline__ void coop_advance(unsigned jumping, long long mj, double t, double step, D3 p, D3 sd,
-                                             double& nt, D3& np, CoWork&& co_work) {
+                                             double& nt, D3& np, unsigned char* s_owner, CoWork&& co_work) {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const int tasks = 4 * __popc(jumping);
-    const int my_first = 4 * __popc(jumping & ((1u << lane) - 1u));  // task number of this lane's t
+    const int my_rank = __popc(jumping & ((1u << lane) - 1u));
+    const int my_first = 4 * my_rank;  // task number of this lane's t
+    // the lane that owns task number k is the (k / 4)-th set bit of `jumping`: every jumping lane posts its
+    // number at its rank (s_owner: 32 bytes of shared memory private to the warp; __fns is a long software
+    // loop, stripping the lower bits one by one was 3.7 % of k_march's instructions)
+    __syncwarp();
+    if ((jumping >> lane) & 1u) s_owner[my_rank] = (unsigned char)lane;
+    __syncwarp();
     double out[4] = {0.0, 0.0, 0.0, 0.0};
     for (int base = 0; base < tasks; base += 32) {
         const int task = base + lane;
         const bool active = task < tasks;
-        // the lane that owns this task: the (task / 4)-th set bit of `jumping` (strip the lower ones;
-        // __fns is a long software loop)
-        unsigned rem = jumping;
-        for (int i = 0; i < (task >> 2) && rem; i++) rem &= rem - 1;
-        const int src = (active && rem) ? __ffs(rem) - 1 : lane;
+        const int src = active ? (int)s_owner[task >> 2] : lane;
         const int comp = task & 3;
         const double a0 = __shfl_sync(FULL, t, src), a1 = __shfl_sync(FULL, p.x, src), a2 = __shfl_sync(FULL, p.y, src),
                      a3 = __shfl_sync(FULL, p.z, src);
@@ -491,6 +494,8 @@ k_march(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32_
     const uint32_t n = *march_count;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
+    __shared__ unsigned char s_owner_all[128];
+    unsigned char* const s_owner = s_owner_all + (threadIdx.x & ~31u);
     bool have = false, marching = false, exhausted = false;
     uint32_t slot = 0, mask = 0, entry = 0;
     int shape = -1, winner = -1;
@@ -583,7 +588,7 @@ k_march(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32_
             if (jumping) {
                 double nt = 0.0;
                 D3 np = mk(0.0, 0.0, 0.0);
-                coop_advance(jumping, mj, m.t, m.step, m.p, m.sd, nt, np, []() {});
+                coop_advance(jumping, mj, m.t, m.step, m.p, m.sd, nt, np, s_owner, []() {});
                 if (mj > 0) m.attempt_land(pl, nt, np);
             }
         } else if (want_literal) {
@@ -722,6 +727,8 @@ k_march2(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32
     __shared__ uint32_t s_len[4];
     __shared__ uint32_t s_base, s_take, s_next;
     __shared__ int s_exhausted;
+    __shared__ unsigned char s_owner_all[RT_M2_THREADS];
+    unsigned char* const s_owner = s_owner_all + (threadIdx.x & ~31u);
     DevCounters c = {};
     MarchRec* state = state_all + (size_t)blockIdx.x * RT_M2_SLOTS;
     const uint32_t n = *march_count;
@@ -805,7 +812,7 @@ k_march2(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32
                 if (jumping) {
                     double nt = 0.0;
                     D3 np = mk(0.0, 0.0, 0.0);
-                    coop_advance(jumping, mj, m.t, m.step, m.p, m.sd, nt, np, []() {});
+                    coop_advance(jumping, mj, m.t, m.step, m.p, m.sd, nt, np, s_owner, []() {});
                     if (mj > 0) m.attempt_land(pl, nt, np);
                 }
                 if (active) {
@@ -920,6 +927,7 @@ k_replay(DevScene S, PathQueue in, HitQueue hq, const uint32_t* __restrict__ rep
     }
 }
 
+// (64 registers / 4 CTAs per SM was measured: spills, 1.44 -> 1.64 ms per 4 Mi paths)
 template <bool COUNT>
 __global__ void __launch_bounds__(256)
 k_shade(DevScene S, PathQueue in, const uint32_t* __restrict__ count_in, HitQueue hq, PathQueue out, uint32_t* count_out,

@@ -70,16 +70,33 @@ __host__ __device__ __forceinline__ double adv_from_bits(long long b) {
     return r;
 #endif
 }
-// a lower bound of num / D, at least 3 below it unless it is tiny (any smaller value is safe)
-__host__ __device__ __forceinline__ long long adv_room(unsigned long long num, unsigned long long D) {
+// floor(num / D) for num < 2^52, D >= 1 -- or, when the quotient is 2^20 or more, a lower bound at least 3
+// below it (any smaller value is safe: the remaining steps are simply handled by the next iterations).
+// The quotient is estimated in FP32 (conversions + fast division: relative error < 2^-20, so the estimate
+// is within 2 of the truth below 2^20) and corrected exactly with one 64-bit multiplication; the correction
+// loops make the result independent of the quality of the estimate.  (__fdiv_rd is a subroutine call with a
+// long slow path, a 64-bit integer division ~100 instructions.)
+__host__ __device__ __forceinline__ long long adv_steps_to_edge(unsigned long long num, unsigned long long D) {
 #ifdef __CUDA_ARCH__
-    // num rounded down, D rounded up, the fast division's <= 2 ulp (2.4e-7) more than covered by the factor
-    // 1 - 1e-6.  (__fdiv_rd is a subroutine call with a long slow path: 6 % of k_march's instructions.)
-    const float qf = __fdividef(__ull2float_rd(num), __ull2float_ru(D)) * 0.999999f;
-    return (long long)qf - 3;
+    const float qf = __fdividef(__ull2float_rd(num), __ull2float_ru(D));
 #else
-    return (long long)((double)num / (double)D * 0.999998) - 3;
+    const float qf = (float)num / (float)D;
 #endif
+    if (!(qf < 1048576.0f)) {
+        const long long room = (long long)(qf * 0.99999f) - 3;
+        return room;
+    }
+    long long q = (long long)qf;
+    long long r = (long long)num - q * (long long)D;  // |q D| < 2^21 * 2^52
+    while (r < 0) {
+        q--;
+        r += (long long)D;
+    }
+    while (r >= (long long)D) {
+        q++;
+        r -= (long long)D;
+    }
+    return q;
 }
 __host__ __device__ __forceinline__ bool adv_mul_fits(unsigned long long a, unsigned long long b) {
 #ifdef __CUDA_ARCH__
@@ -151,19 +168,18 @@ __host__ __device__ __forceinline__ void advance_iter(double& a, const double s,
         m = 0;
         return;
     }
-    // steps that provably stay inside this binade (going down, the landing mantissa must stay >= 1):
-    // take <= num / D - 2, in integer arithmetic (64-bit int <-> double conversions and a double
-    // division per binade used to dominate the marcher)
+    // Steps that stay inside this binade.  Going up, j steps are regular as long as mant + j D <= MANT: the
+    // exact sum (mant + (j - 1) D + S) u + rem is below (MANT + 1) u = 2^(e+1), so it is rounded on this
+    // binade's grid.  Going down, as long as mant - j D >= 1: the exact difference then lies above 2^e (by
+    // u - rem > 0 when D = S + 1, by more than u / 2 when D = S).  So floor(num / D) steps are regular and
+    // the one after them -- the only one whose rounding is irregular -- is taken literally.
     const unsigned long long num = (unsigned long long)(up ? (MANT - mant) : (mant - 1));
     const unsigned long long Du = (unsigned long long)D, mu = (unsigned long long)m;
-    const unsigned long long lo = mu * Du;
     long long take;
-    if (adv_mul_fits(mu, Du) && lo <= num && num - lo >= 2 * Du) {
+    if (adv_mul_fits(mu, Du) && mu * Du <= num) {
         take = m;  // the whole jump stays inside the binade (the common case)
     } else {
-        // at most floor(num / D) - 2 from a quotient pushed down at every stage (a smaller take is always
-        // safe: the remaining steps are simply handled by the next iteration)
-        long long room = adv_room(num, Du);
+        long long room = adv_steps_to_edge(num, Du);  // < m here (or a lower bound of it)
         if (room < 0) room = 0;
         take = room < m ? room : m;
     }
@@ -172,12 +188,9 @@ __host__ __device__ __forceinline__ void advance_iter(double& a, const double s,
         m -= take;
         if (m == 0) return;  // the common case: the whole jump in one binade
     }
-    // next to the binade edge (the margin above leaves 2-3 steps): literal steps carry it across
-#pragma unroll 1
-    for (int e = 0; e < 4 && m > 0; e++) {
-        a = a + s;
-        m--;
-    }
+    // at the binade edge: one literal step carries it across
+    a = a + s;
+    m--;
 }
 
 // returns the value `a` holds after m iterations of `a = a + s` in IEEE double arithmetic
