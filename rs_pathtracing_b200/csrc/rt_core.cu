@@ -240,7 +240,8 @@ __device__ __forceinline__ uint32_t queue_append(bool alive, uint32_t* counter) 
 // path id = pixel_local * spp + sample.  Padding pixels of clipped tiles produce no path.
 __global__ void __launch_bounds__(256)
 k_raygen(RayCasterDev rc, ShardMap map, unsigned long long first_owned, uint32_t n_pixels, uint32_t spp,
-         uint32_t k0, uint32_t k1, PathQueue q, uint32_t* count_out, float4* __restrict__ radiance) {
+         uint32_t k0, uint32_t k1, PathQueue q, uint32_t* count_out, float4* __restrict__ radiance,
+         uint2* __restrict__ path_key) {
     const unsigned long long n = (unsigned long long)n_pixels * spp;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     // round the trip count up so that whole warps stay converged for the ballot in queue_append
@@ -263,6 +264,7 @@ k_raygen(RayCasterDev rc, ShardMap map, unsigned long long first_owned, uint32_t
                 D3 d = rc.left_top + (rc.pixel_resolution * ((double)x + u)) * rc.camera_right -
                        (rc.pixel_resolution * ((double)y + v)) * rc.camera_up;
                 dir = normalize(d - rc.camera_position);  // Ray::new
+                path_key[id] = make_uint2(rng.pixel, s);
                 alive = true;
             } else {
                 radiance[id] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -352,6 +354,8 @@ struct HitQueue {
     uint32_t* mq_slot;  // march queue: path slot ...
     uint32_t* mq_mask;  // ... and the marched shapes (bit k = S.march_index[k]) it still has to test
     uint32_t* rq_slot;  // replay queue: degenerate rays (Sphere D == 0, NaN t) that must go through the literal loop
+    uint2* key;         // [path id] the path's RNG key (image pixel index, sample), written once by k_raygen /
+                        // k_load_rays: k_shade reads 8 B instead of redoing six integer divisions per segment
 };
 
 // per-level counters of one batch (zeroed by one memset): live paths, march / replay queue lengths and
@@ -368,7 +372,8 @@ struct HitQueue {
 template <bool COUNT>
 __global__ void __launch_bounds__(256, RT_EXTEND_MIN_BLOCKS)
 k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ count_in, HitQueue hq,
-         uint32_t* march_count, uint32_t* replay_count, DevCounters* g_counters, bool any_hit_suffices) {
+         uint32_t* march_count, uint32_t* replay_count, DevCounters* g_counters, bool any_hit_suffices,
+         bool defer_bound) {
     Staged st = stage_scene(S, use_smem);
     DevCounters c = {};
     const uint32_t n = *count_in;
@@ -389,6 +394,10 @@ k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
             if (!degenerate && !(any_hit_suffices && winner >= 0)) {
                 for (int k = 0; k < S.n_march; k++) {
                     if (!cull_pass(cr, S.march_cull[k])) continue;  // the line misses the marching bound
+                    if (defer_bound) {  // k_march runs march_needed anyway, with (nearly) full warps
+                        mask |= 1u << k;
+                        continue;
+                    }
                     const int si = S.march_index[k];
                     D3 o, d;
                     double start, end_c;
@@ -962,10 +971,9 @@ k_shade(DevScene S, PathQueue in, const uint32_t* __restrict__ count_in, HitQueu
                 D3 ro = mk(in.ox[i], in.oy[i], in.oz[i]);
                 const rt_material mat = S.materials[S.material[bi]];
                 finalize_hit(S, bi, hq.t[i], ro, rd, h, material_reads_uv(S, mat));
-                uint32_t pl = pid / spp, s = pid % spp, x, y;
-                map.pixel_of(first_owned + pl, x, y);
-                rng.pixel = x + y * map.width;
-                rng.sample = s;
+                const uint2 key = hq.key[pid];
+                rng.pixel = key.x;
+                rng.sample = key.y;
                 shading = true;
                 need_ball = material_needs_ball(mat);
             }
@@ -1048,7 +1056,8 @@ k_tonemap(const rt_vec3* __restrict__ frame, unsigned long long n, uchar4* __res
 // scatter owned-order pixels into a full frame (host path of a sharded render keeps it simple and
 // does this on the host; this kernel serves rt_trace_pixel_samples' ray upload)
 __global__ void __launch_bounds__(256)
-k_load_rays(const rt_ray* __restrict__ rays, uint32_t n, PathQueue q, uint32_t* count_out) {
+k_load_rays(const rt_ray* __restrict__ rays, uint32_t n, PathQueue q, uint32_t* count_out, uint2* __restrict__ path_key,
+            uint32_t pixel_index) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) *count_out = n;
     if (i >= n) return;
@@ -1057,6 +1066,7 @@ k_load_rays(const rt_ray* __restrict__ rays, uint32_t n, PathQueue q, uint32_t* 
     q.dx[i] = r.direction.x; q.dy[i] = r.direction.y; q.dz[i] = r.direction.z;
     q.bx[i] = 1.0; q.by[i] = 1.0; q.bz[i] = 1.0;
     q.pid[i] = i;
+    path_key[i] = make_uint2(pixel_index, i);  // sample i of the pixel
 }
 
 // FMA micro-benchmarks: 8 independent chains per thread, FMA counted as 2 flop
@@ -1142,6 +1152,7 @@ struct rt_scene {
     uint32_t kind_mask[6] = {0, 0, 0, 0, 0, 0};  // marched shapes (bits of the march-queue mask) per surface kind
     MarchRec* d_march_state = nullptr;           // k_march2: RT_M2_SLOTS records per block
     int grid_march2 = 0;
+    bool defer_bound = false;                    // k_extend queues every ray whose line touches a marching bound's ball; k_march sorts out the rest (RT_B200_DEFER_BOUND=1)
     bool march_v1 = true;                        // false (RT_B200_MARCH_V2=1): the block-local wavefront k_march2 instead of k_march
     int3 march_tune = make_int3(8, 8, 8);        // k_march scheduling thresholds (RT_B200_MARCH_TUNE=a,b,c)
     int march_grid_scale = 100;                  // percent of the occupancy grid
@@ -1372,6 +1383,7 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
     if (sc->grid_march < 1) sc->grid_march = 1;
     sc->grid_march2 = occ_grid(k_march2<RT_SURF_HEART, false>, RT_M2_THREADS, 0);
     sc->march_v1 = getenv("RT_B200_MARCH_V2") == nullptr;
+    if (const char* db = getenv("RT_B200_DEFER_BOUND")) sc->defer_bound = atoi(db) != 0;
     sc->grid_shade = occ_grid(k_shade<false>, 256, 0);
     sc->wavefront = sc->ds.n_march <= 32 && !getenv("RT_B200_FUSED_BOUNCE");
 
@@ -1624,9 +1636,9 @@ static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long 
         {
             KernelSpan span(sc, RT_KCLASS_EXTEND);
             if (sc->counters_on)
-                k_extend<true><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, rcount, sc->d_counters, level == max_depth);
+                k_extend<true><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, rcount, sc->d_counters, level == max_depth, sc->defer_bound);
             else
-                k_extend<false><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, rcount, sc->d_counters, level == max_depth);
+                k_extend<false><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, rcount, sc->d_counters, level == max_depth, sc->defer_bound);
         }
         if (sc->ds.n_march > 0) {
             KernelSpan span(sc, RT_KCLASS_MARCH);
@@ -1695,6 +1707,7 @@ static int ensure_path_buffers(rt_scene* sc, uint64_t need_paths) {
         CU(cudaMalloc(&p, need_paths * sizeof(uint32_t))); sc->qallocs.push_back(p); sc->hq.mq_slot = (uint32_t*)p;
         CU(cudaMalloc(&p, need_paths * sizeof(uint32_t))); sc->qallocs.push_back(p); sc->hq.mq_mask = (uint32_t*)p;
         CU(cudaMalloc(&p, need_paths * sizeof(uint32_t))); sc->qallocs.push_back(p); sc->hq.rq_slot = (uint32_t*)p;
+        CU(cudaMalloc(&p, need_paths * sizeof(uint2))); sc->qallocs.push_back(p); sc->hq.key = (uint2*)p;
     }
     if (!sc->d_counts) CU(cudaMalloc(&sc->d_counts, RT_CNT_WORDS * sizeof(uint32_t)));
     if (!sc->d_march_state && sc->ds.n_march > 0 && !sc->march_v1)
@@ -1765,7 +1778,7 @@ int rt_render_start(rt_scene* sc, const rt_camera* cam, const rt_render_params* 
             CU(cudaMemsetAsync(sc->d_counts, 0, RT_CNT_WORDS * sizeof(uint32_t), sc->stream));
             {
                 KernelSpan span(sc, RT_KCLASS_RAYGEN);
-                k_raygen<<<sc->grid, 256, 0, sc->stream>>>(rcd, sc->map, first, npx, spp, k0, k1, sc->q[0], sc->d_counts, sc->d_radiance);
+                k_raygen<<<sc->grid, 256, 0, sc->stream>>>(rcd, sc->map, first, npx, spp, k0, k1, sc->q[0], sc->d_counts, sc->d_radiance, sc->hq.key);
             }
             launch_bounces(sc, p->max_depth, first, spp, p->seed);
             {
@@ -1953,7 +1966,7 @@ int rt_trace_pixel_samples(rt_scene* sc, const rt_ray* rays, uint32_t n_rays, ui
     cudaMalloc(&d_mean, sizeof(rt_vec3));
     cudaMemcpyAsync(d_rays, rays, n_rays * sizeof(rt_ray), cudaMemcpyHostToDevice, sc->stream);
     cudaMemsetAsync(sc->d_counts, 0, RT_CNT_WORDS * sizeof(uint32_t), sc->stream);
-    k_load_rays<<<(n_rays + 255) / 256, 256, 0, sc->stream>>>(d_rays, n_rays, sc->q[0], sc->d_counts);
+    k_load_rays<<<(n_rays + 255) / 256, 256, 0, sc->stream>>>(d_rays, n_rays, sc->q[0], sc->d_counts, sc->hq.key, pixel_index);
     sc->launches++;
     // a 1-pixel-wide "image" whose only pixel is pixel_index: owned pixel 0 -> (x = pixel_index, y = 0)
     ShardMap saved = sc->map;

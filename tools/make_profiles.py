@@ -97,7 +97,8 @@ quoted as a bench value. Regenerate with `python tools/make_profiles.py {cid}`.
 
 History of `value` on this config in round 1: 72.8 (fused k_bounce) -> 288 (wavefront split, FP32 ball cull,
 exact-skip marching) -> 456 (cull tree) -> 534 (cooperative advance, near-zero walk) -> 586 (two lanes) ->
-{b['value']:.0f} (8 Mi-path batches, staged jump planning, landing cooldown).
+643 (8 Mi-path batches, staged jump planning, landing cooldown) -> {b['value']:.0f} (k_shade: cooperative rejection
+sampling + shared-reciprocal division; k_extend: flat-list records; k_march: exact steps-to-edge, owner table).
 
 ## Per-kernel device time of one step (CUDA event pairs on the library's stream, `bench.py`, single lane)
 
@@ -122,9 +123,13 @@ command (`{cid}_launches_bench_cornell1024x256.csv`, first 400 launches, `--metr
 * ncu (`{cid}_ncu_full_extend_march_shade_cornell1024x4.md`, bounce levels 0 / 1 / 2): FP64 pipe {rng('k_extend', 'fp64')} % busy,
   {rng('k_extend', 'lanes', '{:.1f}')} of 32 lanes active per instruction (warp execution efficiency), SM issue slots
   {rng('k_extend', 'issue')} % busy, achieved occupancy {rng('k_extend', 'occ')} %
-  ({rng('k_extend', 'regs')} registers), stalls dominated by fixed-latency FP64 dependencies (`wait`) and L1/L2 loads
-  of the 96 B inverse rows (`long_scoreboard`): the kernel is latency-bound, not issue-bound -- removing 29 % of
-  its instructions (Rectangle fast path, marching-bound pre-cull) did not change its time, nor did 4 CTAs / SM;
+  ({rng('k_extend', 'regs')} registers), stalls dominated by fixed-latency FP64 dependencies (`wait`) and loads
+  (`long_scoreboard`).  All three kernels sit at IPC 2.2-2.3 whatever their mix: an FP64 instruction occupies its
+  sub-partition's pipe for two cycles, so ~57 % issue-slot utilisation with a quarter to a third of the
+  instructions in FP64 is close to what the issue ports deliver, and what moves the time is the instruction count
+  (flat-list records: 145 M -> 120 M warp instructions at level 0, 236 -> 198 us; 4 CTAs / SM changed nothing);
+  at the deeper levels half of the lanes are idle: the Cube tests and marching-bound tests behind the ball
+  pre-tests run for the few lanes that need them (`r1z_source_hotspots.txt`: `divide` at 6.5 of 32 lanes);
 * DRAM traffic per launch (`ncu_traffic.json`): {traffic['k_extend']['per_launch'][0] / 1e6:.0f} MB at level 0 of a 4 Mi-path batch against 251 MB
   algorithmic (48 B ray in + 12 B hit out per ray): no re-reads. Whole step: {b['roofline']['hbm']['achieved']:.0f} GB/s algorithmic queue traffic
   = {b['roofline']['hbm']['frac'] * 100:.1f} % of the measured {b['roofline']['hbm']['peak']:.0f} GB/s.
@@ -148,6 +153,16 @@ What was tried, with the measured effect on cornell 1024x1024x4 (k_march ms per 
 | landing cooldown instead of the doomed re-attempt (4 of 7.5 attempts per ray failed) | 3.90 |
 | staged planning: re-plan by Taylor shift inside one attempt (jumps 5.0 M -> 2.8 M) | 3.65 |
 | fast FP32 division for the in-binade step count | 3.49 |
+| owner table in shared memory instead of stripping mask bits in the cooperative advance | 3.44 |
+| exact steps-to-edge: one literal step per binade edge instead of 3-6 | 3.32 |
+| block-wide task list for k_march2's advances (dealt with refill) | 4.84 (k_march2 stays off) |
+| k_extend queues every ray whose line touches the bound's ball, k_march sorts them out (`RT_B200_DEFER_BOUND=1`) | 3.70, k_extend 1.98 -> 1.81: net loss, off |
+
+`k_shade` on the same probe (ms per 4 Mi paths): 1.72 -> 1.67 (warp-cooperative rejection sampling: 5.7 -> ~3 rounds per warp,
+but 2 Philox blocks per try instead of 1.5) -> 1.44 (vector / scalar division from one exact reciprocal: nvcc's division
+took its slow path for every zero component of an axis-aligned normal).  Tried and dropped: grouping each block's survivors
+by direction octant before they are queued (k_extend 2.07 -> 1.96, k_shade +0.2 from the extra registers and barriers),
+64 registers / 4 CTAs per SM for k_shade (1.44 -> 1.64).
 
 `tools/march_coherence_probe.py`: 1 Mi different rays 4.70 ms, the same work with every warp marching 32 copies
 of one ray 0.83 ms (5.7x) -- the divergence cost that remains. `RT_B200_MARCH_TUNE` sweeps are flat within 5 %.
@@ -169,7 +184,7 @@ stress. cfg 5 (8.5 G paths) streams through the same 2 x 1.6 GB of path state as
 | `ncu_traffic.json` | DRAM bytes per launch from that capture (read by `bench.py` for `roofline.traffic`) |
 | `{cid}_configs_1gpu.md` | the five configurations |
 | `{cid}_render_*.jpg` | `tools/render.py` output (GpuRenderer -> rt_tonemap_rgba8 -> rth_save_png), 512x384, 256 spp, depth 50, as JPEG previews |
-| `r1a_*` ... `r1v_*` | earlier captures of this round (fused k_bounce; first wavefront split; cull tree; before / after the march work) |
+| `r1a_*` ... `r1x_*` | earlier captures of this round (fused k_bounce; first wavefront split; cull tree; before / after the march work) |
 """
 open(os.path.join(P, "README.md"), "w").write(readme)
 print("profiles/README.md written for", cid)
