@@ -53,7 +53,15 @@ struct ShardMap {  // which pixels this handle owns, in "owned order" (tile-majo
     // owned pixel index -> (x, y); false for the padding of clipped border tiles
     __host__ __device__ bool pixel_of(uint64_t q, uint32_t& x, uint32_t& y) const {
         uint32_t tp = tile_w * tile_h;
-        uint32_t j = (uint32_t)(q / tp), r = (uint32_t)(q % tp);
+        uint32_t j, r;
+        if ((q >> 32) == 0) {  // 32-bit division whenever the index allows (a 64-bit one is ~100 instructions)
+            const uint32_t q32 = (uint32_t)q;
+            j = q32 / tp;
+            r = q32 - j * tp;
+        } else {
+            j = (uint32_t)(q / tp);
+            r = (uint32_t)(q % tp);
+        }
         uint32_t k = shard_index + j * shard_count;
         uint32_t ty = k / tiles_x, tx = k % tiles_x;
         x = tx * tile_w + r % tile_w;
@@ -250,7 +258,9 @@ k_raygen(RayCasterDev rc, ShardMap map, unsigned long long first_owned, uint32_t
         bool alive = false;
         D3 dir = mk(0.0, 0.0, 0.0);
         if (id < n) {
-            uint32_t pl = (uint32_t)(id / spp), s = (uint32_t)(id % spp);
+            // (a batch holds fewer than 2^32 paths -- rt_render_start checks -- so the division is a 32-bit one)
+            const uint32_t id32 = (uint32_t)id;
+            uint32_t pl = id32 / spp, s = id32 - pl * spp;
             uint32_t x, y;
             if (map.pixel_of(first_owned + pl, x, y)) {
                 PathRng rng;
