@@ -214,12 +214,16 @@ def test_work_counters_match_oracle():
 def test_alternative_schedules_give_the_same_frame(monkeypatch, name):
     """the marching result does not depend on how the work is scheduled: the block-local wavefront marcher
     (RT_B200_MARCH_V2, an experiment kept off by default), the fused k_bounce (RT_B200_FUSED_BOUNCE) and
-    other k_march voting thresholds reproduce the default frame bit for bit"""
+    other k_march voting thresholds reproduce the default frame bit for bit; so do the flat list without its
+    staged records (RT_B200_NO_FLAT_REC) and marching-bound tests deferred to k_march (RT_B200_DEFER_BOUND).
+    The fused k_bounce draws random_in_unit_sphere with the sequential rejection loop and the default k_shade
+    warp-cooperatively, so this also pins the cooperative sampler to the sequential one"""
     w, h, spp, depth, seed = 96, 72, 4, 8, 21
     sc = rt.Scene.from_file(scene_path(name), random_spheres_seed=1)
     ref = gpu_frame(sc, sc.camera(), w, h, spp, depth, seed)
     for var, val in (("RT_B200_MARCH_V2", "1"), ("RT_B200_FUSED_BOUNCE", "1"), ("RT_B200_MARCH_TUNE", "2,30,3"),
-                     ("RT_B200_NO_CULL_TREE", "1"), ("RT_B200_NO_MARCH_SKIP", "1")):
+                     ("RT_B200_NO_CULL_TREE", "1"), ("RT_B200_NO_MARCH_SKIP", "1"), ("RT_B200_NO_FLAT_REC", "1"),
+                     ("RT_B200_DEFER_BOUND", "1")):
         monkeypatch.setenv(var, val)
         alt = rt.Scene.from_file(scene_path(name), random_spheres_seed=1)
         got = gpu_frame(alt, alt.camera(), w, h, spp, depth, seed)
