@@ -210,7 +210,8 @@ def test_work_counters_match_oracle():
     assert st.kernel_launches > 0
 
 
-@pytest.mark.parametrize("name", ["spheres.json", "cornell_box.json", "dupin.json"])
+@pytest.mark.parametrize("name", ["spheres.json", "cornell_box.json", "dupin.json", "detached_materials.json",
+                                  "light_source.json"])
 def test_alternative_schedules_give_the_same_frame(monkeypatch, name):
     """the marching result does not depend on how the work is scheduled: the block-local wavefront marcher
     (RT_B200_MARCH_V2, an experiment kept off by default), the fused k_bounce (RT_B200_FUSED_BOUNCE) and
