@@ -19,15 +19,19 @@ from ._ffi import Camera
 
 def owned_pixel_coords(width: int, height: int, tile: int, world: int, shard: int):
     """Host mirror of ShardMap::pixel_of (csrc/rt_core.cu): the pixels shard `shard` owns, in its
-    tile-packed "owned order" (tile k -> shard k % world, tiles row-major, row-major inside a tile, border
-    tiles padded to tile*tile).  Returns (x, y, valid) int arrays of length rt_shard_float4_count."""
+    tile-packed "owned order" (tile k -> shard k % world; tiles numbered row-major with row ty rotated by ty
+    positions, so that a shard owns diagonals rather than columns of tiles when tiles_x is a multiple of world;
+    row-major inside a tile, border tiles padded to tile*tile).  Returns (x, y, valid) int arrays of length
+    rt_shard_float4_count."""
     if world == 1:   # whole image: one "tile" per row, owned order == x + y*width
-        tw, th = width, 1
+        tw, th, skew = width, 1, 0
     else:
         tw = th = tile
+        skew = 1
     tiles_x, tiles_y = (width + tw - 1) // tw, (height + th - 1) // th
     ks = np.arange(shard, tiles_x * tiles_y, world)
-    tx, ty = ks % tiles_x, ks // tiles_x
+    ty = ks // tiles_x
+    tx = (ks % tiles_x + (ty % tiles_x) * skew) % tiles_x
     r = np.arange(tw * th)
     x = (tx[:, None] * tw + r[None, :] % tw).reshape(-1)
     y = (ty[:, None] * th + r[None, :] // tw).reshape(-1)
