@@ -232,6 +232,16 @@ int rt_render_wait(rt_scene* scene, rt_vec3* buffer);
 /* Renderer::stop_rendering: abandons the frame in flight (no-op when idle). */
 int rt_render_stop(rt_scene* scene);
 
+/* Progressive accumulation across rt_render_start calls (the reference's interactive loop,
+ * src/bin/main_raylib.rs:204-237, re-renders from scratch every time).  While enabled, a frame started with
+ * the same camera, image, sharding, max_depth and seed as the previous one ADDS its samples_number samples to
+ * the accumulator: its paths take the sample indices that follow the ones already traced (so k frames of n
+ * samples are the very paths of one frame of k*n samples), and rt_render_poll / rt_render_device_result deliver
+ * the mean over everything accumulated.  Any other frame, and every call of this function, starts afresh.
+ * rt_render_accumulated_samples: the number of samples per pixel the accumulator holds (0 = empty). */
+int rt_render_set_accumulate(rt_scene* scene, int enabled);
+int rt_render_accumulated_samples(rt_scene* scene, uint32_t* samples);
+
 /* Device-side result of the last started frame, for callers that gather shards over NCCL:
  * a float4 (r,g,b sums; w = samples) per owned pixel, tile-packed in this shard's tile order
  * (tile-major, row-major inside a tile, tiles clipped at the image border are still padded to

@@ -137,6 +137,8 @@ CORE_SYMBOLS = {
     "rt_render_poll": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "rt_render_wait": (C.c_int, [C.c_void_p, C.c_void_p]),
     "rt_render_stop": (C.c_int, [C.c_void_p]),
+    "rt_render_set_accumulate": (C.c_int, [C.c_void_p, C.c_int]),
+    "rt_render_accumulated_samples": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint32)]),
     "rt_render_device_result": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "rt_shard_float4_count": (C.c_uint64, [C.POINTER(RenderParams), C.c_uint32]),
     "rt_assemble_frame": (C.c_int, [C.c_void_p, C.POINTER(RenderParams), C.POINTER(C.c_void_p), C.c_void_p,

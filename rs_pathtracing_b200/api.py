@@ -298,6 +298,17 @@ def render_wait(dev_scene, buffer: Optional[np.ndarray]) -> None:
     _check(_ffi.core().rt_render_wait(dev_scene, ptr))
 
 
+def render_set_accumulate(dev_scene, enabled: bool) -> None:
+    """progressive accumulation across render_start calls (rt_render_set_accumulate)"""
+    _check(_ffi.core().rt_render_set_accumulate(dev_scene, 1 if enabled else 0))
+
+
+def render_accumulated_samples(dev_scene) -> int:
+    n = C.c_uint32(0)
+    _check(_ffi.core().rt_render_accumulated_samples(dev_scene, C.byref(n)))
+    return n.value
+
+
 def render_device_result(dev_scene):
     """(device pointer, n_float4) of the shard's tile-packed float4 accumulator."""
     ptr, n = C.c_void_p(), C.c_uint64()

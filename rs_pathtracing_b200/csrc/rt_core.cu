@@ -255,7 +255,7 @@ __device__ __forceinline__ uint32_t queue_append(bool alive, uint32_t* counter) 
 __global__ void __launch_bounds__(256)
 k_raygen(RayCasterDev rc, ShardMap map, unsigned long long first_owned, uint32_t n_pixels, uint32_t spp,
          uint32_t k0, uint32_t k1, PathQueue q, uint32_t* count_out, float4* __restrict__ radiance,
-         uint2* __restrict__ path_key) {
+         uint2* __restrict__ path_key, uint32_t sample_base) {
     const unsigned long long n = (unsigned long long)n_pixels * spp;
     const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
     // round the trip count up so that whole warps stay converged for the ballot in queue_append
@@ -272,7 +272,7 @@ k_raygen(RayCasterDev rc, ShardMap map, unsigned long long first_owned, uint32_t
                 PathRng rng;
                 rng.k0 = k0; rng.k1 = k1;
                 rng.pixel = x + y * map.width;
-                rng.sample = s;
+                rng.sample = sample_base + s;  // (samples of earlier frames of a progressive accumulation come first)
                 rng.begin_event(0);
                 double u = rng.next();   // ray_caster.rs:106-107
                 double v = rng.next();
@@ -280,7 +280,7 @@ k_raygen(RayCasterDev rc, ShardMap map, unsigned long long first_owned, uint32_t
                 D3 d = rc.left_top + (rc.pixel_resolution * ((double)x + u)) * rc.camera_right -
                        (rc.pixel_resolution * ((double)y + v)) * rc.camera_up;
                 dir = normalize(d - rc.camera_position);  // Ray::new
-                path_key[id] = make_uint2(rng.pixel, s);
+                path_key[id] = make_uint2(rng.pixel, rng.sample);
                 alive = true;
             } else {
                 radiance[id] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -1022,7 +1022,7 @@ k_shade(DevScene S, PathQueue in, const uint32_t* __restrict__ count_in, HitQueu
 // buffer the f64 mean for the host path.
 __global__ void __launch_bounds__(256)
 k_resolve(const float4* __restrict__ radiance, uint32_t n_pixels, uint32_t spp, unsigned long long first_owned,
-          float4* __restrict__ accum, rt_vec3* __restrict__ frame_owned) {
+          float4* __restrict__ accum, rt_vec3* __restrict__ frame_owned, bool add) {
     uint32_t pl = blockIdx.x * blockDim.x + threadIdx.x;
     if (pl >= n_pixels) return;
     const float4* r = radiance + (size_t)pl * spp;
@@ -1031,8 +1031,13 @@ k_resolve(const float4* __restrict__ radiance, uint32_t n_pixels, uint32_t spp, 
         float4 v = r[s];
         sx += (double)v.x; sy += (double)v.y; sz += (double)v.z;
     }
-    accum[first_owned + pl] = make_float4((float)sx, (float)sy, (float)sz, (float)spp);
     double ln = (double)spp;
+    if (add) {  // progressive accumulation: the sums and the sample count of the earlier frames
+        const float4 prev = accum[first_owned + pl];
+        sx += (double)prev.x; sy += (double)prev.y; sz += (double)prev.z;
+        ln += (double)prev.w;
+    }
+    accum[first_owned + pl] = make_float4((float)sx, (float)sy, (float)sz, (float)ln);
     frame_owned[first_owned + pl] = rt_vec3{sx / ln, sy / ln, sz / ln};
 }
 
@@ -1177,6 +1182,11 @@ struct rt_scene {
     float4* d_accum = nullptr;
     rt_vec3* d_frame = nullptr;    // owned order
     uint64_t frame_capacity = 0;
+    // progressive accumulation (rt_render_set_accumulate): samples already in d_accum and the frame they belong to
+    bool accumulate = false;
+    uint32_t accumulated_spp = 0;
+    rt_render_params accum_rp{};
+    rt_camera accum_cam{};
     // the fields q, hq, d_radiance, d_counts, d_march_state, qallocs, path_capacity and `stream` above are
     // the BOUND lane's (bind_lane swaps them); lanes[0].stream is the main stream
     PathLane lanes[RT_MAX_LANES];
@@ -1745,6 +1755,18 @@ int rt_render_start(rt_scene* sc, const rt_camera* cam, const rt_render_params* 
     CU(cudaSetDevice(sc->device));
     if (sc->rendering) rt_render_stop(sc);
 
+    // progressive accumulation: this frame adds its samples to the previous ones when it is the same frame
+    // (image, sharding, depth, seed, camera) and nothing was abandoned; otherwise it starts afresh
+    uint32_t sample_base = 0;
+    if (sc->accumulate && sc->accumulated_spp > 0 && sc->wavefront && memcmp(&sc->accum_cam, cam, sizeof *cam) == 0 &&
+        sc->accum_rp.image.width == p->image.width && sc->accum_rp.image.height == p->image.height &&
+        sc->accum_rp.max_depth == p->max_depth && sc->accum_rp.seed == p->seed &&
+        (sc->accum_rp.shard_count ? sc->accum_rp.shard_count : 1) == shard_count &&
+        sc->accum_rp.shard_index == p->shard_index && sc->accum_rp.tile_width == p->tile_width &&
+        sc->accum_rp.tile_height == p->tile_height &&
+        (uint64_t)sc->accumulated_spp + p->samples_number <= (1u << 24))  // the float sample counter stays exact
+        sample_base = sc->accumulated_spp;
+    sc->accumulated_spp = 0;  // until this frame is enqueued (an abandoned frame breaks the chain)
     sc->rp = *p;
     sc->rp.shard_count = shard_count;
     sc->map = make_shard_map(sc->rp, p->shard_index);
@@ -1795,12 +1817,12 @@ int rt_render_start(rt_scene* sc, const rt_camera* cam, const rt_render_params* 
             CU(cudaMemsetAsync(sc->d_counts, 0, RT_CNT_WORDS * sizeof(uint32_t), sc->stream));
             {
                 KernelSpan span(sc, RT_KCLASS_RAYGEN);
-                k_raygen<<<sc->grid, 256, 0, sc->stream>>>(rcd, sc->map, first, npx, spp, k0, k1, sc->q[0], sc->d_counts, sc->d_radiance, sc->hq.key);
+                k_raygen<<<sc->grid, 256, 0, sc->stream>>>(rcd, sc->map, first, npx, spp, k0, k1, sc->q[0], sc->d_counts, sc->d_radiance, sc->hq.key, sample_base);
             }
             launch_bounces(sc, p->max_depth, first, spp, p->seed);
             {
                 KernelSpan span(sc, RT_KCLASS_RESOLVE);
-                k_resolve<<<(npx + 255) / 256, 256, 0, sc->stream>>>(sc->d_radiance, npx, spp, first, sc->d_accum, sc->d_frame);
+                k_resolve<<<(npx + 255) / 256, 256, 0, sc->stream>>>(sc->d_radiance, npx, spp, first, sc->d_accum, sc->d_frame, sample_base != 0);
             }
             Batch b;
             b.first_owned = first;
@@ -1824,6 +1846,24 @@ int rt_render_start(rt_scene* sc, const rt_camera* cam, const rt_render_params* 
     if (rc != RT_OK) return rc;
     sc->rendering = true;
     sc->frame_complete = false;
+    if (sc->accumulate && sc->wavefront) {  // (enqueued work always runs to completion: rt_render_stop drains it)
+        sc->accumulated_spp = sample_base + spp;
+        sc->accum_rp = *p;
+        sc->accum_cam = *cam;
+    }
+    return RT_OK;
+}
+
+int rt_render_set_accumulate(rt_scene* sc, int enabled) {
+    if (!sc) return fail(RT_ERR_INVALID, "null scene");
+    sc->accumulate = enabled != 0;
+    sc->accumulated_spp = 0;
+    return RT_OK;
+}
+
+int rt_render_accumulated_samples(rt_scene* sc, uint32_t* samples) {
+    if (!sc || !samples) return fail(RT_ERR_INVALID, "null argument");
+    *samples = sc->accumulated_spp;
     return RT_OK;
 }
 
@@ -1994,7 +2034,7 @@ int rt_trace_pixel_samples(rt_scene* sc, const rt_ray* rays, uint32_t n_rays, ui
     // pixel_of(first_owned + 0) must give x = pixel_index: use first_owned = pixel_index
     launch_bounces(sc, max_depth, pixel_index, n_rays, seed);
     sc->map = saved;
-    k_resolve<<<1, 256, 0, sc->stream>>>(sc->d_radiance, 1, n_rays, 0, d_acc, d_mean);
+    k_resolve<<<1, 256, 0, sc->stream>>>(sc->d_radiance, 1, n_rays, 0, d_acc, d_mean, false);
     sc->launches++;
     cudaMemcpyAsync(mean_out, d_mean, sizeof(rt_vec3), cudaMemcpyDeviceToHost, sc->stream);
     cudaError_t e = cudaStreamSynchronize(sc->stream);

@@ -87,6 +87,8 @@ extern "C" {
     pub fn rt_render_poll(scene: *mut rt_scene, buffer: *mut rt_vec3, done: *mut c_int) -> c_int;
     pub fn rt_render_wait(scene: *mut rt_scene, buffer: *mut rt_vec3) -> c_int;
     pub fn rt_render_stop(scene: *mut rt_scene) -> c_int;
+    pub fn rt_render_set_accumulate(scene: *mut rt_scene, enabled: c_int) -> c_int;
+    pub fn rt_render_accumulated_samples(scene: *mut rt_scene, samples: *mut u32) -> c_int;
     pub fn rt_render_device_result(scene: *mut rt_scene, d_accum: *mut *const c_void, n_float4: *mut u64) -> c_int;
     pub fn rt_shard_float4_count(params: *const rt_render_params, shard_index: u32) -> u64;
     pub fn rt_assemble_frame(scene: *mut rt_scene, params: *const rt_render_params, d_shards: *const *const c_void,

@@ -150,6 +150,47 @@ def test_progressive_delivery_and_batching(monkeypatch):
     assert np.array_equal(buf, ref)
 
 
+def test_progressive_accumulation_across_start_calls():
+    """rt_render_set_accumulate: k frames of n samples with an unchanged camera trace the very
+    paths of one frame of k*n samples -- sample indices continue where the previous frame stopped -- and deliver
+    the mean over all of them; a different camera / seed / image, or toggling the switch, starts afresh"""
+    w, h, depth, seed = 64, 48, 8, 9
+    sc = rt.Scene.from_file(scene_path("cornell_box.json"), random_spheres_seed=1)
+    cam = sc.camera()
+    other = rt.Scene.from_file(scene_path("cornell_box.json"), random_spheres_seed=1)   # references: a handle of their own
+    ref12 = gpu_frame(other, cam, w, h, 12, depth, seed)
+    ref4 = gpu_frame(other, cam, w, h, 4, depth, seed)
+    ds = sc.device_scene(0)
+    api.render_set_accumulate(ds, True)
+    assert api.render_accumulated_samples(ds) == 0
+    buf = np.zeros((h, w, 3))
+    for k in range(3):
+        api.render_start(ds, cam, api.render_params(w, h, 4, depth, seed))
+        api.render_wait(ds, buf)
+        assert api.render_accumulated_samples(ds) == 4 * (k + 1)
+        if k == 0:
+            assert np.array_equal(buf, ref4)
+    # same paths; the float4 accumulator is rounded once per frame instead of once: 1e-6 relative
+    assert np.allclose(buf, ref12, rtol=2e-6, atol=1e-7)
+    assert not np.allclose(buf, ref4, rtol=1e-3, atol=1e-4)
+    # device-side result carries the total sample count
+    torch = pytest.importorskip("torch")
+    ptr, n = api.render_device_result(ds)
+    assert n == w * h
+    # another seed starts afresh
+    api.render_start(ds, cam, api.render_params(w, h, 4, depth, seed + 1))
+    api.render_wait(ds, buf)
+    assert api.render_accumulated_samples(ds) == 4
+    assert np.array_equal(buf, gpu_frame(other, cam, w, h, 4, depth, seed + 1))
+    # switching it off and on empties the accumulator; off = the reference's behaviour (every frame from scratch)
+    api.render_set_accumulate(ds, False)
+    for _ in range(2):
+        api.render_start(ds, cam, api.render_params(w, h, 4, depth, seed))
+        api.render_wait(ds, buf)
+        assert np.array_equal(buf, ref4)
+    assert api.render_accumulated_samples(ds) == 0
+
+
 def test_sharded_render_assembles_to_the_unsharded_frame():
     """interleaved tiles: N shards rendered independently assemble bit-for-bit to the 1-shard frame"""
     torch = pytest.importorskip("torch")
