@@ -29,7 +29,7 @@ pub trait Describe { fn describe(&self, flat: &mut FlatScene); }
 fn v(a: &Vector3d) -> sys::rt_vec3 { sys::rt_vec3 { x: a.x, y: a.y, z: a.z } }
 fn check(rc: i32) { if rc != sys::RT_OK { panic!("rt_b200: {}", sys::last_error()) } }  // the reference unwraps too
 
-pub struct GpuRenderer { scene: *mut sys::rt_scene, depth: u32, seed: u64 }
+pub struct GpuRenderer { scene: *mut sys::rt_scene, depth: u32, seed: u64, progressive: bool }
 
 impl GpuRenderer {
     /// same constructor convention as ThreadPoolRenderer::new (step_by_step.rs:37); `thread_number` is ignored
@@ -49,7 +49,14 @@ impl GpuRenderer {
         };
         let mut h = std::ptr::null_mut();
         check(unsafe { sys::rt_scene_create(&desc, 0, &mut h) });   // copies the description
-        GpuRenderer { scene: h, depth, seed: 0 }
+        GpuRenderer { scene: h, depth, seed: 0, progressive: false }
+    }
+    /// Progressive accumulation (rt_render_set_accumulate): while on, start_rendering calls with an unchanged
+    /// camera ADD their samples to the frame instead of starting over -- what RendererState::render
+    /// (main_raylib.rs:204-237) would call with samples_number = 1 per UI frame while the camera is still.
+    pub fn set_progressive(&mut self, on: bool) {
+        self.progressive = on;
+        check(unsafe { sys::rt_render_set_accumulate(self.scene, on as i32) });
     }
 }
 
@@ -65,7 +72,8 @@ impl Renderer for GpuRenderer {
             samples_number, max_depth: self.depth, seed: self.seed,
             shard_count: 1, shard_index: 0, tile_width: 0, tile_height: 0,
         };
-        self.seed = self.seed.wrapping_add(1);                         // a fresh stream per frame, like thread_rng
+        if !self.progressive { self.seed = self.seed.wrapping_add(1); } // a fresh stream per frame, like thread_rng
+                                                                       // (an accumulating frame keeps its key)
         check(unsafe { sys::rt_render_start(self.scene, &cam, &p) });  // returns immediately
     }
     /// non-blocking, partial pixels may arrive before completion (step_by_step.rs:101-121);
