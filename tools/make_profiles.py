@@ -165,7 +165,11 @@ by direction octant before they are queued (k_extend 2.07 -> 1.96, k_shade +0.2 
 64 registers / 4 CTAs per SM for k_shade (1.44 -> 1.64).
 
 `tools/march_coherence_probe.py`: 1 Mi different rays 4.70 ms, the same work with every warp marching 32 copies
-of one ray 0.83 ms (5.7x) -- the divergence cost that remains. `RT_B200_MARCH_TUNE` sweeps are flat within 5 %.
+of one ray 0.83 ms (5.7x) -- the divergence cost that remains. `RT_B200_MARCH_TUNE` sweeps are flat within 5 %
+(re-run after the changes above: 3.23 - 3.48 ms over eleven settings).  Occupancy is not the limiter either:
+k_march at 5 CTAs / SM (96 registers) 3.31 ms against 3.29, k_extend at 4 CTAs / SM (64 registers, 534 B of spills)
+1.99 against 1.97; nor is the batch size (4 / 8 / 16 / 32 Mi paths per batch: 712 / 727 / 732 / 731 Mpaths/s on the bench
+frame) or a third lane (727).
 
 ## All five BASELINE.json configurations, 1 GPU (`{cid}_configs_1gpu.md`, `tools/run_configs.py`)
 
