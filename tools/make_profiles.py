@@ -85,7 +85,8 @@ readme = f"""# profiles/ — measured evidence (round 1)
 Everything here was produced on the pool's B200s (148 SMs, {b['clocks']['sm_mhz']:.0f} MHz under load, throttle reasons
 {b['clocks']['reasons']}) through `gpurun`; names carry the capture id (`{cid}` = the last full capture of round 1;
 older captures are kept for the history of the kernels). A number printed by a run under ncu is never
-quoted as a bench value. Regenerate with `python tools/make_profiles.py {cid}`.
+quoted as a bench value. Captured with `gpurun -- 'bash tools/capture.sh {cid}'` (+ `--gpus N ... {cid} N` for the
+multi-GPU lines); regenerate this file with `python tools/make_profiles.py {cid}`.
 
 ## Headline (BASELINE.json configs[2]: cornell_box.json + 481 random spheres, 1024x1024, 256 spp, depth 8)
 
