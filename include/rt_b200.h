@@ -254,7 +254,9 @@ uint64_t rt_shard_float4_count(const rt_render_params* params, uint32_t shard_in
 
 /* Assemble a full frame from the gathered shard buffers (all DEVICE pointers on the scene's
  * device): d_shards[s] = shard s's tile-packed float4 buffer; d_frame = w*h rt_vec3 (x + y*w,
- * linear mean).  Runs on `stream` (NULL = library stream), does not synchronise. */
+ * linear mean).  Runs on `stream`, does not synchronise.  NULL = the library's own non-blocking stream, which is
+ * NOT ordered against the caller's copies / NCCL receives into d_shards: a caller whose stream is the legacy
+ * default stream (handle 0, e.g. torch's default stream) passes cudaStreamLegacy (0x1) to name it. */
 int rt_assemble_frame(rt_scene* scene, const rt_render_params* params, const void* const* d_shards,
                       rt_vec3* d_frame, void* stream);
 

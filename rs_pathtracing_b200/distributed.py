@@ -16,6 +16,8 @@ import numpy as np
 from . import api
 from ._ffi import Camera
 
+CUDA_STREAM_LEGACY = 0x1   # cudaStreamLegacy (driver_types.h): explicit handle of the legacy default stream
+
 
 def owned_pixel_coords(width: int, height: int, tile: int, world: int, shard: int):
     """Host mirror of ShardMap::pixel_of (csrc/rt_core.cu): the pixels shard `shard` owns, in its
@@ -87,6 +89,7 @@ class DistributedRenderer:
         self._gather_bufs = None
         self._frame = None
         self._host = None
+        self._exchanged = None   # event on torch's stream: the previous frame's accumulator has been read
 
     def _params(self, w, h, spp, shard):
         return api.render_params(w, h, spp, self.depth, self.seed, self.world, shard, tile=self.tile)
@@ -96,21 +99,34 @@ class DistributedRenderer:
         rank 0 (h x w x 3 float64), None elsewhere.  No host synchronisation besides NCCL's own."""
         torch, dist = self.torch, self.dist
         p = self._params(width, height, samples_number, self.rank)
+        # The library renders on its own non-blocking streams, the exchange runs on torch's / NCCL's: the
+        # orderings between the two are explicit.  (1) This frame's k_resolve overwrites the accumulator the
+        # previous frame's send (rank 0: copy) reads, so that read must be over before the frame starts.
+        if self._exchanged is not None:
+            self._exchanged.synchronize()
         api.render_start(self.dev_scene, camera, p)
         ptr, n = api.render_device_result(self.dev_scene)   # waits for this shard's kernels
         mine = torch.as_tensor(api.DevicePointer(ptr, (n, 4), "<f4", owner=self), device=f"cuda:{self.device}")
         counts = [api.shard_float4_count(p, s) for s in range(self.world)]
         # one exchange per frame: every rank's tile-packed accumulator to rank 0 over NVLink
         shards = exchange_to_rank0(dist, mine, counts, self.rank, self.world, self._gather_bufs)
+        if self._exchanged is None:
+            self._exchanged = torch.cuda.Event()
+        self._exchanged.record()   # (the current stream waits for the NCCL work: req.wait() in exchange_to_rank0)
         if shards is None:
             return None
         if self.world > 1:
             self._gather_bufs = shards
         if self._frame is None or tuple(self._frame.shape) != (height, width, 3):
             self._frame = torch.empty((height, width, 3), dtype=torch.float64, device=mine.device)
+        # (2) k_assemble must run after the receives, i.e. on torch's current stream, and the host copy of
+        # render() after k_assemble.  torch's default stream has the handle 0, which rt_assemble_frame reads as
+        # "the library's stream" (unordered against the NCCL receives: shards arrived after the frame had been
+        # assembled from the previous frame's buffers); cudaStreamLegacy (0x1) names that stream explicitly.
         api.assemble_frame(self.dev_scene, self._params(width, height, samples_number, 0),
                            [int(s.data_ptr()) for s in shards], int(self._frame.data_ptr()),
-                           stream=int(torch.cuda.current_stream().cuda_stream))
+                           stream=int(torch.cuda.current_stream().cuda_stream) or CUDA_STREAM_LEGACY)
+        self._exchanged.record()   # rank 0's own accumulator is read by k_assemble when it is the only shard
         return self._frame
 
     def render(self, camera: Camera, width: int, height: int, samples_number: int) -> Optional[np.ndarray]:

@@ -10,6 +10,7 @@ Two kinds of checks:
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import pytest
@@ -271,3 +272,20 @@ def test_alternative_schedules_give_the_same_frame(monkeypatch, name):
         got = gpu_frame(alt, alt.camera(), w, h, spp, depth, seed)
         monkeypatch.delenv(var)
         assert np.array_equal(got, ref), var
+
+
+def test_distributed_renderer_frames_follow_their_parameters():
+    """DistributedRenderer (world size 1 in-process; every GPU of the box under torchrun when there are several):
+    a sequence of frames with CHANGING sample counts, rendered back to back, each equal to the unsharded frame.
+    Identical consecutive frames cannot show a frame assembled / copied before its shards arrived; this can."""
+    import subprocess
+    import sys
+    torch = pytest.importorskip("torch")
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "check_distributed_frames.py")
+    n = min(torch.cuda.device_count(), 8)
+    cmd = [sys.executable, tool] if n < 2 else [
+        sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+        "--master-port", "29547", tool]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert "deviating pixels 0" in r.stdout

@@ -28,6 +28,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--spp", type=int, default=1024)
     ap.add_argument("--frames", type=int, default=1)
+    ap.add_argument("--check", action="store_true",
+                    help="rank 0 also renders the frame unsharded and reports the pixels that differ beyond float rounding")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -78,6 +80,24 @@ def main():
         frame = dr.render(cam, W, H, args.spp)
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / args.frames)
+    check = None
+    if rank == 0 and args.check:
+        from rs_pathtracing_b200 import api
+        from rs_pathtracing_b200.distributed import owned_pixel_coords
+        sc2 = rt.Scene.from_file(os.path.join(ROOT, "scenes", "dupin.json"), random_spheres_seed=1)
+        ref = np.full((H, W, 3), -1.0)
+        d2 = sc2.device_scene(local_rank)
+        api.render_start(d2, cam, api.render_params(W, H, args.spp, DEPTH, 2024))
+        api.render_wait(d2, ref)
+        bad = (np.abs(frame - ref) > 3e-7 * np.maximum(np.abs(ref), 1e-9)).any(axis=2)
+        per = []
+        for s in range(world):
+            x, y, ok = owned_pixel_coords(W, H, 32, world, s)
+            per.append(int(bad[y[ok], x[ok]].sum()))
+        ys, xs = np.nonzero(bad)
+        check = {"deviating_pixels": int(bad.sum()), "per_shard": per, "unsharded_mean": float(ref.mean()),
+                 "first": [[int(a), int(b), frame[b, a].tolist(), ref[b, a].tolist()] for b, a in list(zip(ys, xs))[:6]],
+                 "tiles": len(set(zip((xs // 32).tolist(), (ys // 32).tolist())))}
     if rank == 0:
         assert frame is not None and np.isfinite(frame).all()
         line = {"config": f"scenes/dupin.json +481 seeded random spheres ({sc.shape_count} shapes), {W}x{H}, "
@@ -87,7 +107,7 @@ def main():
                 "rank0_shard_device_ms": shard_ms, "slowest_shard_device_ms": slowest_shard_ms,
                 "e2e": {"value": n_paths / (e2e_ms * 1e-3) / 1e6, "unit": "Mpaths/s", "ms_per_frame": e2e_ms,
                         "d2h_bytes_per_frame": W * H * 24},
-                "scaling": "strong", "frame_mean": float(frame.mean())}
+                "scaling": "strong", "frame_mean": float(frame.mean()), "check_against_unsharded": check}
         os.write(out_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.barrier()
