@@ -191,5 +191,8 @@ stress. cfg 5 (8.5 G paths) streams through the same 2 x 1.6 GB of path state as
 | `{cid}_render_*.jpg` | `tools/render.py` output (GpuRenderer -> rt_tonemap_rgba8 -> rth_save_png), 512x384, 256 spp, depth 50, as JPEG previews |
 | `r1a_*` ... `r1x_*` | earlier captures of this round (fused k_bounce; first wavefront split; cull tree; before / after the march work) |
 """
+# hand-written notes of later, partial captures (profiles/NOTES_*.md) are kept below the generated part
+for extra in sorted(f for f in os.listdir(P) if f.startswith("NOTES_") and f.endswith(".md")):
+    readme += open(os.path.join(P, extra)).read()
 open(os.path.join(P, "README.md"), "w").write(readme)
 print("profiles/README.md written for", cid)
