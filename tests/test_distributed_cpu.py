@@ -72,3 +72,41 @@ def test_owned_pixels_partition_the_image(world):
         assert len(x) == api.shard_float4_count(p, s)
         np.add.at(seen, (y[ok], x[ok]), 1)
     assert (seen == 1).all()
+
+
+def _worker_sequence(rank, world, port, width, height, tile, out_path):
+    """consecutive frames with DIFFERENT contents through the same (reused) gather buffers, no barrier between"""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        x, y, ok = owned_pixel_coords(width, height, tile, world, rank)
+        p = api.render_params(width, height, 1, 8, 0, world, rank, tile=tile)
+        counts = [api.shard_float4_count(p, s) for s in range(world)]
+        bufs, frames = None, []
+        mine = torch.zeros((counts[rank], 4), dtype=torch.float32)    # one accumulator, overwritten every frame
+        for k, spp in enumerate((4, 1, 16, 2)):
+            acc = np.zeros((counts[rank], 4), dtype=np.float32)
+            acc[ok, :3] = ((_pixel_value(x[ok], y[ok]) + k) * spp).astype(np.float32)
+            acc[ok, 3] = spp
+            mine.copy_(torch.from_numpy(acc))
+            shards = exchange_to_rank0(dist, mine, counts, rank, world, bufs)
+            if rank == 0:
+                bufs = shards
+                frames.append(assemble_host([t.numpy() for t in shards], width, height, tile, world))
+        if rank == 0:
+            np.save(out_path, np.stack(frames))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_consecutive_frames_through_reused_gather_buffers(tmp_path):
+    world, width, height, tile = 2, 100, 70, 32
+    out = str(tmp_path / "frames.npy")
+    mp.spawn(_worker_sequence, args=(world, _free_port(), width, height, tile, out), nprocs=world, join=True)
+    frames = np.load(out)
+    yy, xx = np.mgrid[0:height, 0:width]
+    for k in range(4):
+        want = (_pixel_value(xx, yy) + k).astype(np.float32).astype(np.float64)
+        assert np.array_equal(frames[k], want), k
