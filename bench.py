@@ -249,6 +249,29 @@ def main():
     h2d = C.sizeof(_ffi.Camera) + C.sizeof(_ffi.RenderParams)
     d2h = WIDTH * HEIGHT * 24
 
+    # --- frame check (untimed): consecutive bench frames are identical, which would hide a frame assembled from
+    # stale shard buffers; so one more frame with ANOTHER seed and fewer samples goes through the same
+    # DistributedRenderer and is compared, on rank 0, with the unsharded render of that seed -----------------
+    frame_check = None
+    try:
+        dr.seed = RNG_SEED + 1
+        check_spp = 16
+        chk = dr.render(cam, WIDTH, HEIGHT, check_spp)        # collective: every rank takes part
+        dr.seed = RNG_SEED
+        if rank == 0:
+            sc2 = rt.Scene.from_file(SCENE, random_spheres_seed=SCENE_SEED)
+            ref = np.full((HEIGHT, WIDTH, 3), -1.0)
+            d2 = sc2.device_scene(local_rank)
+            api.render_start(d2, cam, api.render_params(WIDTH, HEIGHT, check_spp, DEPTH, RNG_SEED + 1))
+            api.render_wait(d2, ref)
+            # the exchanged accumulators hold float sums: equal to the f64 frame up to float rounding
+            bad = (np.abs(chk - ref) > 3e-7 * np.maximum(np.abs(ref), 1e-9)).any(axis=2)
+            frame_check = {"what": f"DistributedRenderer frame (seed {RNG_SEED + 1}, {check_spp} spp) against the unsharded "
+                                   "render on rank 0, tolerance 3e-7 relative", "deviating_pixels": int(bad.sum())}
+    except Exception as e:   # the check must never cost the bench line
+        frame_check = {"error": repr(e)}
+    barrier()
+
     line = None
     if rank == 0:
         assert host_frame is not None and np.isfinite(host_frame).all() and host_frame.mean() > 0.01
@@ -328,6 +351,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "Mpaths/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "scene_upload_ms_once": scene_upload_ms},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "frame_check": frame_check,
         }
         emit(line)
     if dist is not None:
