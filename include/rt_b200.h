@@ -197,7 +197,8 @@ int rt_intersect_batch(rt_scene* scene, const rt_ray* rays, uint64_t n, double t
                        double* uv, uint8_t* front_face);
 
 /* Same, with every pointer a DEVICE pointer on the scene's device and no copies; runs on
- * `stream` (a cudaStream_t passed as void*, NULL = the library's stream) and does not
+ * `stream` (a cudaStream_t passed as void*, NULL = the library's own non-blocking stream; the legacy
+ * default stream, whose handle is 0, is named by cudaStreamLegacy = 0x1) and does not
  * synchronise.  Used for kernel-only timing and by callers that keep rays resident. */
 int rt_intersect_batch_device(rt_scene* scene, const rt_ray* d_rays, uint64_t n, double t_min,
                               double t_max, int mode, int32_t* d_shape_index, double* d_t,
