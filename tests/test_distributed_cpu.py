@@ -110,3 +110,22 @@ def test_consecutive_frames_through_reused_gather_buffers(tmp_path):
     for k in range(4):
         want = (_pixel_value(xx, yy) + k).astype(np.float32).astype(np.float64)
         assert np.array_equal(frames[k], want), k
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_cfg5_frame_partition_and_balance(world):
+    """BASELINE configs[4]: 3840x2160 in 32x32 tiles (120 x 67.5: the last tile row is clipped, and 120 is a multiple
+    of every shard count, so the row rotation is what keeps a shard from owning whole tile columns)"""
+    width, height, tile = 3840, 2160, 32
+    seen = np.zeros((height, width), dtype=np.uint8)
+    valid = []
+    for s in range(world):
+        x, y, ok = owned_pixel_coords(width, height, tile, world, s)
+        p = api.render_params(width, height, 1, 8, 0, world, s, tile=tile)
+        assert len(x) == api.shard_float4_count(p, s)
+        np.add.at(seen, (y[ok], x[ok]), 1)
+        valid.append(int(ok.sum()))
+        # a shard's tiles spread over (nearly) all tile columns, not width / world of them
+        assert len(np.unique(x[ok] // tile)) >= 120 - 1
+    assert (seen == 1).all()
+    assert max(valid) - min(valid) <= 120 * tile * tile // world   # within one tile row's share of each other
