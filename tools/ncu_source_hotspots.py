@@ -43,5 +43,8 @@ print(f"kernel {want} launch {which}: warp instr {T}, samples {S}")
 byfile = collections.Counter()
 for (fn, ln), v in tot.items(): byfile[fn] += v
 print("by file:", {k: f"{v / T * 100:.1f}%" for k, v in byfile.items()})
-for line, v in tot.most_common(60):
+order = sorted(tot.items(), key=lambda kv: kv[0]) if os.environ.get("NCU_ALL_LINES") else tot.most_common(60)
+for line, v in order:
+    if os.environ.get("NCU_ALL_LINES") and v / T < 0.0005:
+        continue
     print(f"{line[0]:14s}:{line[1]:4d} instr {v / T * 100:5.1f}%  samples {smp[line] / max(S,1) * 100:5.1f}%  thr/instr {thr[line] / max(v, 1):5.1f} | {text[line].strip()[:90]}")
