@@ -1,8 +1,10 @@
 """ORACLE — TEST INFRASTRUCTURE ONLY.  ctypes loader for oracle/liboracle.so.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import
-this module; the product package never does.  The scene description structs come from the product's
-ctypes bindings because they are the C-ABI types of include/rt_b200.h (plain data, no code).
+this module; the product package never does.  The scene description structs are the C-ABI types of
+include/rt_b200.h (plain data, no code): when the product package is already imported (the tests) its
+ctypes classes are used, so that structures pass between the two without conversion; otherwise (bench.py
+--impl reference) the oracle's own copy in abi_types.py, and nothing of the product is loaded.
 """
 from __future__ import annotations
 
@@ -13,7 +15,12 @@ import subprocess
 
 import numpy as np
 
-from rs_pathtracing_b200._ffi import Camera, ImageParams, Ray, SceneDesc, Vec3
+import sys
+
+if "rs_pathtracing_b200" in sys.modules:
+    from rs_pathtracing_b200._ffi import Camera, Image, ImageParams, Material, Perlin, Ray, SceneDesc, Texture, Vec3
+else:
+    from .abi_types import Camera, Image, ImageParams, Material, Perlin, Ray, SceneDesc, Texture, Vec3
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "liboracle.so")
@@ -164,6 +171,65 @@ def perlin_noise(table, p) -> float:
 
 def perlin_turb(table, p, depth=7) -> float:
     return lib().orc_perlin_turb(C.addressof(table), Vec3(*map(float, p)), depth)
+
+
+def save_flat_scene(path: str, desc, cam, note: str = "") -> None:
+    """Write an rt_scene_desc + camera as an .npz (tools/make_oracle_scenes.py): what the reference arm of bench.py
+    loads instead of importing the product's scene loader."""
+    n = desc.n_shapes
+    arr = lambda ptr, shape, dt: np.ctypeslib.as_array(ptr, shape=shape).astype(dt).copy() if shape[0] else np.zeros(shape, dt)
+    mats = np.array([(desc.materials[i].kind, desc.materials[i].texture, desc.materials[i].scalar)
+                     for i in range(desc.n_materials)], dtype=np.float64).reshape(-1, 3)
+    texs = np.array([(t.kind, t.odd, t.even, t.image, t.color.x, t.color.y, t.color.z)
+                     for t in (desc.textures[i] for i in range(desc.n_textures))], dtype=np.float64).reshape(-1, 7)
+    out = {"kind": arr(desc.kind, (n,), np.uint8), "flags": arr(desc.flags, (n,), np.uint8),
+           "inverse": arr(desc.inverse, (n, 12), np.float64), "direct": arr(desc.direct, (n, 12), np.float64),
+           "params": arr(desc.params, (n, 8), np.float64), "material": arr(desc.material, (n,), np.uint32),
+           "materials": mats, "textures": texs, "note": np.array(note),
+           "camera": np.array(cam.position.tuple() + cam.direction.tuple() + cam.up.tuple() + cam.right.tuple()
+                              + (cam.fov_rad, cam.focal_length))}
+    for i in range(desc.n_images):
+        im = desc.images[i]
+        out[f"image{i}"] = np.ctypeslib.as_array(im.rgba, shape=(im.height, im.width, 4)).copy()
+    if desc.n_noise:
+        out["noise"] = np.frombuffer(C.string_at(desc.noise, C.sizeof(Perlin) * desc.n_noise), dtype=np.uint8).copy()
+    np.savez_compressed(path, **out)
+
+
+def load_flat_scene(path: str):
+    """-> (OracleScene, Camera) from a file written by save_flat_scene"""
+    z = np.load(path)
+    keep = {k: np.ascontiguousarray(z[k]) for k in z.files}
+    d = SceneDesc()
+    n = keep["kind"].shape[0]
+    d.n_shapes = n
+    ptr = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    d.kind, d.flags = ptr(keep["kind"], C.c_uint8), ptr(keep["flags"], C.c_uint8)
+    d.inverse, d.direct, d.params = (ptr(keep[k], C.c_double) for k in ("inverse", "direct", "params"))
+    d.material = ptr(keep["material"], C.c_uint32)
+    mats = (Material * max(len(keep["materials"]), 1))()
+    for i, (k, t, s) in enumerate(keep["materials"]):
+        mats[i].kind, mats[i].texture, mats[i].scalar = int(k), int(t), float(s)
+    texs = (Texture * max(len(keep["textures"]), 1))()
+    for i, row in enumerate(keep["textures"]):
+        texs[i].kind, texs[i].odd, texs[i].even, texs[i].image = (int(v) for v in row[:4])
+        texs[i].color = Vec3(*row[4:7])
+    d.n_materials, d.materials = len(keep["materials"]), mats
+    d.n_textures, d.textures = len(keep["textures"]), texs
+    n_img = sum(1 for k in keep if k.startswith("image"))
+    imgs = (Image * max(n_img, 1))()
+    for i in range(n_img):
+        a = keep[f"image{i}"]
+        imgs[i].height, imgs[i].width, imgs[i].rgba = a.shape[0], a.shape[1], ptr(a, C.c_uint8)
+    d.n_images, d.images = n_img, imgs
+    if "noise" in keep:
+        d.n_noise = keep["noise"].size // C.sizeof(Perlin)
+        d.noise = C.cast(keep["noise"].ctypes.data, C.POINTER(Perlin))
+    c = keep["camera"]
+    cam = Camera()
+    cam.position, cam.direction, cam.up, cam.right = (Vec3(*c[3 * i: 3 * i + 3]) for i in range(4))
+    cam.fov_rad, cam.focal_length = float(c[12]), float(c[13])
+    return OracleScene(d, keepalive=(keep, mats, texs, imgs)), cam
 
 
 class OracleScene:

@@ -114,5 +114,5 @@ def test_cuda_reproduces_golden_frames(tag):
     got = rt.GpuRenderer(sc, 12, depth, seed=seed).render(sc.camera(), w, h, spp)
     want = g["frame"]
     scale = np.maximum(want.max(axis=2, keepdims=True), 1.0) * spp   # radiance is accumulated as float
-    bad = (np.abs(got - want) / scale > 2e-6).any(axis=2)
-    assert bad.mean() <= 0.002, f"{bad.sum()} of {w * h} pixels differ from the golden frame"
+    bad = (np.abs(got - want) / scale > 1e-7).any(axis=2)   # float32 rounding of the stored radiance, no pixel exempt
+    assert not bad.any(), f"{bad.sum()} of {w * h} pixels differ from the golden frame"

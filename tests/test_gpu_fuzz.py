@@ -103,5 +103,5 @@ def test_random_scene_parity(seed):
     got = rt.GpuRenderer(sc, 12, depth, seed=seed).render(cam, w, h, spp)
     ref, _ = osc.render(cam, w, h, spp, depth, seed=seed, rng="philox")
     scale = np.maximum(ref.max(axis=2, keepdims=True), 1.0) * spp
-    bad = (np.abs(got - ref) / scale > 2e-6).any(axis=2)
-    assert bad.mean() <= 0.004, f"seed {seed}: {bad.sum()} of {w * h} pixels differ"
+    bad = (np.abs(got - ref) / scale > 1e-7).any(axis=2)   # float32 rounding of the stored radiance; no pixel exempt
+    assert not bad.any(), f"seed {seed}: {bad.sum()} of {w * h} pixels differ, max {(np.abs(got - ref) / scale).max():.3e}"

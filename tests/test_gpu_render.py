@@ -2,8 +2,11 @@
 
 Two kinds of checks:
   * SAME paths: the oracle run with the shared Philox schedule follows exactly the GPU's paths, so
-    frames agree per pixel up to the float4 radiance rounding (tolerance 2e-6 relative to the pixel's
-    brightest sample, written below);
+    EVERY pixel agrees up to the float32 rounding of the stored per-path radiance: each of the spp samples of a
+    pixel is rounded once (2^-24 relative), so the pixel sum is off by at most 6e-8 x (sum of the samples); the
+    tolerance below is 1e-7 of max(mean, 1) x spp, and NO pixel may exceed it.  (Round 1 allowed 0.2 % of the
+    pixels to deviate; tools/pixel_allowance_probe.py found none on 553 k pixels of all seven scenes, max
+    relative error 1.4e-8 -- profiles/r2c_pixel_allowance_probe.jsonl -- so the allowance is gone.)
   * INDEPENDENT streams: against an oracle render with an unrelated RNG the frames must agree within
     the statistical tolerance of SURVEY §8(d): RMSE <= 1.25 * r0 + 1e-3 with r0 the oracle-vs-oracle
     noise floor, and mean luminance within 0.5 % (+ a noise allowance at the tiny test sizes).
@@ -29,7 +32,7 @@ def gpu_frame(sc, cam, w, h, spp, depth, seed):
     return r.render(cam, w, h, spp)
 
 
-SAME_PATH_TOL = 2e-6
+SAME_PATH_TOL = 1e-7
 
 
 @pytest.mark.parametrize("name,w,h,spp,depth", [
@@ -48,7 +51,7 @@ def test_same_paths_as_oracle(name, w, h, spp, depth):
     scale = np.maximum(want.max(axis=2, keepdims=True), 1.0) * spp   # a pixel is a mean of spp float-rounded samples
     err = np.abs(got - want) / scale
     bad = (err > SAME_PATH_TOL).any(axis=2)
-    assert bad.mean() <= 0.002, f"{bad.sum()} of {w*h} pixels differ (max err {err.max():.3e})"
+    assert not bad.any(), f"{bad.sum()} of {w*h} pixels differ (max err {err.max():.3e})"
     assert np.isfinite(got).all()
 
 
@@ -67,7 +70,7 @@ def test_same_paths_all_material_and_texture_branches():
     want, _ = po.OracleScene(sc.desc()).render(cam, w, h, spp, depth, seed=99, rng="philox")
     scale = np.maximum(want.max(axis=2, keepdims=True), 1.0) * spp
     err = np.abs(got - want) / scale
-    assert ((err > SAME_PATH_TOL).any(axis=2)).mean() <= 0.002, err.max()
+    assert not (err > SAME_PATH_TOL).any(), err.max()
 
 
 def luminance(img):
@@ -78,10 +81,24 @@ def display(img):  # main_raylib.rs:240-245 before quantisation
     return np.minimum(np.sqrt(np.maximum(img, 0)), 0.999)
 
 
-@pytest.mark.parametrize("name", ["spheres.json", "cornell_box.json"])
-def test_statistical_agreement_with_independent_oracle(name):
+def _variant_4b(sc):
+    """config 4b: every material / texture kind live, camera looking at the origin"""
+    sc.assign_material(1, "EarthMap")        # Sphere1  -> Metal + ImageTexture
+    sc.assign_material(2, "Glass")           # Cushion  -> Dielectric
+    sc.assign_material(5, "Lambertian01")    # a random sphere -> Lambertian + UVChecker
+    sc.assign_material(6, "WhiteMirror")
+    c0 = sc.camera()
+    pos = np.array(c0.position.tuple())
+    return rt.camera_new(pos, -pos, (0, 1, 0), 1.0, c0.fov_rad)
+
+
+# BASELINE.md's gate names configurations 1, 3, 4 and 5: spheres, cornell_box, detached_materials (as shipped = 4a and
+# the all-branches variant 4b) and dupin
+@pytest.mark.parametrize("name,variant", [("spheres.json", ""), ("cornell_box.json", ""), ("detached_materials.json", ""),
+                                          ("detached_materials.json", "4b"), ("dupin.json", "")])
+def test_statistical_agreement_with_independent_oracle(name, variant):
     sc = rt.Scene.from_file(scene_path(name), random_spheres_seed=1)
-    cam = sc.camera()
+    cam = _variant_4b(sc) if variant == "4b" else sc.camera()
     w, h, spp, depth = 48, 36, 64, 8
     osc = po.OracleScene(sc.desc())
     a, _ = osc.render(cam, w, h, spp, depth, seed=1, rng="xoshiro", use_bvh=True)
