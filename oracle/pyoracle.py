@@ -57,17 +57,17 @@ def lib() -> C.CDLL:
     L.orc_reflect.restype = Vec3
     L.orc_refract.argtypes = [Vec3, Vec3, C.c_double]
     L.orc_refract.restype = Vec3
-    L.orc_camera_new.argtypes = [Vec3, Vec3, Vec3, C.c_double, C.c_double, C.POINTER(Camera)]
-    L.orc_raycaster_pixel_resolution.argtypes = [C.POINTER(Camera), ImageParams]
+    L.orc_camera_new.argtypes = [Vec3, Vec3, Vec3, C.c_double, C.c_double, C.c_void_p]
+    L.orc_raycaster_pixel_resolution.argtypes = [C.c_void_p, ImageParams]
     L.orc_raycaster_pixel_resolution.restype = C.c_double
-    L.orc_raycaster_get_ray.argtypes = [C.POINTER(Camera), ImageParams, C.c_double, C.c_double, C.POINTER(Ray)]
+    L.orc_raycaster_get_ray.argtypes = [C.c_void_p, ImageParams, C.c_double, C.c_double, C.c_void_p]
     L.orc_philox4x32_10.argtypes = [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.orc_philox_stream.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, d16]
     L.orc_surface_func.argtypes = [d16, Vec3]
     L.orc_surface_func.restype = C.c_double
     L.orc_surface_gradient.argtypes = [d16, Vec3]
     L.orc_surface_gradient.restype = Vec3
-    L.orc_scene_create.argtypes = [C.POINTER(SceneDesc)]
+    L.orc_scene_create.argtypes = [C.c_void_p]
     L.orc_scene_create.restype = C.c_void_p
     L.orc_scene_destroy.argtypes = [C.c_void_p]
     L.orc_scene_build_bvh.argtypes = [C.c_void_p, C.c_uint64]
@@ -76,12 +76,12 @@ def lib() -> C.CDLL:
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p]
     L.orc_intersect_batch.restype = C.c_double
-    L.orc_render.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+    L.orc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                              C.c_uint64, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
     L.orc_render.restype = C.c_double
     L.orc_trace_pixel_samples.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
                                           C.c_int, C.POINTER(Vec3)]
-    L.orc_pixel_sample_colors.argtypes = [C.c_void_p, C.POINTER(Camera), C.c_uint32, C.c_uint32, C.c_uint32,
+    L.orc_pixel_sample_colors.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                           C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]
     L.orc_hardware_threads.restype = C.c_uint32
     L.orc_shape_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]

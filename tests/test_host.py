@@ -304,3 +304,61 @@ def test_cull_tree_invariant_on_a_large_random_scene():
                                          C.byref(worst)) == 0
     assert tree.value + flat.value == 1400 and tree.value > 1300 and roots.value >= 3
     assert worst.value <= 1e-7, worst.value
+
+
+def test_oracle_abi_types_match_the_product_bindings():
+    """oracle/abi_types.py is a second copy of the plain-data C-ABI structs (so that bench.py's reference arm runs
+    the oracle without importing the product): field names, ctypes and sizes must agree with _ffi.py"""
+    import ctypes as C
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("oracle_abi_types", os.path.join(ROOT, "oracle", "abi_types.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    from rs_pathtracing_b200 import _ffi
+
+    def flat(t):
+        out = []
+        for name, ct in t._fields_:
+            if isinstance(ct, type) and issubclass(ct, C.Structure):
+                out.append((name, flat(ct)))
+            elif hasattr(ct, "_type_") and isinstance(ct._type_, type) and issubclass(ct._type_, C.Structure):
+                out.append((name, getattr(ct, "_length_", "ptr"), flat(ct._type_)))
+            else:
+                out.append((name, C.sizeof(ct), getattr(ct, "_type_", None) if not hasattr(ct, "contents") else "ptr"))
+        return out
+
+    for name in ("Vec3", "Ray", "Camera", "ImageParams", "Material", "Texture", "Image", "Perlin", "SceneDesc"):
+        a, b = getattr(mod, name), getattr(_ffi, name)
+        assert C.sizeof(a) == C.sizeof(b), name
+        assert [f[0] for f in a._fields_] == [f[0] for f in b._fields_], name
+        assert flat(a) == flat(b), name
+
+
+def test_committed_flat_scenes_equal_the_loader_output(tmp_path):
+    """oracle/scenes/cfg*.npz (what bench.py --impl reference renders) against a fresh flattening by the host mirror"""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from make_oracle_scenes import config_scene
+    from oracle import pyoracle as po
+    for cfg in ("1", "3", "4a", "4b", "5"):
+        sc, cam, note = config_scene(cfg)
+        fresh = os.path.join(tmp_path, f"cfg{cfg}.npz")
+        po.save_flat_scene(fresh, sc.desc(), cam, note)
+        a, b = np.load(fresh), np.load(os.path.join(ROOT, "oracle", "scenes", f"cfg{cfg}.npz"))
+        assert sorted(a.files) == sorted(b.files), cfg
+        for k in a.files:
+            assert np.array_equal(a[k], b[k]), (cfg, k)
+
+
+def test_bench_reference_arm_runs_the_oracle_alone():
+    """`bench.py --impl reference` prints the contract's JSON line and loads nothing of the product package (it
+    asserts that itself); config 2 is the quick one"""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "2",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "Mrays/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
