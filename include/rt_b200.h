@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 3
+#define RT_B200_ABI_VERSION 4
 
 typedef enum rt_status {
     RT_OK = 0,
@@ -171,6 +171,20 @@ int rt_device_count(void);
 int rt_scene_create(const rt_scene_desc* desc, int device, rt_scene** out);
 void rt_scene_destroy(rt_scene* scene);
 
+/* The same for SEVERAL devices of one box behind ONE handle -- what a single-process caller like the reference's
+ * bins (one UI thread, one `impl Renderer`, src/renderer/mod.rs:47-56) needs to use more than one GPU.  The scene
+ * is replicated on every listed device.  A whole-frame rt_render_start (shard_count 0 or 1) is then sharded over
+ * the devices by interleaved tiles (the rule documented at rt_render_params, shard k on device_ids[k]); the shards
+ * render concurrently, each accumulator reaches device_ids[0] with one peer copy on its own stream, and the frame
+ * is assembled there.  rt_render_poll / rt_render_wait deliver the assembled frame (no partial delivery: *done
+ * flips when the whole frame is there), rt_render_device_frame exposes it on device_ids[0].  The frame is the one a
+ * single device renders, bit for bit (the RNG is keyed per pixel, the accumulators are f64 sums).  Every other
+ * entry point (rt_intersect_batch, rt_trace_pixel_samples, statistics, an explicitly sharded rt_render_start)
+ * addresses device_ids[0].  n_devices = 1 is rt_scene_create. */
+int rt_scene_create_multi(const rt_scene_desc* desc, int n_devices, const int* device_ids, rt_scene** out);
+/* number of devices behind the handle (1 for rt_scene_create) */
+int rt_scene_device_count(rt_scene* scene);
+
 /* ---- batched nearest hit (replaces Scene::closest_hit, src/world/mod.rs:42-44, with the
  *      ShapeCollection semantics of src/world/shapes/mod.rs:573-597) -------------------- */
 
@@ -212,8 +226,14 @@ typedef struct rt_render_params {
     uint32_t samples_number;   /* start_rendering's samples_number                               */
     uint32_t max_depth;        /* ThreadPoolRenderer::new's depth (ray_color's depth argument)   */
     uint64_t seed;             /* counter-based RNG key                                          */
-    /* image sharding (one process per GPU): this handle renders the tiles t with
-     * t % shard_count == shard_index, tiles numbered row-major.  1 / 0 = whole image. */
+    /* image sharding (one process per GPU): this handle renders the tiles k with k % shard_count == shard_index.
+     * 1 / 0 = whole image.  Tile NUMBERING (shard_count > 1): with tiles_x = ceil(width / tile_width), tile
+     * number k lies in tile row ty = k / tiles_x at tile column
+     *     tx = (k % tiles_x + ty % tiles_x) % tiles_x
+     * -- row-major, with row ty rotated by ty positions, so that a shard owns diagonals instead of whole columns
+     * of tiles when tiles_x is a multiple of shard_count.  A shard's accumulator (rt_render_device_result) lists
+     * its tiles in increasing k, each tile row-major and padded to tile_width*tile_height at the image border.
+     * rt_assemble_frame is the supported way to turn gathered accumulators back into a frame. */
     uint32_t shard_count, shard_index;
     uint32_t tile_width, tile_height;   /* 0 = default (32 x 32)                                 */
 } rt_render_params;
@@ -238,20 +258,28 @@ int rt_render_stop(rt_scene* scene);
  * the same camera, image, sharding, max_depth and seed as the previous one ADDS its samples_number samples to
  * the accumulator: its paths take the sample indices that follow the ones already traced (so k frames of n
  * samples are the very paths of one frame of k*n samples), and rt_render_poll / rt_render_device_result deliver
- * the mean over everything accumulated.  Any other frame, and every call of this function, starts afresh.
+ * the mean over everything accumulated, bit for bit).  Any other frame, and every call of this function, starts
+ * afresh.  Scenes with more than 32 ray-marched shapes are rendered by the fused fallback kernel, which cannot
+ * accumulate: enabling returns RT_ERR_STATE there.
  * rt_render_accumulated_samples: the number of samples per pixel the accumulator holds (0 = empty). */
 int rt_render_set_accumulate(rt_scene* scene, int enabled);
 int rt_render_accumulated_samples(rt_scene* scene, uint32_t* samples);
 
 /* Device-side result of the last started frame, for callers that gather shards over NCCL:
- * a float4 (r,g,b sums; w = samples) per owned pixel, tile-packed in this shard's tile order
- * (tile-major, row-major inside a tile, tiles clipped at the image border are still padded to
+ * FOUR DOUBLES (r, g, b sums; samples) per owned pixel -- the f64 sums themselves, so that the assembled frame
+ * equals the unsharded one bit for bit; they were floats before ABI 4, hence the names -- tile-packed in this
+ * shard's tile order (see rt_render_params; tiles clipped at the image border are still padded to
  * tile_width*tile_height).  *d_accum is a device pointer owned by the library, valid until the
- * next rt_render_start / rt_scene_destroy; *n_float4 its length.  The frame must be complete. */
+ * next rt_render_start / rt_scene_destroy; *n_float4 the number of 4-vectors.  The frame must be complete. */
 int rt_render_device_result(rt_scene* scene, const void** d_accum, uint64_t* n_float4);
 
-/* number of float4 slots a shard owns (so every rank can size the gather) */
+/* number of 4-vector slots (32 bytes each) a shard owns, so every rank can size the gather */
 uint64_t rt_shard_float4_count(const rt_render_params* params, uint32_t shard_index);
+
+/* The completed frame on the device: *d_frame = width*height rt_vec3 (x + y*width, linear mean radiance) on the
+ * handle's (first) device, valid until the next rt_render_start; waits for the frame in flight.  For an unsharded
+ * frame of a single-device handle and for every frame of a multi-device handle. */
+int rt_render_device_frame(rt_scene* scene, const rt_vec3** d_frame, uint64_t* n_pixels);
 
 /* Assemble a full frame from the gathered shard buffers (all DEVICE pointers on the scene's
  * device): d_shards[s] = shard s's tile-packed float4 buffer; d_frame = w*h rt_vec3 (x + y*w,
@@ -262,8 +290,13 @@ int rt_assemble_frame(rt_scene* scene, const rt_render_params* params, const voi
                       rt_vec3* d_frame, void* stream);
 
 /* Frame post-process of the bins (src/bin/main_raylib.rs:239-247): sqrt, clamp(0,0.999)*256 ->
- * RGBA8, alpha 255.  Host in / host out convenience running on the device. */
+ * RGBA8, alpha 255.  Host in / host out convenience running on the device (persistent device buffers). */
 int rt_tonemap_rgba8(rt_scene* scene, const rt_vec3* frame, uint64_t n_pixels, uint8_t* rgba);
+/* The same applied to the frame the library already holds on the device (rt_render_device_frame): no f64 frame
+ * crosses the bus -- 4 bytes per pixel instead of 24 come back.  Either output may be NULL: *d_rgba = the
+ * library's persistent RGBA8 buffer on the device (valid until the next tonemap call), rgba_host = a host buffer
+ * of 4*n_pixels bytes to copy it to. */
+int rt_tonemap_rgba8_device(rt_scene* scene, const uint8_t** d_rgba, uint8_t* rgba_host, uint64_t* n_pixels);
 
 /* ---- pixel probe (replaces renderer::trace_pixel_samples, src/renderer/mod.rs:151-155) */
 

@@ -43,6 +43,8 @@ const char* rth_scene_material_name(rth_scene* scene, uint32_t index);
 int rth_scene_assign_material(rth_scene* scene, uint32_t shape_index, const char* material_name);
 /* the device-resident rt_scene (uploaded on first use); owned by the rth_scene */
 int rth_scene_device(rth_scene* scene, int device, rt_scene** out);
+/* ONE rt_scene over several devices (rt_scene_create_multi), created on first use per device list */
+int rth_scene_device_multi(rth_scene* scene, int n_devices, const int* device_ids, rt_scene** out);
 
 /* Camera::new (fov in radians) */
 int rth_camera_new(rt_vec3 position, rt_vec3 direction, rt_vec3 up, double focal_length, double fov_rad,
@@ -53,6 +55,9 @@ int rth_transform_new(rt_vec3 translate, rt_vec3 rotate_deg, rt_vec3 scale, doub
 /* GpuRenderer: ThreadPoolRenderer::new(scene, thread_number, depth) + the Renderer trait */
 int rth_renderer_new(rth_scene* scene, uint32_t thread_number, uint32_t depth, int device, uint64_t seed,
                      rth_renderer** out);
+/* the same renderer over several devices of the box, one process (frames sharded by interleaved tiles) */
+int rth_renderer_new_multi(rth_scene* scene, uint32_t thread_number, uint32_t depth, int n_devices,
+                           const int* device_ids, uint64_t seed, rth_renderer** out);
 void rth_renderer_free(rth_renderer* r);
 int rth_renderer_start_rendering(rth_renderer* r, const rt_camera* camera, rt_image_params img,
                                  uint32_t samples_number);

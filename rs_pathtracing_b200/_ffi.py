@@ -128,6 +128,8 @@ CORE_SYMBOLS = {
     "rt_device_count": (C.c_int, []),
     "rt_scene_create": (C.c_int, [C.POINTER(SceneDesc), C.c_int, C.POINTER(C.c_void_p)]),
     "rt_scene_destroy": (None, [C.c_void_p]),
+    "rt_scene_create_multi": (C.c_int, [C.POINTER(SceneDesc), C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
+    "rt_scene_device_count": (C.c_int, [C.c_void_p]),
     "rt_intersect_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rt_intersect_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_int,
@@ -143,7 +145,9 @@ CORE_SYMBOLS = {
     "rt_shard_float4_count": (C.c_uint64, [C.POINTER(RenderParams), C.c_uint32]),
     "rt_assemble_frame": (C.c_int, [C.c_void_p, C.POINTER(RenderParams), C.POINTER(C.c_void_p), C.c_void_p,
                                     C.c_void_p]),
+    "rt_render_device_frame": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     "rt_tonemap_rgba8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "rt_tonemap_rgba8_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p, C.POINTER(C.c_uint64)]),
     "rt_trace_pixel_samples": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32,
                                          C.POINTER(Vec3)]),
     "rt_get_stats": (C.c_int, [C.c_void_p, C.POINTER(Stats)]),
@@ -174,9 +178,12 @@ HOST_SYMBOLS = {
     "rth_scene_material_name": (C.c_char_p, [C.c_void_p, C.c_uint32]),
     "rth_scene_assign_material": (C.c_int, [C.c_void_p, C.c_uint32, C.c_char_p]),
     "rth_scene_device": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "rth_scene_device_multi": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_void_p)]),
     "rth_camera_new": (C.c_int, [Vec3, Vec3, Vec3, C.c_double, C.c_double, C.POINTER(Camera)]),
     "rth_transform_new": (C.c_int, [Vec3, Vec3, Vec3, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "rth_renderer_new": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "rth_renderer_new_multi": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(C.c_int), C.c_uint64,
+                                         C.POINTER(C.c_void_p)]),
     "rth_renderer_free": (None, [C.c_void_p]),
     "rth_renderer_start_rendering": (C.c_int, [C.c_void_p, C.POINTER(Camera), ImageParams, C.c_uint32]),
     "rth_renderer_render_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_int)]),

@@ -90,6 +90,7 @@ class Scene:
     def __init__(self, handle):
         self._h = handle
         self._keep = None
+        self._device = 0   # the device the helpers below address by default: the last one asked for explicitly
 
     @classmethod
     def from_json(cls, data: str, random_spheres_seed: int = 1, add_random_spheres: bool = True,
@@ -150,14 +151,27 @@ class Scene:
     def assign_material(self, shape_index: int, material_name: str) -> None:
         _check(_ffi.host().rth_scene_assign_material(self._h, shape_index, material_name.encode()), host=True)
 
-    def device_scene(self, device: int = 0) -> C.c_void_p:
+    def device_scene(self, device: Optional[int] = None) -> C.c_void_p:
+        """the rt_scene handle on `device` (one per device, created on first use, alive as long as this Scene).
+        device=None: the device last asked for explicitly (a renderer's), 0 at first."""
+        if device is None:
+            device = self._device
+        else:
+            self._device = device
         out = C.c_void_p()
         _check(_ffi.host().rth_scene_device(self._h, device, C.byref(out)), host=True)
         return out
 
+    def device_scene_multi(self, devices) -> C.c_void_p:
+        """ONE rt_scene handle over several devices (rt_scene_create_multi): whole-frame renders are sharded over them"""
+        ids = (C.c_int * len(devices))(*devices)
+        out = C.c_void_p()
+        _check(_ffi.host().rth_scene_device_multi(self._h, len(devices), ids, C.byref(out)), host=True)
+        return out
+
     # Scene::closest_hit (src/world/mod.rs:42-44) on a batch
     def closest_hit(self, rays: np.ndarray, min_t: float = 0.001, max_t: float = math.inf,
-                    mode: int = _ffi.RT_ISECT_BRUTE, device: int = 0, want=("index", "t", "normal", "point", "uv", "front")):
+                    mode: int = _ffi.RT_ISECT_BRUTE, device: Optional[int] = None, want=("index", "t", "normal", "point", "uv", "front")):
         rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
         n = rays.shape[0]
         out = {
@@ -175,7 +189,7 @@ class Scene:
         return {k: v for k, v in out.items() if v is not None}
 
     def trace_pixel_samples(self, rays: np.ndarray, depth: int, seed: int = 0, pixel_index: int = 0,
-                            device: int = 0):
+                            device: Optional[int] = None):
         """renderer::trace_pixel_samples (src/renderer/mod.rs:151-155)."""
         rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
         mean = Vec3()
@@ -183,18 +197,18 @@ class Scene:
                                                   rays.shape[0], depth, seed, pixel_index, C.byref(mean)))
         return np.array(mean.tuple())
 
-    def stats(self, device: int = 0) -> Stats:
+    def stats(self, device: Optional[int] = None) -> Stats:
         s = Stats()
         _check(_ffi.core().rt_get_stats(self.device_scene(device), C.byref(s)))
         return s
 
-    def reset_stats(self, device: int = 0) -> None:
+    def reset_stats(self, device: Optional[int] = None) -> None:
         _check(_ffi.core().rt_reset_stats(self.device_scene(device)))
 
-    def set_counters(self, enabled: bool, device: int = 0) -> None:
+    def set_counters(self, enabled: bool, device: Optional[int] = None) -> None:
         _check(_ffi.core().rt_set_counters(self.device_scene(device), int(enabled)))
 
-    def set_kernel_timing(self, enabled: bool, device: int = 0) -> None:
+    def set_kernel_timing(self, enabled: bool, device: Optional[int] = None) -> None:
         _check(_ffi.core().rt_set_kernel_timing(self.device_scene(device), int(enabled)))
 
 
@@ -202,12 +216,23 @@ class GpuRenderer:
     """Drop-in for step_by_step::ThreadPoolRenderer (src/renderer/step_by_step.rs:37) implementing the
     Renderer trait (src/renderer/mod.rs:47-56)."""
 
-    def __init__(self, scene: Scene, thread_number: int = 0, depth: int = 50, device: int = 0, seed: int = 0):
+    def __init__(self, scene: Scene, thread_number: int = 0, depth: int = 50, device: int = 0, seed: int = 0,
+                 devices=None):
+        """devices: a list of device indices -> ONE renderer (one process, one handle) that shards every frame
+        over all of them by interleaved tiles; the frame is the single-device one, bit for bit"""
         self.scene = scene
         self.depth = depth
-        self.device = device
+        self.devices = list(devices) if devices else None
+        self.device = self.devices[0] if self.devices else device
+        scene._device = self.device
         self._h = C.c_void_p()
-        _check(_ffi.host().rth_renderer_new(scene._h, thread_number, depth, device, seed, C.byref(self._h)), host=True)
+        if self.devices and len(self.devices) > 1:
+            ids = (C.c_int * len(self.devices))(*self.devices)
+            _check(_ffi.host().rth_renderer_new_multi(scene._h, thread_number, depth, len(self.devices), ids, seed,
+                                                      C.byref(self._h)), host=True)
+        else:
+            _check(_ffi.host().rth_renderer_new(scene._h, thread_number, depth, self.device, seed, C.byref(self._h)),
+                   host=True)
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
@@ -240,7 +265,7 @@ class GpuRenderer:
         return buf
 
 
-def tonemap_rgba8(scene: Scene, frame: np.ndarray, device: int = 0) -> np.ndarray:
+def tonemap_rgba8(scene: Scene, frame: np.ndarray, device: Optional[int] = None) -> np.ndarray:
     """src/bin/main_raylib.rs:239-247 on the device."""
     frame = np.ascontiguousarray(frame, dtype=np.float64)
     n = frame.size // 3
@@ -248,6 +273,18 @@ def tonemap_rgba8(scene: Scene, frame: np.ndarray, device: int = 0) -> np.ndarra
     _check(_ffi.core().rt_tonemap_rgba8(scene.device_scene(device), frame.ctypes.data_as(C.c_void_p), n,
                                         out.ctypes.data_as(C.c_void_p)))
     return out.reshape(frame.shape[:-1] + (4,))
+
+
+def tonemap_last_frame(dev_scene, n_pixels_hint: int = 0) -> np.ndarray:
+    """rt_tonemap_rgba8_device: the frame the library holds on the device -> (n, 4) uint8 on the host; only the 4
+    bytes per pixel cross the bus"""
+    n = C.c_uint64(0)
+    ptr = C.c_void_p()
+    frame_ptr = C.c_void_p()
+    _check(_ffi.core().rt_render_device_frame(dev_scene, C.byref(frame_ptr), C.byref(n)))
+    out = np.empty((n.value, 4), np.uint8)
+    _check(_ffi.core().rt_tonemap_rgba8_device(dev_scene, C.byref(ptr), out.ctypes.data_as(C.c_void_p), C.byref(n)))
+    return out
 
 
 def save_png(path: str, rgba: np.ndarray) -> None:
@@ -310,7 +347,7 @@ def render_accumulated_samples(dev_scene) -> int:
 
 
 def render_device_result(dev_scene):
-    """(device pointer, n_float4) of the shard's tile-packed float4 accumulator."""
+    """(device pointer, n) of the shard's tile-packed accumulator: n x 4 doubles (sum r, g, b; samples)."""
     ptr, n = C.c_void_p(), C.c_uint64()
     _check(_ffi.core().rt_render_device_result(dev_scene, C.byref(ptr), C.byref(n)))
     return ptr.value, n.value
@@ -330,7 +367,7 @@ class DevicePointer:
     """Expose a raw device allocation to torch (torch.as_tensor(DevicePointer(...), device='cuda'))
     through __cuda_array_interface__, without copying."""
 
-    def __init__(self, ptr: int, shape, typestr: str = "<f4", owner=None):
+    def __init__(self, ptr: int, shape, typestr: str = "<f8", owner=None):
         self._owner = owner
         self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr,
                                          "version": 3, "strides": None}

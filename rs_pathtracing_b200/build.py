@@ -12,6 +12,7 @@ import os
 import shutil
 import subprocess
 import sys
+import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
@@ -19,8 +20,10 @@ CSRC = os.path.join(HERE, "csrc")
 CORE_SO = os.path.join(HERE, "librt_b200.so")
 HOST_SO = os.path.join(HERE, "librt_b200_host.so")
 
-CORE_SOURCES = [os.path.join(CSRC, "rt_core.cu")]
+CORE_SOURCES = [os.path.join(CSRC, f) for f in ("rt_core.cu", "rt_march_kernels.cu", "rt_march3.cu")]
+OBJ_DIR = os.path.join(HERE, "build")
 CORE_HEADERS = [
+    os.path.join(CSRC, "rt_queues.cuh"),
     os.path.join(CSRC, "rt_math.cuh"),
     os.path.join(CSRC, "rt_scene.cuh"),
     os.path.join(CSRC, "rt_march.cuh"),
@@ -44,8 +47,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math",
     "-Xptxas", "-v",
     "-diag-suppress", "20014",   # surface_func_t<Jet2> is a host-only instantiation of a __host__ __device__ template
-    "-shared", "-cudart", "static",
 ]
+NVCC_LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static"]
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-shared"]
 
 
@@ -74,10 +77,47 @@ def nvcc_path() -> str:
 
 
 def build_core(force: bool = False) -> str:
-    if force or _stale(CORE_SO, CORE_SOURCES + CORE_HEADERS + [os.path.abspath(__file__)]):
-        extra = os.environ.get("RT_B200_NVCC_EXTRA", "").split()   # tuning experiments, e.g. -DRT_MARCH_MIN_BLOCKS=5
-        _run([nvcc_path(), *NVCC_FLAGS, *extra, "-o", CORE_SO, *CORE_SOURCES], "build_core.log")
+    """one object per translation unit, compiled in parallel (no relocatable device code: every kernel is launched
+    from its own unit), then linked into librt_b200.so"""
+    deps = CORE_HEADERS + [os.path.abspath(__file__)]
+    extra = os.environ.get("RT_B200_NVCC_EXTRA", "").split()   # tuning experiments, e.g. -DRT_M3_R=64
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    objs, jobs = [], []
+    for src in CORE_SOURCES:
+        obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or extra or _stale(obj, [src] + deps):
+            log = "build_" + os.path.basename(src)[:-3] + ".log"
+            jobs.append((threading.Thread(target=_run_job, args=([nvcc_path(), *NVCC_FLAGS, *extra, "-c", "-o", obj, src], log)),
+                         obj))
+    errors = []
+    for t, _ in jobs:
+        t.start()
+    for t, obj in jobs:
+        t.join()
+    errors = [e for e in _JOB_ERRORS]
+    _JOB_ERRORS.clear()
+    if errors:
+        raise RuntimeError("build failed:\n" + "\n".join(errors))
+    if jobs or not os.path.exists(CORE_SO) or _stale(CORE_SO, objs):
+        _run([nvcc_path(), *NVCC_LINK_FLAGS, "-o", CORE_SO, *objs])
+        # one log with every unit's ptxas -v output (registers / spills), as before
+        with open(os.path.join(HERE, "build_core.log"), "w") as out:
+            for src in CORE_SOURCES:
+                lp = os.path.join(HERE, "build_" + os.path.basename(src)[:-3] + ".log")
+                if os.path.exists(lp):
+                    out.write(open(lp).read())
     return CORE_SO
+
+
+_JOB_ERRORS: list[str] = []
+
+
+def _run_job(cmd: list[str], log_name: str) -> None:
+    try:
+        _run(cmd, log_name)
+    except Exception as e:   # collected by build_core
+        _JOB_ERRORS.append(str(e))
 
 
 def build_host(force: bool = False) -> str:

@@ -82,6 +82,11 @@ int rth_scene_device(rth_scene* s, int device, rt_scene** out) {
     return guarded([&] { *out = s->scene->device_scene(device); });
 }
 
+int rth_scene_device_multi(rth_scene* s, int n_devices, const int* device_ids, rt_scene** out) {
+    if (!s || !out || !device_ids || n_devices < 1) { g_err = "null argument"; return RT_ERR_INVALID; }
+    return guarded([&] { *out = s->scene->device_scene(std::vector<int>(device_ids, device_ids + n_devices)); });
+}
+
 int rth_camera_new(rt_vec3 position, rt_vec3 direction, rt_vec3 up, double focal_length, double fov_rad,
                    rt_camera* out) {
     if (!out) { g_err = "null argument"; return RT_ERR_INVALID; }
@@ -100,6 +105,15 @@ int rth_renderer_new(rth_scene* s, uint32_t thread_number, uint32_t depth, int d
     if (!s || !out) { g_err = "null argument"; return RT_ERR_INVALID; }
     return guarded([&] {
         auto r = std::make_unique<renderer::GpuRenderer>(s->scene, thread_number, depth, device, seed);
+        *out = new rth_renderer{std::move(r)};
+    });
+}
+int rth_renderer_new_multi(rth_scene* s, uint32_t thread_number, uint32_t depth, int n_devices, const int* device_ids,
+                           uint64_t seed, rth_renderer** out) {
+    if (!s || !out || !device_ids || n_devices < 1) { g_err = "null argument"; return RT_ERR_INVALID; }
+    return guarded([&] {
+        auto r = std::make_unique<renderer::GpuRenderer>(s->scene, thread_number, depth,
+                                                         std::vector<int>(device_ids, device_ids + n_devices), seed);
         *out = new rth_renderer{std::move(r)};
     });
 }

@@ -543,11 +543,12 @@ std::shared_ptr<Scene> Scene::from_json(const std::string& data, uint64_t seed, 
 }
 
 Scene::~Scene() {
-    if (dev_) rt_scene_destroy(dev_);
+    for (auto& kv : dev_) rt_scene_destroy(kv.second);
+    for (auto& kv : multi_) rt_scene_destroy(kv.second);
 }
 
 void Scene::assign_material(uint32_t shape_index, const std::string& material_name) {
-    if (dev_) throw std::runtime_error("assign_material: the scene is already on the device");
+    if (!dev_.empty() || !multi_.empty()) throw std::runtime_error("assign_material: the scene is already on the device");
     if (shape_index >= flat_.material.size()) throw std::runtime_error("assign_material: bad shape index");
     for (size_t i = 0; i < flat_.material_names.size(); i++)
         if (flat_.material_names[i] == material_name) {
@@ -557,17 +558,30 @@ void Scene::assign_material(uint32_t shape_index, const std::string& material_na
     throw std::runtime_error("material `" + material_name + "` not found");
 }
 
+// One rt_scene per device, created on first use and kept until the Scene dies: a handle given out for one device
+// (GpuRenderer, DistributedRenderer, the Python helpers) stays valid when another device is asked for.
 rt_scene* Scene::device_scene(int device) {
-    if (dev_ && dev_id_ == device) return dev_;
-    if (dev_) {
-        rt_scene_destroy(dev_);
-        dev_ = nullptr;
-    }
+    auto it = dev_.find(device);
+    if (it != dev_.end()) return it->second;
     rt_scene_desc d = flat_.desc();
-    int rc = rt_scene_create(&d, device, &dev_);
+    rt_scene* h = nullptr;
+    int rc = rt_scene_create(&d, device, &h);
     if (rc != RT_OK) throw std::runtime_error(std::string("rt_scene_create: ") + rt_last_error());
-    dev_id_ = device;
-    return dev_;
+    dev_[device] = h;
+    return h;
+}
+
+rt_scene* Scene::device_scene(const std::vector<int>& devices) {
+    if (devices.empty()) throw std::runtime_error("device_scene: empty device list");
+    if (devices.size() == 1) return device_scene(devices[0]);
+    auto it = multi_.find(devices);
+    if (it != multi_.end()) return it->second;
+    rt_scene_desc d = flat_.desc();
+    rt_scene* h = nullptr;
+    int rc = rt_scene_create_multi(&d, (int)devices.size(), devices.data(), &h);
+    if (rc != RT_OK) throw std::runtime_error(std::string("rt_scene_create_multi: ") + rt_last_error());
+    multi_[devices] = h;
+    return h;
 }
 
 std::vector<RayHit> Scene::closest_hit(const std::vector<Ray>& rays, double min_t, double max_t, int mode,
@@ -608,6 +622,18 @@ GpuRenderer::GpuRenderer(std::shared_ptr<world::Scene> scene, uint32_t /*thread_
     scene_->device_scene(device_);  // upload now, like ThreadPoolRenderer::new spawning its workers
 }
 
+GpuRenderer::GpuRenderer(std::shared_ptr<world::Scene> scene, uint32_t /*thread_number*/, uint32_t depth,
+                         const std::vector<int>& devices, uint64_t seed)
+    : scene_(scene), depth_(depth), device_(devices.empty() ? 0 : devices[0]), devices_(devices), seed_(seed),
+      started_(false), pixels_(0) {
+    if (devices_.size() == 1) devices_.clear();
+    handle();
+}
+
+rt_scene* GpuRenderer::handle() const {
+    return devices_.empty() ? scene_->device_scene(device_) : scene_->device_scene(devices_);
+}
+
 void GpuRenderer::start_rendering(std::shared_ptr<camera::Camera> camera, const camera::ImageParams& img,
                                   uint32_t samples_number) {
     rt_render_params p;
@@ -618,7 +644,7 @@ void GpuRenderer::start_rendering(std::shared_ptr<camera::Camera> camera, const 
     p.seed = seed_;
     p.shard_count = 1;
     rt_camera c = camera->to_pod();
-    int rc = rt_render_start(scene_->device_scene(device_), &c, &p);
+    int rc = rt_render_start(handle(), &c, &p);
     if (rc != RT_OK) throw std::runtime_error(std::string("rt_render_start: ") + rt_last_error());
     started_ = true;
     pixels_ = (uint64_t)img.width * img.height;
@@ -632,14 +658,14 @@ bool GpuRenderer::render_step(Vector3d* buffer, size_t len) {
     // the reference indexes buffer[index] and panics when it is too short (step_by_step.rs:116)
     if (len < pixels_) throw std::runtime_error("render_step: buffer shorter than width*height");
     int done = 0;
-    int rc = rt_render_poll(scene_->device_scene(device_), (rt_vec3*)buffer, &done);
+    int rc = rt_render_poll(handle(), (rt_vec3*)buffer, &done);
     if (rc != RT_OK) throw std::runtime_error(std::string("rt_render_poll: ") + rt_last_error());
     if (done) started_ = false;
     return done != 0;
 }
 
 void GpuRenderer::stop_rendering() {
-    if (started_) rt_render_stop(scene_->device_scene(device_));
+    if (started_) rt_render_stop(handle());
     started_ = false;
 }
 

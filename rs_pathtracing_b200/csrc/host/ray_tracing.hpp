@@ -156,16 +156,18 @@ public:
     std::vector<RayHit> closest_hit(const std::vector<Ray>& rays, double min_t, double max_t,
                                     int mode = RT_ISECT_BRUTE, int device = 0);
 
-    // the device-resident copy (created on first use)
+    // the device-resident copy on `device` (created on first use, one per device, alive as long as the Scene)
     rt_scene* device_scene(int device = 0);
+    // ONE handle over several devices (rt_scene_create_multi): whole-frame renders are sharded over all of them
+    rt_scene* device_scene(const std::vector<int>& devices);
 
 private:
-    Scene() : dev_(nullptr), dev_id_(-1) {}
+    Scene() {}
     camera::Camera camera_;
     algebra::Vector3d background_;   // parsed, and ignored exactly like the reference (:199-202)
     FlatScene flat_;
-    rt_scene* dev_;
-    int dev_id_;
+    std::map<int, rt_scene*> dev_;
+    std::map<std::vector<int>, rt_scene*> multi_;
 };
 
 }  // namespace world
@@ -189,6 +191,10 @@ class GpuRenderer : public Renderer {
 public:
     GpuRenderer(std::shared_ptr<world::Scene> scene, uint32_t thread_number, uint32_t depth, int device = 0,
                 uint64_t seed = 0);
+    // the same renderer over SEVERAL devices of the box (one process, one handle: rt_scene_create_multi); the frame
+    // is the single-device one, bit for bit
+    GpuRenderer(std::shared_ptr<world::Scene> scene, uint32_t thread_number, uint32_t depth,
+                const std::vector<int>& devices, uint64_t seed = 0);
     void start_rendering(std::shared_ptr<camera::Camera> camera, const camera::ImageParams& img_params,
                          uint32_t samples_number) override;
     bool render_step(std::vector<algebra::Vector3d>& buffer) override;
@@ -196,9 +202,11 @@ public:
     void stop_rendering() override;
 
 private:
+    rt_scene* handle() const;
     std::shared_ptr<world::Scene> scene_;
     uint32_t depth_;
     int device_;
+    std::vector<int> devices_;   // empty: the single device `device_`
     uint64_t seed_;
     bool started_;
     uint64_t pixels_;

@@ -5,7 +5,7 @@
 //   k_raygen            MultisamplerRayCaster::next for a batch of pixels x samples
 //   k_bounce            one segment of ray_color for every live path: nearest hit, scatter / emit /
 //                       sky, survivors compacted into the next queue (ballot + popc + one atomic per warp)
-//   k_resolve           per-pixel mean (trace_pixel_samples) -> float4 accumulator + f64 frame
+//   k_resolve           per-pixel mean (trace_pixel_samples) -> (f64 sums, samples) accumulator + f64 frame
 //   k_assemble          multi-GPU: gathered tile-packed shards -> frame
 //   k_tonemap           the bins' sqrt / clamp / *256 -> RGBA8
 // Compile with -fmad=false (see rt_math.cuh).
@@ -19,7 +19,7 @@
 #include <vector>
 
 #include "march_bounds.hpp"
-#include "rt_scene.cuh"
+#include "rt_queues.cuh"
 
 using namespace rt;
 
@@ -37,15 +37,6 @@ static int fail(int code, const std::string& msg) {
         if (e_ != cudaSuccess)                                                                     \
             return fail(RT_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
     } while (0)
-
-// ------------------------------------------------------------------------------------------------
-// path state: structure of arrays in HBM, two queues (ping-pong per bounce)
-// ------------------------------------------------------------------------------------------------
-struct PathQueue {
-    double *ox, *oy, *oz, *dx, *dy, *dz;  // ray
-    double *bx, *by, *bz;                 // throughput (product of attenuations so far)
-    uint32_t* pid;                        // path id inside the batch = pixel_local * spp + sample
-};
 
 // Tiles are numbered row-major with tile row ty rotated by ty * skew positions (tile number k sits at column
 // (k % tiles_x + ty * skew) % tiles_x of row ty = k / tiles_x), and tile k belongs to shard k % shard_count.  The
@@ -121,36 +112,6 @@ __device__ __forceinline__ Staged stage_scene(const DevScene& S, bool use_smem) 
     for (int k = threadIdx.x; k < nf; k += blockDim.x) s_tab[n + k] = frec[k];
     __syncthreads();
     return Staged{true};
-}
-
-__device__ __forceinline__ void flush_counters(const DevCounters& c, DevCounters* g) {
-    // warp-reduce, one atomic per warp and counter
-    unsigned long long v[6] = {c.segments, c.shape_tests, c.cull_tests, c.march_steps, c.march_rays, c.march_long_rays};
-    unsigned long long mx = c.march_max_evals;
-    for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_down_sync(0xffffffffu, mx, o));
-#pragma unroll
-    for (int k = 0; k < 6; k++) {
-        unsigned long long x = v[k];
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        v[k] = x;
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomicAdd(&g->segments, v[0]);
-        atomicAdd(&g->shape_tests, v[1]);
-        atomicAdd(&g->cull_tests, v[2]);
-        atomicAdd(&g->march_steps, v[3]);
-        atomicAdd(&g->march_rays, v[4]);
-        atomicAdd(&g->march_long_rays, v[5]);
-        atomicMax(&g->march_max_evals, mx);
-    }
-    if (c.verify_rays) atomicAdd(&g->verify_rays, c.verify_rays);
-    if (c.verify_false_culls) atomicAdd(&g->verify_false_culls, c.verify_false_culls);
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-        unsigned long long x = c.march_prof[k];
-        for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
-        if ((threadIdx.x & 31) == 0 && x) atomicAdd(&g->march_prof[k], x);
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -364,24 +325,6 @@ k_bounce(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
 // busy and only QUEUES the rays whose bounding chord can still beat their best analytic hit; k_march
 // runs those rays densely packed; k_shade finalises the winner, scatters and compacts the survivors.
 
-struct HitQueue {
-    double* t;        // best t so far (max_t = +inf when nothing was hit)
-    int32_t* index;   // winning shape, -1 = none
-    uint32_t* mq_slot;  // march queue: path slot ...
-    uint32_t* mq_mask;  // ... and the marched shapes (bit k = S.march_index[k]) it still has to test
-    uint32_t* rq_slot;  // replay queue: degenerate rays (Sphere D == 0, NaN t) that must go through the literal loop
-    uint2* key;         // [path id] the path's RNG key (image pixel index, sample), written once by k_raygen /
-                        // k_load_rays: k_shade reads 8 B instead of redoing six integer divisions per segment
-};
-
-// per-level counters of one batch (zeroed by one memset): live paths, march / replay queue lengths and
-// the march kernels' queue heads (one per surface kind)
-#define RT_CNT_LIVE 0
-#define RT_CNT_MARCH (RT_MAX_LEVELS)
-#define RT_CNT_REPLAY (2 * RT_MAX_LEVELS)
-#define RT_CNT_HEAD (3 * RT_MAX_LEVELS)              // + kind * RT_MAX_LEVELS
-#define RT_CNT_WORDS (9 * RT_MAX_LEVELS)
-
 #ifndef RT_EXTEND_MIN_BLOCKS
 #define RT_EXTEND_MIN_BLOCKS 3
 #endif
@@ -433,503 +376,6 @@ k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
         }
         slot = queue_append(degenerate, replay_count);
         if (degenerate) hq.rq_slot[slot] = i;
-    }
-    if (COUNT) flush_counters(c, g_counters);
-}
-
-// a marched candidate came out NaN: the sequential loop is not an arg-min for this ray -> literal loop
-__device__ __noinline__ void replay_brute(const DevScene& S, const PathQueue& in, const HitQueue& hq, uint32_t i) {
-    D3 ro = mk(in.ox[i], in.oy[i], in.oz[i]);
-    D3 rd = mk(in.dx[i], in.dy[i], in.dz[i]);
-    double best;
-    int winner;
-    DevCounters cc = {};
-    nearest_hit_brute<false>(S, ro, rd, 0.001, INFINITY, best, winner, cc);
-    hq.t[i] = best;
-    hq.index[i] = winner;
-}
-
-// The exact advance of a jump (rt_march.cuh, advance_exact) for every jumping lane of the warp: 4 tasks
-// per lane (t, p.x, p.y, p.z), dealt out one per lane, so that the loops over binades -- whose trip
-// counts differ wildly between accumulators -- run with up to 32 lanes busy instead of one lane doing its
-// four advances in a row while the others wait.  Must be called by the whole warp (convergent).
-template <class CoWork>
-__device__ __forceinline__ void coop_advance(unsigned jumping, long long mj, double t, double step, D3 p, D3 sd,
-                                             double& nt, D3& np, unsigned char* s_owner, CoWork&& co_work) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int tasks = 4 * __popc(jumping);
-    const int my_rank = __popc(jumping & ((1u << lane) - 1u));
-    const int my_first = 4 * my_rank;  // task number of this lane's t
-    // the lane that owns task number k is the (k / 4)-th set bit of `jumping`: every jumping lane posts its
-    // number at its rank (s_owner: 32 bytes of shared memory private to the warp; __fns is a long software
-    // loop, stripping the lower bits one by one was 3.7 % of k_march's instructions)
-    __syncwarp();
-    if ((jumping >> lane) & 1u) s_owner[my_rank] = (unsigned char)lane;
-    __syncwarp();
-    double out[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int base = 0; base < tasks; base += 32) {
-        const int task = base + lane;
-        const bool active = task < tasks;
-        const int src = active ? (int)s_owner[task >> 2] : lane;
-        const int comp = task & 3;
-        const double a0 = __shfl_sync(FULL, t, src), a1 = __shfl_sync(FULL, p.x, src), a2 = __shfl_sync(FULL, p.y, src),
-                     a3 = __shfl_sync(FULL, p.z, src);
-        const double s0 = __shfl_sync(FULL, step, src), s1 = __shfl_sync(FULL, sd.x, src),
-                     s2 = __shfl_sync(FULL, sd.y, src), s3 = __shfl_sync(FULL, sd.z, src);
-        const long long mm = __shfl_sync(FULL, mj, src);
-        double res = comp == 0 ? a0 : comp == 1 ? a1 : comp == 2 ? a2 : a3;
-        const double s = comp == 0 ? s0 : comp == 1 ? s1 : comp == 2 ? s2 : s3;
-        long long left = active ? mm : 0;
-        // one binade (or one stretch of the near-zero walk) per trip; the lanes whose task is finished -- or
-        // that never had one -- do their co-work (literal steps of their own rays) instead of idling
-        while (__any_sync(FULL, left > 0)) {
-            if (left > 0) advance_iter(res, s, left);
-            co_work();
-        }
-#pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const int from = my_first + c - base;  // lane holding this lane's result number c in this round
-            const double v = __shfl_sync(FULL, res, from & 31);
-            if (from >= 0 && from < 32) out[c] = v;
-        }
-    }
-    nt = out[0];
-    np = mk(out[1], out[2], out[3]);
-}
-
-// K3: exact-skip marching of the queued (ray, marched shapes) entries, one surface kind per launch.
-// Per-ray cost is heavy-tailed (a grazing ray needs 50x the work of a typical one), so lanes are
-// persistent: a lane that finishes its entry takes the next one from the queue (warp-aggregated atomic on
-// `head`) while the other lanes of its warp keep marching.
-#ifndef RT_MARCH_MIN_BLOCKS
-#define RT_MARCH_MIN_BLOCKS 4
-#endif
-// tune.x: refill / start a shape when at least this many lanes of the warp are idle (or none is busy)
-// tune.y: run the attempt phase when this many lanes want it (or nobody can step)
-// tune.z: literal steps per literal phase
-#define RT_MARCH_REFILL_MIN tune.x
-#define RT_MARCH_ATTEMPT_MIN tune.y
-#define RT_MARCH_LITERAL_BURST tune.z
-template <int KIND, bool COUNT>
-__global__ void __launch_bounds__(128, RT_MARCH_MIN_BLOCKS)
-k_march(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32_t* __restrict__ march_count,
-        uint32_t* head, DevCounters* g_counters, int3 tune) {
-    DevCounters c = {};
-    const uint32_t n = *march_count;
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    __shared__ unsigned char s_owner_all[128];
-    unsigned char* const s_owner = s_owner_all + (threadIdx.x & ~31u);
-    bool have = false, marching = false, exhausted = false;
-    uint32_t slot = 0, mask = 0, entry = 0;
-    int shape = -1, winner = -1;
-    double best = 0.0;
-    Marcher<KIND, COUNT> m;
-    for (;;) {
-        // ---- refill ------------------------------------------------------------------------------
-        const unsigned idle = __ballot_sync(FULL, !have && !exhausted);
-        const unsigned busy = __ballot_sync(FULL, have);
-        if (idle && (busy == 0 || __popc(idle) >= RT_MARCH_REFILL_MIN)) {
-            uint32_t base = 0;
-            const int leader = __ffs(idle) - 1;
-            if (lane == leader) base = atomicAdd(head, (uint32_t)__popc(idle));
-            base = __shfl_sync(FULL, base, leader);
-            if (!have && !exhausted) {
-                const uint32_t j = base + __popc(idle & ((1u << lane) - 1u));
-                if (j < n) {
-                    entry = j;
-                    slot = hq.mq_slot[j];
-                    mask = hq.mq_mask[j] & kind_mask;
-                    best = hq.t[slot];
-                    winner = hq.index[slot];
-                    have = mask != 0;
-                    marching = false;
-                } else {
-                    exhausted = true;
-                }
-            }
-        }
-        if (__ballot_sync(FULL, have) == 0) {
-            if (__ballot_sync(FULL, !exhausted) == 0) break;
-            continue;
-        }
-        // ---- start the next marched shape of this lane's entry (batched like the refill) -------------
-        const unsigned need_start = __ballot_sync(FULL, have && !marching);
-        const unsigned marching_any = __ballot_sync(FULL, marching);
-        if (have && !marching && (marching_any == 0 || __popc(need_start) >= RT_MARCH_REFILL_MIN)) {
-            if (mask == 0) {
-                hq.t[slot] = best;
-                hq.index[slot] = winner;
-                have = false;
-            } else {
-                const int k = __ffs(mask) - 1;
-                mask &= mask - 1;
-                shape = S.march_index[k];
-                const double* q = S.params + RT_SHAPE_PARAMS * shape;
-                D3 ro = mk(in.ox[slot], in.oy[slot], in.oz[slot]);
-                D3 rd = mk(in.dx[slot], in.dy[slot], in.dz[slot]);
-                D3 o, d;
-                double start, end_c;
-                if (march_needed(S, S.inv + 12 * shape, q, ro, rd, best, o, d, start, end_c)) {
-                    m.begin(q, o, d, start, end_c, S.march_G[k], S.march_F[k]);
-                    marching = true;
-                    if (COUNT) c.march_rays++;
-                }
-            }
-        }
-        // ---- marching: the warp votes between the expensive exact-jump attempt and the cheap literal
-        //      steps, so that attempts run with many lanes at once ---------------------------------------
-        int ph = marching ? m.phase() : -1;
-        if (ph == RT_PHASE_END) {
-            marching = false;
-            if (COUNT) {
-                c.march_steps += m.n;
-                for (int k = 0; k < 4; k++) c.march_prof[k] += m.prof[k];
-                if (m.n > 2048) c.march_long_rays++;
-                if (m.n > c.march_max_evals) c.march_max_evals = m.n;
-            }
-            if (m.finish() == RT_MARCH_DONE && !(m.t < 0.001)) {  // ray_marching.rs:55 with max_t = +inf
-                const double t = m.t;
-                if (t != t) {  // NaN candidate: replay now, and hide the entry from later kind passes
-                    replay_brute(S, in, hq, slot);
-                    hq.mq_mask[entry] = 0;
-                    have = false;
-                } else if (t < best || (t == best && shape > winner)) {
-                    best = t;
-                    winner = shape;
-                }
-            }
-        }
-        const unsigned want_attempt = __ballot_sync(FULL, ph == RT_PHASE_ATTEMPT);
-        const unsigned want_literal = __ballot_sync(FULL, ph == RT_PHASE_LITERAL);
-        if (want_attempt && (want_literal == 0 || __popc(want_attempt) >= RT_MARCH_ATTEMPT_MIN)) {
-            // (Letting the literal-phase lanes take steps inside the attempt's loops -- coop_advance's co_work
-            // hook -- was measured: the longer loop bodies cost more than the idle lanes, 4.1 -> 4.65 ms.)
-            typename Marcher<KIND, COUNT>::Plan pl;
-            long long mj = 0;
-            if (ph == RT_PHASE_ATTEMPT) mj = m.attempt_plan(pl);
-            const unsigned jumping = __ballot_sync(FULL, mj > 0);
-            if (jumping) {
-                double nt = 0.0;
-                D3 np = mk(0.0, 0.0, 0.0);
-                coop_advance(jumping, mj, m.t, m.step, m.p, m.sd, nt, np, s_owner, []() {});
-                if (mj > 0) m.attempt_land(pl, nt, np);
-            }
-        } else if (want_literal) {
-            if (ph == RT_PHASE_LITERAL) {
-#pragma unroll 1
-                for (int rep = 0; rep < RT_MARCH_LITERAL_BURST; rep++) {
-                    m.literal();
-                    if (m.phase() != RT_PHASE_LITERAL) break;
-                }
-            }
-        }
-    }
-    if (COUNT) flush_counters(c, g_counters);
-}
-
-// K3, experimental alternative (RT_B200_MARCH_V2=1): the same marching as a block-local wavefront.
-// Measured 27 % SLOWER than k_march on cornell_box (5.4 vs 4.3 ms per 4 Mi paths): the divergence that
-// matters is inside the phases (trip counts of advance_exact and of the hop loop), not between them.
-// k_march keeps one ray per lane; its lanes sit in different phases of their rays (start / exact-jump
-// attempt / literal steps / finish) and a warp executes the union of those instruction streams: ~10 of 32
-// lanes busy, 5.7x slower than a warp marching 32 copies of ONE ray (tools/march_coherence_probe.py).
-// k_march2 keeps the rays of a block in RECORDS instead (256 B each, in the block's slice of a global
-// buffer that stays L2-resident), RT_M2_SLOTS of them for RT_M2_THREADS threads, and runs the phases one
-// after the other over compacted lists of the records that want them, so that every warp executes one
-// phase with (nearly) all lanes busy.  The arithmetic per ray -- Marcher, rt_march.cuh -- is unchanged, so
-// the result is bit-identical to k_march and to the reference's loop.
-#define RT_M2_THREADS 256
-#define RT_M2_SLOTS 1024
-#define RT_M2_LITERAL_BURST 8
-struct __align__(16) MarchRec {
-    // [0] t [1] r [2] step [3..5] p [6..8] d [9] start [10] end [11] best so far
-    // [12..18] P.c [19] P.t0 [20..22] P.p0 [23] P.tau_hi [24] P.err0 [25] P.drift1
-    // [26] (it | cooldown << 8 | backoff << 16 | flags << 24, n)   [27] (path slot, queue entry)
-    // [28] (remaining shape mask, winner)   [29] (march-list index k or -1, shape index)
-    // [30] [31] work-profile counters (COUNT only)
-    double v[32];
-};
-enum { RT_M2_FREE = 0, RT_M2_TRANS = 1, RT_M2_ATTEMPT = 2, RT_M2_LITERAL = 3 };
-#define RT_M2_FLAG_SKIP_OK 1u
-#define RT_M2_FLAG_HAVE_POLY 2u
-
-__device__ __forceinline__ uint2 m2_get_u2(const MarchRec* rec, int i) {
-    return *reinterpret_cast<const uint2*>(&rec->v[i]);
-}
-__device__ __forceinline__ void m2_set_u2(MarchRec* rec, int i, uint32_t x, uint32_t y) {
-    *reinterpret_cast<uint2*>(&rec->v[i]) = make_uint2(x, y);
-}
-
-// the marcher's loop state (everything literal() and phase() touch)
-template <int KIND, bool COUNT>
-__device__ __forceinline__ void m2_load_core(const DevScene& S, const MarchRec* rec, Marcher<KIND, COUNT>& m, int& k) {
-    const double2* r2 = reinterpret_cast<const double2*>(rec->v);
-    const double2 a0 = r2[0], a1 = r2[1], a2 = r2[2], a3 = r2[3], a4 = r2[4], a5 = r2[5];
-    m.t = a0.x; m.r = a0.y; m.step = a1.x; m.p = mk(a1.y, a2.x, a2.y);
-    m.d = mk(a3.x, a3.y, a4.x); m.start = a4.y; m.end = a5.x;
-    const uint2 w = m2_get_u2(rec, 26), ks = m2_get_u2(rec, 29);
-    m.it = (int)(w.x & 0xffu);
-    m.cooldown = (int)((w.x >> 8) & 0xffu);
-    m.backoff = (int)((w.x >> 16) & 0xffu);
-    m.skip_ok = ((w.x >> 24) & RT_M2_FLAG_SKIP_OK) != 0;
-    m.have_poly = ((w.x >> 24) & RT_M2_FLAG_HAVE_POLY) != 0;
-    m.n = w.y;
-    k = (int)ks.x;
-    m.q = S.params + RT_SHAPE_PARAMS * (int)ks.y;
-    m.step0 = m.q[1];
-    m.depth = (int)m.q[2];
-    m.G = S.march_G[k];
-    m.F = S.march_F[k];
-    m.sd = m.step * m.d;
-    if (COUNT) {
-        const uint2 p0 = m2_get_u2(rec, 30), p1 = m2_get_u2(rec, 31);
-        m.prof[0] = p0.x; m.prof[1] = p0.y; m.prof[2] = p1.x; m.prof[3] = p1.y;
-    }
-}
-template <int KIND, bool COUNT>
-__device__ __forceinline__ void m2_store_core(MarchRec* rec, const Marcher<KIND, COUNT>& m, bool with_ray) {
-    double2* r2 = reinterpret_cast<double2*>(rec->v);
-    r2[0] = make_double2(m.t, m.r);
-    r2[1] = make_double2(m.step, m.p.x);
-    r2[2] = make_double2(m.p.y, m.p.z);
-    if (with_ray) {
-        r2[3] = make_double2(m.d.x, m.d.y);
-        r2[4] = make_double2(m.d.z, m.start);
-        rec->v[10] = m.end;
-    }
-    const uint32_t flags = (m.skip_ok ? RT_M2_FLAG_SKIP_OK : 0u) | (m.have_poly ? RT_M2_FLAG_HAVE_POLY : 0u);
-    const uint32_t nn = m.n > 0xffffffffull ? 0xffffffffu : (uint32_t)m.n;
-    m2_set_u2(rec, 26, (uint32_t)m.it | ((uint32_t)m.cooldown << 8) | ((uint32_t)m.backoff << 16) | (flags << 24), nn);
-    if (COUNT) {
-        m2_set_u2(rec, 30, m.prof[0], m.prof[1]);
-        m2_set_u2(rec, 31, m.prof[2], m.prof[3]);
-    }
-}
-template <int KIND, bool COUNT>
-__device__ __forceinline__ void m2_load_poly(const MarchRec* rec, Marcher<KIND, COUNT>& m) {
-    constexpr int DEG = Marcher<KIND, COUNT>::DEG;
-    const double2* r2 = reinterpret_cast<const double2*>(rec->v);
-    double c[8];
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const double2 v = r2[6 + i];
-        c[2 * i] = v.x;
-        c[2 * i + 1] = v.y;
-    }
-#pragma unroll
-    for (int i = 0; i <= DEG; i++) m.P.c[i] = c[i];
-    m.P.t0 = c[7];
-    const double2 b0 = r2[10], b1 = r2[11], b2 = r2[12];
-    m.P.p0 = mk(b0.x, b0.y, b1.x);
-    m.P.tau_hi = b1.y; m.P.err0 = b2.x; m.P.drift1 = b2.y;
-}
-template <int KIND, bool COUNT>
-__device__ __forceinline__ void m2_store_poly(MarchRec* rec, const Marcher<KIND, COUNT>& m) {
-    constexpr int DEG = Marcher<KIND, COUNT>::DEG;
-    double c[8];
-#pragma unroll
-    for (int i = 0; i < 7; i++) c[i] = i <= DEG ? m.P.c[i] : 0.0;
-    c[7] = m.P.t0;
-    double2* r2 = reinterpret_cast<double2*>(rec->v);
-#pragma unroll
-    for (int i = 0; i < 4; i++) r2[6 + i] = make_double2(c[2 * i], c[2 * i + 1]);
-    r2[10] = make_double2(m.P.p0.x, m.P.p0.y);
-    r2[11] = make_double2(m.P.p0.z, m.P.tau_hi);
-    r2[12] = make_double2(m.P.err0, m.P.drift1);
-}
-__device__ __forceinline__ uint8_t m2_phase_of(int ph) {
-    return ph == RT_PHASE_ATTEMPT ? RT_M2_ATTEMPT : ph == RT_PHASE_LITERAL ? RT_M2_LITERAL : RT_M2_TRANS;
-}
-
-template <int KIND, bool COUNT>
-__global__ void __launch_bounds__(RT_M2_THREADS, 2)
-k_march2(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32_t* __restrict__ march_count,
-         uint32_t* head, MarchRec* state_all, DevCounters* g_counters) {
-    __shared__ uint8_t s_phase[RT_M2_SLOTS];
-    __shared__ uint16_t s_list[4][RT_M2_SLOTS];   // [RT_M2_FREE] = free slots
-    __shared__ uint32_t s_len[4];
-    __shared__ uint32_t s_base, s_take, s_next;
-    __shared__ int s_exhausted;
-    __shared__ unsigned char s_owner_all[RT_M2_THREADS];
-    unsigned char* const s_owner = s_owner_all + (threadIdx.x & ~31u);
-    DevCounters c = {};
-    MarchRec* state = state_all + (size_t)blockIdx.x * RT_M2_SLOTS;
-    const uint32_t n = *march_count;
-    const int tid = threadIdx.x;
-    // records this block works with: an even share of the queue, so that every SM gets work
-    uint32_t cap = (n + gridDim.x - 1) / gridDim.x;
-    cap = (cap + 31u) & ~31u;
-    cap = min((uint32_t)RT_M2_SLOTS, max((uint32_t)RT_M2_THREADS, cap));
-    for (uint32_t i = tid; i < cap; i += RT_M2_THREADS) s_phase[i] = RT_M2_FREE;
-    if (tid == 0) s_exhausted = n == 0;
-    __syncthreads();
-    for (;;) {
-        // ---- classify the records by the phase they want next -------------------------------------------
-        if (tid < 4) s_len[tid] = 0;
-        if (tid == 4) s_next = 0;
-        __syncthreads();
-        for (uint32_t i = tid; i < cap; i += RT_M2_THREADS) {
-            const int ph = s_phase[i];
-            s_list[ph][atomicAdd(&s_len[ph], 1u)] = (uint16_t)i;
-        }
-        __syncthreads();
-        const uint32_t n_free = s_len[RT_M2_FREE];
-        const uint32_t live = cap - n_free;
-        // ---- refill the free records from the march queue ------------------------------------------------
-        uint32_t take = 0;
-        if (!s_exhausted && n_free > 0 && (live == 0 || 4 * n_free >= cap)) {  // (block-uniform condition)
-            if (tid == 0) {
-                const uint32_t base = atomicAdd(head, n_free);
-                s_base = base;
-                s_take = base < n ? min(n_free, n - base) : 0u;
-                if (base + n_free >= n) s_exhausted = 1;
-            }
-            __syncthreads();
-            take = s_take;
-            for (uint32_t i = tid; i < take; i += RT_M2_THREADS) {
-                const uint32_t slot = s_list[RT_M2_FREE][i];
-                const uint32_t j = s_base + i;
-                const uint32_t pslot = hq.mq_slot[j];
-                MarchRec* rec = state + slot;
-                rec->v[11] = hq.t[pslot];
-                m2_set_u2(rec, 27, pslot, j);
-                m2_set_u2(rec, 28, hq.mq_mask[j] & kind_mask, (uint32_t)hq.index[pslot]);
-                m2_set_u2(rec, 29, 0xffffffffu, 0u);
-                s_phase[slot] = RT_M2_TRANS;
-                s_list[RT_M2_TRANS][atomicAdd(&s_len[RT_M2_TRANS], 1u)] = (uint16_t)slot;
-            }
-            __syncthreads();
-        }
-        if (live + take == 0 && s_exhausted) break;
-        // ---- one pass over the three lists, 32 records at a time; warps take chunks dynamically so that
-        //      different warps run different phases at the same time (attempts, the longest, first) ---------
-        const uint32_t n_att = s_len[RT_M2_ATTEMPT], n_lit = s_len[RT_M2_LITERAL], n_trans = s_len[RT_M2_TRANS];
-        const uint32_t c_att = (n_att + 31u) >> 5, c_lit = (n_lit + 31u) >> 5, c_trans = (n_trans + 31u) >> 5;
-        const uint32_t n_chunks = c_att + c_lit + c_trans;
-        for (;;) {
-            uint32_t chunk = 0;
-            if ((tid & 31) == 0) chunk = atomicAdd(&s_next, 1u);
-            chunk = __shfl_sync(0xffffffffu, chunk, 0);
-            if (chunk >= n_chunks) break;
-            if (chunk < c_att) {
-                // ---- exact-jump attempt (the whole warp takes part: coop_advance is warp-collective) --------
-                const uint32_t idx = chunk * 32u + (tid & 31);
-                const bool active = idx < n_att;
-                const uint32_t slot = active ? s_list[RT_M2_ATTEMPT][idx] : 0u;
-                MarchRec* rec = state + slot;
-                Marcher<KIND, COUNT> m;
-                typename Marcher<KIND, COUNT>::Plan pl;
-                long long mj = 0;
-                bool had_poly = true;
-                if (active) {
-                    int k;
-                    m2_load_core(S, rec, m, k);
-                    had_poly = m.have_poly;
-                    if (had_poly) m2_load_poly(rec, m);
-                    mj = m.attempt_plan(pl);
-                } else {
-                    m.t = m.step = 0.0;
-                    m.p = m.sd = mk(0.0, 0.0, 0.0);
-                }
-                const unsigned jumping = __ballot_sync(0xffffffffu, mj > 0);
-                if (jumping) {
-                    double nt = 0.0;
-                    D3 np = mk(0.0, 0.0, 0.0);
-                    coop_advance(jumping, mj, m.t, m.step, m.p, m.sd, nt, np, s_owner, []() {});
-                    if (mj > 0) m.attempt_land(pl, nt, np);
-                }
-                if (active) {
-                    m2_store_core(rec, m, false);
-                    if (!had_poly) m2_store_poly(rec, m);
-                    s_phase[slot] = m2_phase_of(m.phase());
-                }
-            } else if (chunk < c_att + c_lit) {
-                // ---- the reference's literal steps -----------------------------------------------------------
-                const uint32_t idx = (chunk - c_att) * 32u + (tid & 31);
-                if (idx < n_lit) {
-                    const uint32_t slot = s_list[RT_M2_LITERAL][idx];
-                    MarchRec* rec = state + slot;
-                    Marcher<KIND, COUNT> m;
-                    int k;
-                    m2_load_core(S, rec, m, k);
-#pragma unroll 1
-                    for (int rep = 0; rep < RT_M2_LITERAL_BURST; rep++) {
-                        m.literal();
-                        if (m.phase() != RT_PHASE_LITERAL) break;
-                    }
-                    m2_store_core(rec, m, false);
-                    s_phase[slot] = m2_phase_of(m.phase());
-                }
-            } else {
-                // ---- transition: finish a marched shape, start the next one, or retire the record -----------
-                const uint32_t idx = (chunk - c_att - c_lit) * 32u + (tid & 31);
-                if (idx < n_trans) {
-                    const uint32_t slot = s_list[RT_M2_TRANS][idx];
-                    MarchRec* rec = state + slot;
-                    const uint2 pe = m2_get_u2(rec, 27), mw = m2_get_u2(rec, 28), ks = m2_get_u2(rec, 29);
-                    const uint32_t pslot = pe.x, entry = pe.y;
-                    uint32_t mask = mw.x;
-                    int winner = (int)mw.y;
-                    double best = rec->v[11];
-                    bool retired = false;
-                    Marcher<KIND, COUNT> m;
-                    if (ks.x != 0xffffffffu) {  // a shape has just been marched to its end
-                        int k;
-                        m2_load_core(S, rec, m, k);
-                        const int shape = (int)ks.y;
-                        if (COUNT) {
-                            c.march_steps += m.n;
-                            for (int q = 0; q < 4; q++) c.march_prof[q] += m.prof[q];
-                            if (m.n > 2048) c.march_long_rays++;
-                            if (m.n > c.march_max_evals) c.march_max_evals = m.n;
-                        }
-                        if (m.finish() == RT_MARCH_DONE && !(m.t < 0.001)) {  // ray_marching.rs:55 with max_t = +inf
-                            const double t = m.t;
-                            if (t != t) {  // NaN candidate: replay now, and hide the entry from later kind passes
-                                replay_brute(S, in, hq, pslot);
-                                hq.mq_mask[entry] = 0;
-                                retired = true;
-                            } else if (t < best || (t == best && shape > winner)) {
-                                best = t;
-                                winner = shape;
-                            }
-                        }
-                    }
-                    bool started = false;
-                    while (!retired && mask != 0 && !started) {
-                        const int k = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const int shape = S.march_index[k];
-                        const double* q = S.params + RT_SHAPE_PARAMS * shape;
-                        D3 ro = mk(in.ox[pslot], in.oy[pslot], in.oz[pslot]);
-                        D3 rd = mk(in.dx[pslot], in.dy[pslot], in.dz[pslot]);
-                        D3 o, d;
-                        double start, end_c;
-                        if (march_needed(S, S.inv + 12 * shape, q, ro, rd, best, o, d, start, end_c)) {
-                            m.begin(q, o, d, start, end_c, S.march_G[k], S.march_F[k]);
-                            if (COUNT) c.march_rays++;
-                            m2_store_core(rec, m, true);
-                            m2_set_u2(rec, 29, (uint32_t)k, (uint32_t)shape);
-                            s_phase[slot] = m2_phase_of(m.phase());
-                            started = true;
-                        }
-                    }
-                    if (started) {
-                        rec->v[11] = best;
-                        m2_set_u2(rec, 28, mask, (uint32_t)winner);
-                    } else {
-                        if (!retired) {
-                            hq.t[pslot] = best;
-                            hq.index[pslot] = winner;
-                        }
-                        s_phase[slot] = RT_M2_FREE;
-                    }
-                }
-            }
-        }
-        __syncthreads();
     }
     if (COUNT) flush_counters(c, g_counters);
 }
@@ -1018,32 +464,36 @@ k_shade(DevScene S, PathQueue in, const uint32_t* __restrict__ count_in, HitQueu
 }
 
 // K5: per-pixel mean of the batch (trace_pixel_samples, src/renderer/mod.rs:151-155).  One thread
-// per owned pixel; the float4 accumulator keeps (sum rgb, samples) for the NCCL path, the frame
-// buffer the f64 mean for the host path.
+// per owned pixel; the accumulator keeps (sum rgb, samples) as four doubles for the multi-GPU exchange and the
+// progressive accumulation -- the f64 sums themselves, so that an assembled or accumulated frame is the very
+// mean the unsharded single frame holds -- the frame buffer the f64 mean for the host path.
+struct __align__(16) Acc {
+    double r, g, b, n;
+};
 __global__ void __launch_bounds__(256)
 k_resolve(const float4* __restrict__ radiance, uint32_t n_pixels, uint32_t spp, unsigned long long first_owned,
-          float4* __restrict__ accum, rt_vec3* __restrict__ frame_owned, bool add) {
+          Acc* __restrict__ accum, rt_vec3* __restrict__ frame_owned, bool add) {
     uint32_t pl = blockIdx.x * blockDim.x + threadIdx.x;
     if (pl >= n_pixels) return;
     const float4* r = radiance + (size_t)pl * spp;
-    double sx = 0.0, sy = 0.0, sz = 0.0;
+    double sx = 0.0, sy = 0.0, sz = 0.0, ln = (double)spp;
+    if (add) {  // progressive accumulation: continue the earlier frames' sums, sample by sample (k frames of n
+                // samples then hold the very sum one frame of k*n samples computes)
+        const Acc prev = accum[first_owned + pl];
+        sx = prev.r; sy = prev.g; sz = prev.b;
+        ln += prev.n;
+    }
     for (uint32_t s = 0; s < spp; s++) {
         float4 v = r[s];
         sx += (double)v.x; sy += (double)v.y; sz += (double)v.z;
     }
-    double ln = (double)spp;
-    if (add) {  // progressive accumulation: the sums and the sample count of the earlier frames
-        const float4 prev = accum[first_owned + pl];
-        sx += (double)prev.x; sy += (double)prev.y; sz += (double)prev.z;
-        ln += (double)prev.w;
-    }
-    accum[first_owned + pl] = make_float4((float)sx, (float)sy, (float)sz, (float)ln);
+    accum[first_owned + pl] = Acc{sx, sy, sz, ln};
     frame_owned[first_owned + pl] = rt_vec3{sx / ln, sy / ln, sz / ln};
 }
 
 // K7: de-interleave gathered shards into the frame (x + y*w, f64 linear mean)
 struct ShardPtrs {
-    const float4* p[16];
+    const Acc* p[16];
 };
 __global__ void __launch_bounds__(256)
 k_assemble(ShardPtrs shards, ShardMap map0, rt_vec3* __restrict__ frame) {
@@ -1054,9 +504,8 @@ k_assemble(ShardPtrs shards, ShardMap map0, rt_vec3* __restrict__ frame) {
     uint32_t k = ty * map0.tiles_x + (tx + map0.tiles_x - rot) % map0.tiles_x;
     uint32_t s = k % map0.shard_count, j = k / map0.shard_count;
     size_t q = (size_t)j * map0.tile_pixels() + (size_t)(y % map0.tile_h) * map0.tile_w + (x % map0.tile_w);
-    float4 v = shards.p[s][q];
-    double w = (double)v.w;
-    frame[(size_t)y * map0.width + x] = rt_vec3{(double)v.x / w, (double)v.y / w, (double)v.z / w};
+    const Acc v = shards.p[s][q];
+    frame[(size_t)y * map0.width + x] = rt_vec3{v.r / v.n, v.g / v.n, v.b / v.n};
 }
 
 // src/bin/main_raylib.rs:239-247
@@ -1106,7 +555,6 @@ __global__ void __launch_bounds__(256) k_fma_peak(T* out, int iters, T a, T b) {
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-#define RT_MAX_LEVELS 64  // counters per batch: level 0 .. max_depth + 1
 
 enum { RT_KCLASS_RAYGEN = 0, RT_KCLASS_EXTEND, RT_KCLASS_MARCH, RT_KCLASS_SHADE, RT_KCLASS_RESOLVE, RT_KCLASS_COUNT };
 
@@ -1127,7 +575,7 @@ struct PathLane {
     HitQueue hq{};
     float4* d_radiance = nullptr;
     uint32_t* d_counts = nullptr;
-    MarchRec* d_march_state = nullptr;
+    void* d_march_state = nullptr;
     std::vector<void*> qallocs;
     uint64_t path_capacity = 0;
 };
@@ -1172,14 +620,16 @@ struct rt_scene {
     uint32_t* d_counts = nullptr;  // RT_CNT_WORDS per batch (reset per batch), see RT_CNT_*
     int grid_extend = 0, grid_march = 0, grid_shade = 0;
     uint32_t kind_mask[6] = {0, 0, 0, 0, 0, 0};  // marched shapes (bits of the march-queue mask) per surface kind
-    MarchRec* d_march_state = nullptr;           // k_march2: RT_M2_SLOTS records per block
-    int grid_march2 = 0;
+    void* d_march_state = nullptr;               // k_march2: its records (rt_march_kernels.cu)
+    int grid_march2 = 0, grid_march3 = 0;
+    size_t smem_march3 = 0;
     bool defer_bound = false;                    // k_extend queues every ray whose line touches a marching bound's ball; k_march sorts out the rest (RT_B200_DEFER_BOUND=1)
-    bool march_v1 = true;                        // false (RT_B200_MARCH_V2=1): the block-local wavefront k_march2 instead of k_march
+    int march_version = 3;                       // 3: pooled rays per warp (k_march3, rt_march3.cu); RT_B200_MARCH=1: one ray per lane
+                                                 // (k_march); =2: block-local wavefront (k_march2, experiment)
     int3 march_tune = make_int3(8, 8, 8);        // k_march scheduling thresholds (RT_B200_MARCH_TUNE=a,b,c)
     int march_grid_scale = 100;                  // percent of the occupancy grid
     bool wavefront = true;         // extend/march/shade; false = fused k_bounce (more than 32 marched shapes)
-    float4* d_accum = nullptr;
+    Acc* d_accum = nullptr;        // owned order: (sum r, g, b, samples)
     rt_vec3* d_frame = nullptr;    // owned order
     uint64_t frame_capacity = 0;
     // progressive accumulation (rt_render_set_accumulate): samples already in d_accum and the frame they belong to
@@ -1194,7 +644,25 @@ struct rt_scene {
     std::vector<Batch> batches;
     size_t delivered = 0;          // batches already copied to the caller
     cudaEvent_t ev_frame_start = nullptr, ev_frame_stop = nullptr;
-    std::vector<rt_vec3> host_stage;  // sharded poll: owned-order staging
+    rt_vec3* host_stage = nullptr;    // sharded poll: owned-order staging, pinned
+    uint64_t host_stage_cap = 0;
+    // frame post-process on the device (rt_tonemap_rgba8[_device]): persistent buffers, grown on demand
+    rt_vec3* d_tone_in = nullptr;
+    uchar4* d_tone_out = nullptr;
+    uint64_t tone_in_cap = 0, tone_out_cap = 0;
+    // several devices behind one handle (rt_scene_create_multi): this is the handle of device_ids[0]; `peers` are
+    // complete handles for the other devices.  A whole-frame rt_render_start shards the frame over all of them
+    // by interleaved tiles, every shard's accumulator comes to this device by one peer copy, k_assemble builds
+    // d_full_frame.
+    std::vector<rt_scene*> peers;
+    std::vector<Acc*> d_peer_acc;         // [peers.size()] staging for the peers' accumulators, on this device
+    std::vector<uint64_t> peer_acc_cap;
+    std::vector<cudaEvent_t> ev_peer;     // peer k's accumulator has arrived
+    rt_vec3* d_full_frame = nullptr;      // x + y*w, f64 mean
+    uint64_t full_frame_cap = 0;
+    cudaEvent_t ev_multi_done = nullptr;
+    bool multi_active = false;            // the frame in flight / last completed was rendered by all devices
+    rt_render_params multi_rp{};
 };
 
 template <class T>
@@ -1406,10 +874,15 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
         if (sscanf(tv, "%d,%d,%d,%d", &a, &b, &c2, &g) >= 3) sc->march_tune = make_int3(std::max(a, 1), std::max(b, 1), std::max(c2, 1));
         if (g > 0) sc->march_grid_scale = g;
     }
-    sc->grid_march = occ_grid(k_march<RT_SURF_HEART, false>, 128, 0) * sc->march_grid_scale / 100;
-    if (sc->grid_march < 1) sc->grid_march = 1;
-    sc->grid_march2 = occ_grid(k_march2<RT_SURF_HEART, false>, RT_M2_THREADS, 0);
-    sc->march_v1 = getenv("RT_B200_MARCH_V2") == nullptr;
+    {
+        int per_sm[3] = {1, 1, 1};
+        rt_march_occupancy(per_sm, &sc->smem_march3);
+        sc->grid_march = std::max(sc->n_sm * per_sm[0] * sc->march_grid_scale / 100, 1);
+        sc->grid_march2 = sc->n_sm * per_sm[1];
+        sc->grid_march3 = std::max(sc->n_sm * per_sm[2] * sc->march_grid_scale / 100, 1);
+    }
+    if (const char* mv = getenv("RT_B200_MARCH")) sc->march_version = std::min(std::max(atoi(mv), 1), 3);
+    if (getenv("RT_B200_MARCH_V2")) sc->march_version = 2;
     if (const char* db = getenv("RT_B200_DEFER_BOUND")) sc->defer_bound = atoi(db) != 0;
     sc->grid_shade = occ_grid(k_shade<false>, 256, 0);
     sc->wavefront = sc->ds.n_march <= 32 && !getenv("RT_B200_FUSED_BOUNCE");
@@ -1421,6 +894,54 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
     *out = sc;
     return RT_OK;
 }
+
+int rt_scene_create_multi(const rt_scene_desc* d, int n_devices, const int* device_ids, rt_scene** out) {
+    if (!out) return fail(RT_ERR_INVALID, "null out pointer");
+    *out = nullptr;
+    if (n_devices < 1 || !device_ids) return fail(RT_ERR_INVALID, "no devices");
+    if (n_devices > 16) return fail(RT_ERR_INVALID, "at most 16 devices");
+    for (int a = 0; a < n_devices; a++)
+        for (int b = a + 1; b < n_devices; b++)
+            if (device_ids[a] == device_ids[b]) return fail(RT_ERR_INVALID, "a device is listed twice");
+    rt_scene* sc = nullptr;
+    int rc = rt_scene_create(d, device_ids[0], &sc);
+    if (rc != RT_OK) return rc;
+    for (int k = 1; k < n_devices; k++) {
+        rt_scene* peer = nullptr;
+        rc = rt_scene_create(d, device_ids[k], &peer);
+        if (rc != RT_OK) {
+            rt_scene_destroy(sc);
+            return rc;
+        }
+        sc->peers.push_back(peer);
+        sc->d_peer_acc.push_back(nullptr);
+        sc->peer_acc_cap.push_back(0);
+        // direct NVLink path for the accumulator copies where the topology has one (cudaMemcpyPeerAsync stages
+        // through the host otherwise); "already enabled" is fine
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, device_ids[0], device_ids[k]) == cudaSuccess && can) {
+            cudaSetDevice(device_ids[0]);
+            cudaDeviceEnablePeerAccess(device_ids[k], 0);
+        }
+        if (cudaDeviceCanAccessPeer(&can, device_ids[k], device_ids[0]) == cudaSuccess && can) {
+            cudaSetDevice(device_ids[k]);
+            cudaDeviceEnablePeerAccess(device_ids[0], 0);
+        }
+        cudaGetLastError();
+        cudaSetDevice(device_ids[k]);   // the event is recorded on the peer's stream
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) {
+            rt_scene_destroy(sc);
+            return fail(RT_ERR_CUDA, "cudaEventCreate failed");
+        }
+        sc->ev_peer.push_back(e);
+    }
+    cudaSetDevice(device_ids[0]);
+    *out = sc;
+    return RT_OK;
+}
+
+int rt_scene_device_count(rt_scene* sc) { return sc ? (int)sc->peers.size() + 1 : 0; }
 
 // make lane i the one the launch code sees (sc->stream, sc->q, ...)
 static void bind_lane(rt_scene* sc, int i) {
@@ -1459,7 +980,16 @@ static void free_render_buffers(rt_scene* sc) {
 
 void rt_scene_destroy(rt_scene* sc) {
     if (!sc) return;
+    for (rt_scene* peer : sc->peers) rt_scene_destroy(peer);
+    sc->peers.clear();
     cudaSetDevice(sc->device);
+    for (Acc* a : sc->d_peer_acc) cudaFree(a);
+    for (cudaEvent_t e : sc->ev_peer) cudaEventDestroy(e);
+    if (sc->ev_multi_done) cudaEventDestroy(sc->ev_multi_done);
+    cudaFree(sc->d_full_frame);
+    cudaFree(sc->d_tone_in);
+    cudaFree(sc->d_tone_out);
+    if (sc->host_stage) cudaFreeHost(sc->host_stage);
     bind_lane(sc, 0);
     for (int l = 0; l < RT_MAX_LANES; l++)
         if (sc->lanes[l].stream) cudaStreamSynchronize(l == 0 ? sc->stream : sc->lanes[l].stream);
@@ -1672,31 +1202,12 @@ static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long 
             for (int kind = 0; kind < 6; kind++) {
                 if (!sc->kind_mask[kind]) continue;
                 uint32_t* head = sc->d_counts + RT_CNT_HEAD + kind * RT_MAX_LEVELS + level;
-#define RT_LAUNCH_MARCH(K_)                                                                                             \
-    case K_:                                                                                                            \
-        if (!sc->march_v1) {                                                                                            \
-            if (sc->counters_on)                                                                                        \
-                k_march2<K_, true><<<sc->grid_march2, RT_M2_THREADS, 0, sc->stream>>>(                                  \
-                    sc->ds, sc->kind_mask[kind], in, sc->hq, mcount, head, sc->d_march_state, sc->d_counters);          \
-            else                                                                                                        \
-                k_march2<K_, false><<<sc->grid_march2, RT_M2_THREADS, 0, sc->stream>>>(                                 \
-                    sc->ds, sc->kind_mask[kind], in, sc->hq, mcount, head, sc->d_march_state, sc->d_counters);          \
-        } else if (sc->counters_on)                                                                                     \
-            k_march<K_, true><<<sc->grid_march, 128, 0, sc->stream>>>(sc->ds, sc->kind_mask[kind], in, sc->hq, mcount,  \
-                                                                     head, sc->d_counters, sc->march_tune);            \
-        else                                                                                                            \
-            k_march<K_, false><<<sc->grid_march, 128, 0, sc->stream>>>(sc->ds, sc->kind_mask[kind], in, sc->hq, mcount, \
-                                                                      head, sc->d_counters, sc->march_tune);           \
-        break;
-                switch (kind) {
-                    RT_LAUNCH_MARCH(RT_SURF_HEART)
-                    RT_LAUNCH_MARCH(RT_SURF_SINE)
-                    RT_LAUNCH_MARCH(RT_SURF_STAR)
-                    RT_LAUNCH_MARCH(RT_SURF_DUPIN)
-                    RT_LAUNCH_MARCH(RT_SURF_HUNTS)
-                    RT_LAUNCH_MARCH(RT_SURF_CUSHION)
-                }
-#undef RT_LAUNCH_MARCH
+                MarchLaunch ml;
+                ml.ds = sc->ds; ml.kind = kind; ml.kind_mask = sc->kind_mask[kind]; ml.in = in; ml.hq = sc->hq;
+                ml.march_count = mcount; ml.head = head; ml.counters = sc->d_counters; ml.count = sc->counters_on;
+                ml.stream = sc->stream; ml.version = sc->march_version; ml.grid1 = sc->grid_march; ml.grid2 = sc->grid_march2;
+                ml.grid3 = sc->grid_march3; ml.smem3 = sc->smem_march3; ml.tune = sc->march_tune; ml.march_state = sc->d_march_state;
+                rt_launch_march(ml);
                 sc->launches++;
             }
             sc->launches--;  // the span already counted one launch
@@ -1737,13 +1248,25 @@ static int ensure_path_buffers(rt_scene* sc, uint64_t need_paths) {
         CU(cudaMalloc(&p, need_paths * sizeof(uint2))); sc->qallocs.push_back(p); sc->hq.key = (uint2*)p;
     }
     if (!sc->d_counts) CU(cudaMalloc(&sc->d_counts, RT_CNT_WORDS * sizeof(uint32_t)));
-    if (!sc->d_march_state && sc->ds.n_march > 0 && !sc->march_v1)
-        CU(cudaMalloc(&sc->d_march_state, (size_t)sc->grid_march2 * RT_M2_SLOTS * sizeof(MarchRec)));
+    if (!sc->d_march_state && sc->ds.n_march > 0 && sc->march_version == 2)
+        CU(cudaMalloc(&sc->d_march_state, rt_march2_state_bytes(sc->grid_march2)));
     sc->path_capacity = need_paths;
     return RT_OK;
 }
 
+static int render_start_single(rt_scene* sc, const rt_camera* cam, const rt_render_params* p);
+static int render_start_multi(rt_scene* sc, const rt_camera* cam, const rt_render_params* p);
+
 int rt_render_start(rt_scene* sc, const rt_camera* cam, const rt_render_params* p) {
+    if (!sc || !cam || !p) return fail(RT_ERR_INVALID, "null argument");
+    // a handle over several devices shards a WHOLE-frame request over them; an explicitly sharded request
+    // (one process per GPU on top of it) renders its shard on the first device as always
+    if (!sc->peers.empty() && p->shard_count <= 1) return render_start_multi(sc, cam, p);
+    sc->multi_active = false;
+    return render_start_single(sc, cam, p);
+}
+
+static int render_start_single(rt_scene* sc, const rt_camera* cam, const rt_render_params* p) {
     if (!sc || !cam || !p) return fail(RT_ERR_INVALID, "null argument");
     if (p->image.width == 0 || p->image.height == 0 || p->samples_number == 0)
         return fail(RT_ERR_INVALID, "empty image or zero samples");
@@ -1764,7 +1287,7 @@ int rt_render_start(rt_scene* sc, const rt_camera* cam, const rt_render_params* 
         (sc->accum_rp.shard_count ? sc->accum_rp.shard_count : 1) == shard_count &&
         sc->accum_rp.shard_index == p->shard_index && sc->accum_rp.tile_width == p->tile_width &&
         sc->accum_rp.tile_height == p->tile_height &&
-        (uint64_t)sc->accumulated_spp + p->samples_number <= (1u << 24))  // the float sample counter stays exact
+        (uint64_t)sc->accumulated_spp + p->samples_number <= 0xFFFFFFFFull)
         sample_base = sc->accumulated_spp;
     sc->accumulated_spp = 0;  // until this frame is enqueued (an abandoned frame breaks the chain)
     sc->rp = *p;
@@ -1795,7 +1318,7 @@ int rt_render_start(rt_scene* sc, const rt_camera* cam, const rt_render_params* 
     if (sc->frame_capacity < sc->owned_pixels) {
         cudaFree(sc->d_accum); cudaFree(sc->d_frame);
         sc->d_accum = nullptr; sc->d_frame = nullptr; sc->frame_capacity = 0;
-        CU(cudaMalloc(&sc->d_accum, std::max<uint64_t>(sc->owned_pixels, 1) * sizeof(float4)));
+        CU(cudaMalloc(&sc->d_accum, std::max<uint64_t>(sc->owned_pixels, 1) * sizeof(Acc)));
         CU(cudaMalloc(&sc->d_frame, std::max<uint64_t>(sc->owned_pixels, 1) * sizeof(rt_vec3)));
         sc->frame_capacity = sc->owned_pixels;
     }
@@ -1854,8 +1377,76 @@ int rt_render_start(rt_scene* sc, const rt_camera* cam, const rt_render_params* 
     return RT_OK;
 }
 
+// Whole frame on every device of the handle: device k renders shard k of n (interleaved 32x32 tiles, rotated rows:
+// ShardMap), all of them concurrently -- every call below only enqueues -- then each peer's accumulator travels to
+// the first device with ONE peer copy on the peer's own stream (so it is ordered behind that shard's last
+// k_resolve and the peer is free for its next frame as soon as the copy has left), and k_assemble builds the frame
+// behind the events of all copies.  Nothing here waits on the host.
+static int render_start_multi(rt_scene* sc, const rt_camera* cam, const rt_render_params* p) {
+    if (p->image.width == 0 || p->image.height == 0 || p->samples_number == 0)
+        return fail(RT_ERR_INVALID, "empty image or zero samples");
+    const uint32_t n_dev = (uint32_t)sc->peers.size() + 1;
+    rt_render_params sp = *p;
+    sp.shard_count = n_dev;
+    if (!sp.tile_width) sp.tile_width = 32;
+    if (!sp.tile_height) sp.tile_height = 32;
+    const uint64_t n_px = (uint64_t)p->image.width * p->image.height;
+    CU(cudaSetDevice(sc->device));
+    if (sc->multi_active && sc->ev_multi_done) CU(cudaEventSynchronize(sc->ev_multi_done));   // d_full_frame / staging still in use
+    if (sc->full_frame_cap < n_px) {
+        cudaFree(sc->d_full_frame);
+        sc->d_full_frame = nullptr;
+        sc->full_frame_cap = 0;
+        CU(cudaMalloc(&sc->d_full_frame, n_px * sizeof(rt_vec3)));
+        sc->full_frame_cap = n_px;
+    }
+    if (!sc->ev_multi_done) CU(cudaEventCreate(&sc->ev_multi_done));
+    for (uint32_t k = 1; k < n_dev; k++) {
+        const uint64_t need = rt_shard_float4_count(&sp, k);
+        if (sc->peer_acc_cap[k - 1] < need) {
+            cudaFree(sc->d_peer_acc[k - 1]);
+            sc->d_peer_acc[k - 1] = nullptr;
+            sc->peer_acc_cap[k - 1] = 0;
+            CU(cudaMalloc(&sc->d_peer_acc[k - 1], std::max<uint64_t>(need, 1) * sizeof(Acc)));
+            sc->peer_acc_cap[k - 1] = need;
+        }
+    }
+    // enqueue every shard (the peers first: the first device also assembles)
+    for (uint32_t k = 1; k < n_dev; k++) {
+        rt_scene* peer = sc->peers[k - 1];
+        sp.shard_index = k;
+        int rc = render_start_single(peer, cam, &sp);
+        if (rc != RT_OK) return rc;
+        const uint64_t cnt = rt_shard_float4_count(&sp, k);
+        if (cnt) CU(cudaMemcpyPeerAsync(sc->d_peer_acc[k - 1], sc->device, peer->d_accum, peer->device, cnt * sizeof(Acc), peer->stream));
+        CU(cudaEventRecord(sc->ev_peer[k - 1], peer->stream));
+    }
+    sp.shard_index = 0;
+    int rc = render_start_single(sc, cam, &sp);
+    if (rc != RT_OK) return rc;
+    CU(cudaSetDevice(sc->device));
+    for (uint32_t k = 1; k < n_dev; k++) CU(cudaStreamWaitEvent(sc->stream, sc->ev_peer[k - 1], 0));
+    ShardPtrs ptrs;
+    for (uint32_t k = 0; k < 16; k++) ptrs.p[k] = k == 0 ? sc->d_accum : k < n_dev ? sc->d_peer_acc[k - 1] : nullptr;
+    ShardMap m0 = make_shard_map(sp, 0);
+    dim3 grid((m0.width + 255) / 256, m0.height);
+    k_assemble<<<grid, 256, 0, sc->stream>>>(ptrs, m0, sc->d_full_frame);
+    sc->launches++;
+    CU(cudaEventRecord(sc->ev_multi_done, sc->stream));
+    CU(cudaGetLastError());
+    sc->multi_active = true;
+    sc->multi_rp = *p;
+    return RT_OK;
+}
+
 int rt_render_set_accumulate(rt_scene* sc, int enabled) {
     if (!sc) return fail(RT_ERR_INVALID, "null scene");
+    if (enabled && !sc->wavefront)
+        return fail(RT_ERR_STATE, "progressive accumulation needs the wavefront renderer (at most 32 ray-marched shapes)");
+    for (rt_scene* peer : sc->peers) {
+        int rc = rt_render_set_accumulate(peer, enabled);
+        if (rc != RT_OK) return rc;
+    }
     sc->accumulate = enabled != 0;
     sc->accumulated_spp = 0;
     return RT_OK;
@@ -1875,19 +1466,77 @@ static int deliver(rt_scene* sc, uint64_t q0, uint64_t q1, rt_vec3* buffer) {
         CU(cudaStreamSynchronize(sc->copy_stream));
         return RT_OK;
     }
-    sc->host_stage.resize(q1 - q0);
-    CU(cudaMemcpyAsync(sc->host_stage.data(), sc->d_frame + q0, (q1 - q0) * sizeof(rt_vec3), cudaMemcpyDeviceToHost, sc->copy_stream));
-    CU(cudaStreamSynchronize(sc->copy_stream));
-    for (uint64_t q = q0; q < q1; q++) {
-        uint32_t x, y;
-        if (sc->map.pixel_of(q, x, y)) buffer[(size_t)y * sc->map.width + x] = sc->host_stage[q - q0];
+    // a shard's pixels: pinned staging, then one memcpy per tile row (tile_w contiguous pixels of the caller's frame)
+    if (sc->host_stage_cap < q1 - q0) {
+        if (sc->host_stage) cudaFreeHost(sc->host_stage);
+        sc->host_stage = nullptr;
+        sc->host_stage_cap = 0;
+        CU(cudaMallocHost(&sc->host_stage, (q1 - q0) * sizeof(rt_vec3)));
+        sc->host_stage_cap = q1 - q0;
     }
+    CU(cudaMemcpyAsync(sc->host_stage, sc->d_frame + q0, (q1 - q0) * sizeof(rt_vec3), cudaMemcpyDeviceToHost, sc->copy_stream));
+    CU(cudaStreamSynchronize(sc->copy_stream));
+    const uint32_t tw = sc->map.tile_w;
+    for (uint64_t q = q0; q < q1;) {
+        uint32_t x, y;
+        const uint64_t run = std::min<uint64_t>(tw - (q % tw), q1 - q);   // to the end of this tile row
+        if (sc->map.pixel_of(q, x, y)) {
+            const uint64_t keep = std::min<uint64_t>(run, sc->map.width - x);   // clipped border tile
+            memcpy(buffer + (size_t)y * sc->map.width + x, sc->host_stage + (q - q0), keep * sizeof(rt_vec3));
+        }
+        q += run;
+    }
+    return RT_OK;
+}
+
+static int finish_frame(rt_scene* sc);   // bookkeeping of a completed single-device frame
+
+// the frame of a multi-device handle: complete when k_assemble has run; delivered with one contiguous copy
+static int render_poll_multi(rt_scene* sc, rt_vec3* buffer, int* done) {
+    CU(cudaSetDevice(sc->device));
+    cudaError_t e = cudaEventQuery(sc->ev_multi_done);
+    if (e == cudaErrorNotReady) {
+        *done = 0;
+        return RT_OK;
+    }
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("render: ") + cudaGetErrorString(e));
+    for (rt_scene* peer : sc->peers) {   // their streams are past the peer copy: close their frames
+        int rc = finish_frame(peer);
+        if (rc != RT_OK) return rc;
+    }
+    int rc = finish_frame(sc);
+    if (rc != RT_OK) return rc;
+    CU(cudaSetDevice(sc->device));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, sc->ev_frame_start, sc->ev_multi_done);
+    sc->last_frame_ms = ms;
+    if (buffer) {
+        const uint64_t n_px = (uint64_t)sc->multi_rp.image.width * sc->multi_rp.image.height;
+        CU(cudaMemcpyAsync(buffer, sc->d_full_frame, n_px * sizeof(rt_vec3), cudaMemcpyDeviceToHost, sc->copy_stream));
+        CU(cudaStreamSynchronize(sc->copy_stream));
+    }
+    *done = 1;
+    return RT_OK;
+}
+
+static int finish_frame(rt_scene* sc) {
+    if (!sc->rendering) return RT_OK;
+    CU(cudaSetDevice(sc->device));
+    CU(cudaStreamSynchronize(sc->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, sc->ev_frame_start, sc->ev_frame_stop);
+    sc->last_frame_ms = ms;
+    resolve_spans(sc);
+    sc->delivered = sc->batches.size();
+    sc->rendering = false;
+    sc->frame_complete = true;
     return RT_OK;
 }
 
 int rt_render_poll(rt_scene* sc, rt_vec3* buffer, int* done) {
     if (!sc || !done) return fail(RT_ERR_INVALID, "null argument");
     if (!sc->rendering) return fail(RT_ERR_STATE, "rt_render_poll without rt_render_start");
+    if (sc->multi_active) return render_poll_multi(sc, buffer, done);
     CU(cudaSetDevice(sc->device));
     size_t ready = sc->delivered;
     while (ready < sc->batches.size()) {
@@ -1927,6 +1576,7 @@ int rt_render_wait(rt_scene* sc, rt_vec3* buffer) {
     if (!sc) return fail(RT_ERR_INVALID, "null scene");
     if (!sc->rendering) return fail(RT_ERR_STATE, "rt_render_wait without rt_render_start");
     CU(cudaSetDevice(sc->device));
+    if (sc->multi_active) CU(cudaEventSynchronize(sc->ev_multi_done));
     CU(cudaStreamSynchronize(sc->stream));
     int done = 0;
     int rc = rt_render_poll(sc, buffer, &done);
@@ -1937,6 +1587,8 @@ int rt_render_wait(rt_scene* sc, rt_vec3* buffer) {
 
 int rt_render_stop(rt_scene* sc) {
     if (!sc) return fail(RT_ERR_INVALID, "null scene");
+    if (sc->multi_active)
+        for (rt_scene* peer : sc->peers) rt_render_stop(peer);
     if (!sc->rendering) return RT_OK;
     cudaSetDevice(sc->device);
     // work already enqueued cannot be recalled; drain it so the buffers can be reused
@@ -1947,8 +1599,27 @@ int rt_render_stop(rt_scene* sc) {
     return RT_OK;
 }
 
+int rt_render_device_frame(rt_scene* sc, const rt_vec3** d_frame, uint64_t* n_pixels) {
+    if (!sc || !d_frame || !n_pixels) return fail(RT_ERR_INVALID, "null argument");
+    if (sc->rendering) {
+        int rc = rt_render_wait(sc, nullptr);
+        if (rc != RT_OK) return rc;
+    }
+    if (!sc->frame_complete) return fail(RT_ERR_STATE, "no completed frame");
+    if (sc->multi_active) {
+        *d_frame = sc->d_full_frame;
+        *n_pixels = (uint64_t)sc->multi_rp.image.width * sc->multi_rp.image.height;
+        return RT_OK;
+    }
+    if (sc->map.shard_count != 1) return fail(RT_ERR_STATE, "the last frame was one shard of a frame: use rt_render_device_result + rt_assemble_frame");
+    *d_frame = sc->d_frame;   // owned order == x + y*width for an unsharded frame
+    *n_pixels = (uint64_t)sc->map.width * sc->map.height;
+    return RT_OK;
+}
+
 int rt_render_device_result(rt_scene* sc, const void** d_accum, uint64_t* n_float4) {
     if (!sc || !d_accum || !n_float4) return fail(RT_ERR_INVALID, "null argument");
+    if (sc->multi_active) return fail(RT_ERR_STATE, "a multi-device handle delivers the assembled frame: rt_render_device_frame");
     if (sc->rendering) {
         CU(cudaSetDevice(sc->device));
         CU(cudaStreamSynchronize(sc->stream));
@@ -1977,7 +1648,7 @@ int rt_assemble_frame(rt_scene* sc, const rt_render_params* p, const void* const
     pp.shard_count = shard_count;
     ShardMap m = make_shard_map(pp, 0);
     ShardPtrs sp;
-    for (uint32_t s = 0; s < 16; s++) sp.p[s] = s < shard_count ? (const float4*)d_shards[s] : nullptr;
+    for (uint32_t s = 0; s < 16; s++) sp.p[s] = s < shard_count ? (const Acc*)d_shards[s] : nullptr;
     cudaStream_t st = stream ? (cudaStream_t)stream : sc->stream;
     dim3 grid((m.width + 255) / 256, m.height);
     k_assemble<<<grid, 256, 0, st>>>(sp, m, d_frame);
@@ -1986,23 +1657,53 @@ int rt_assemble_frame(rt_scene* sc, const rt_render_params* p, const void* const
     return RT_OK;
 }
 
+static int ensure_tone_out(rt_scene* sc, uint64_t n) {
+    if (sc->tone_out_cap >= n) return RT_OK;
+    cudaFree(sc->d_tone_out);
+    sc->d_tone_out = nullptr;
+    sc->tone_out_cap = 0;
+    CU(cudaMalloc(&sc->d_tone_out, n * sizeof(uchar4)));
+    sc->tone_out_cap = n;
+    return RT_OK;
+}
+
 int rt_tonemap_rgba8(rt_scene* sc, const rt_vec3* frame, uint64_t n, uint8_t* rgba) {
     if (!sc || !frame || !rgba) return fail(RT_ERR_INVALID, "null argument");
     if (n == 0) return RT_OK;
     CU(cudaSetDevice(sc->device));
-    rt_vec3* d_in = nullptr;
-    uchar4* d_out = nullptr;
-    CU(cudaMalloc(&d_in, n * sizeof(rt_vec3)));
-    cudaError_t e = cudaMalloc(&d_out, n * sizeof(uchar4));
-    if (e != cudaSuccess) { cudaFree(d_in); return fail(RT_ERR_NOMEM, "cudaMalloc failed"); }
-    cudaMemcpyAsync(d_in, frame, n * sizeof(rt_vec3), cudaMemcpyHostToDevice, sc->stream);
-    k_tonemap<<<(unsigned)((n + 255) / 256), 256, 0, sc->stream>>>(d_in, n, d_out);
+    if (sc->tone_in_cap < n) {   // persistent buffers, grown on demand: no allocation per call
+        cudaFree(sc->d_tone_in);
+        sc->d_tone_in = nullptr;
+        sc->tone_in_cap = 0;
+        CU(cudaMalloc(&sc->d_tone_in, n * sizeof(rt_vec3)));
+        sc->tone_in_cap = n;
+    }
+    int rc = ensure_tone_out(sc, n);
+    if (rc != RT_OK) return rc;
+    CU(cudaMemcpyAsync(sc->d_tone_in, frame, n * sizeof(rt_vec3), cudaMemcpyHostToDevice, sc->copy_stream));
+    k_tonemap<<<(unsigned)((n + 255) / 256), 256, 0, sc->copy_stream>>>(sc->d_tone_in, n, sc->d_tone_out);
     sc->launches++;
-    cudaMemcpyAsync(rgba, d_out, n * sizeof(uchar4), cudaMemcpyDeviceToHost, sc->stream);
-    e = cudaStreamSynchronize(sc->stream);
-    cudaFree(d_in);
-    cudaFree(d_out);
+    CU(cudaMemcpyAsync(rgba, sc->d_tone_out, n * sizeof(uchar4), cudaMemcpyDeviceToHost, sc->copy_stream));
+    cudaError_t e = cudaStreamSynchronize(sc->copy_stream);
     if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("tonemap: ") + cudaGetErrorString(e));
+    return RT_OK;
+}
+
+int rt_tonemap_rgba8_device(rt_scene* sc, const uint8_t** d_rgba, uint8_t* rgba_host, uint64_t* n_pixels) {
+    if (!sc) return fail(RT_ERR_INVALID, "null scene");
+    const rt_vec3* d_frame = nullptr;
+    uint64_t n = 0;
+    int rc = rt_render_device_frame(sc, &d_frame, &n);
+    if (rc != RT_OK) return rc;
+    CU(cudaSetDevice(sc->device));
+    if ((rc = ensure_tone_out(sc, n)) != RT_OK) return rc;
+    k_tonemap<<<(unsigned)((n + 255) / 256), 256, 0, sc->copy_stream>>>(d_frame, n, sc->d_tone_out);
+    sc->launches++;
+    if (rgba_host) CU(cudaMemcpyAsync(rgba_host, sc->d_tone_out, n * sizeof(uchar4), cudaMemcpyDeviceToHost, sc->copy_stream));
+    cudaError_t e = cudaStreamSynchronize(sc->copy_stream);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("tonemap: ") + cudaGetErrorString(e));
+    if (d_rgba) *d_rgba = reinterpret_cast<const uint8_t*>(sc->d_tone_out);
+    if (n_pixels) *n_pixels = n;
     return RT_OK;
 }
 
@@ -2016,10 +1717,10 @@ int rt_trace_pixel_samples(rt_scene* sc, const rt_ray* rays, uint32_t n_rays, ui
     int rc = ensure_path_buffers(sc, std::max<uint64_t>(n_rays, 1024));
     if (rc != RT_OK) return rc;
     rt_ray* d_rays = nullptr;
-    float4* d_acc = nullptr;
+    Acc* d_acc = nullptr;
     rt_vec3* d_mean = nullptr;
     CU(cudaMalloc(&d_rays, n_rays * sizeof(rt_ray)));
-    cudaMalloc(&d_acc, sizeof(float4));
+    cudaMalloc(&d_acc, sizeof(Acc));
     cudaMalloc(&d_mean, sizeof(rt_vec3));
     cudaMemcpyAsync(d_rays, rays, n_rays * sizeof(rt_ray), cudaMemcpyHostToDevice, sc->stream);
     cudaMemsetAsync(sc->d_counts, 0, RT_CNT_WORDS * sizeof(uint32_t), sc->stream);

@@ -4,7 +4,10 @@ torch / torch.distributed are plumbing only (process group, device buffers for t
 pixel is produced by the CUDA core through the C ABI (rt_render_start with shard_count/shard_index,
 rt_render_device_result, rt_assemble_frame).  Tile k (row-major, 32x32 by default) belongs to rank
 k % world_size; the RNG is keyed by (pixel, sample, event), so the assembled frame does not depend on
-the number of GPUs.
+the number of GPUs -- bit for bit: the accumulators exchanged are the f64 sums themselves.
+
+A single-process alternative needs no torch at all: GpuRenderer(scene, ..., devices=[0, 1, ...]) drives every GPU of
+the box through one handle of the C ABI (rt_scene_create_multi, peer copies instead of NCCL).
 """
 from __future__ import annotations
 
@@ -41,7 +44,8 @@ def owned_pixel_coords(width: int, height: int, tile: int, world: int, shard: in
 
 
 def exchange_to_rank0(dist, mine, counts, rank: int, world: int, bufs=None):
-    """The one exchange of a frame: every rank's tile-packed float4 accumulator to rank 0 (grouped
+    """The one exchange of a frame: every rank's tile-packed accumulator (4 doubles per pixel: f64 sums of r, g, b and
+    the sample count, so that the assembled frame is the unsharded one bit for bit) to rank 0 (grouped
     send/recv: shard sizes can differ by one tile, so this is not dist.gather).  Returns the list of the
     `world` shard tensors on rank 0, None elsewhere.  Backend-agnostic (NCCL on GPUs, gloo in the CPU tests)."""
     import torch
@@ -50,7 +54,7 @@ def exchange_to_rank0(dist, mine, counts, rank: int, world: int, bufs=None):
     ops = []
     if rank == 0:
         if bufs is None or [b.shape[0] for b in bufs] != list(counts):
-            bufs = [torch.empty((c, 4), dtype=torch.float32, device=mine.device) for c in counts]
+            bufs = [torch.empty((c, 4), dtype=torch.float64, device=mine.device) for c in counts]
         bufs[0].copy_(mine)
         for s in range(1, world):
             ops.append(dist.P2POp(dist.irecv, bufs[s], s))
@@ -106,7 +110,7 @@ class DistributedRenderer:
             self._exchanged.synchronize()
         api.render_start(self.dev_scene, camera, p)
         ptr, n = api.render_device_result(self.dev_scene)   # waits for this shard's kernels
-        mine = torch.as_tensor(api.DevicePointer(ptr, (n, 4), "<f4", owner=self), device=f"cuda:{self.device}")
+        mine = torch.as_tensor(api.DevicePointer(ptr, (n, 4), "<f8", owner=self), device=f"cuda:{self.device}")
         counts = [api.shard_float4_count(p, s) for s in range(self.world)]
         # one exchange per frame: every rank's tile-packed accumulator to rank 0 over NVLink
         shards = exchange_to_rank0(dist, mine, counts, self.rank, self.world, self._gather_bufs)
@@ -138,4 +142,5 @@ class DistributedRenderer:
             self._host = torch.empty(frame.shape, dtype=frame.dtype, pin_memory=True)
         self._host.copy_(frame, non_blocking=True)
         torch.cuda.current_stream().synchronize()
+        # (a view of the renderer's pinned buffer: valid until the next render(); copy it to keep it)
         return self._host.numpy()

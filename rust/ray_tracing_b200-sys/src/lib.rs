@@ -1,9 +1,9 @@
-//! Raw bindings to `include/rt_b200.h` (ABI version 3).  One item per declaration of the header; see
+//! Raw bindings to `include/rt_b200.h` (ABI version 4).  One item per declaration of the header; see
 //! the header for the contract of every entry point and the reference interface it replaces.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const RT_B200_ABI_VERSION: c_int = 3;
+pub const RT_B200_ABI_VERSION: c_int = 4;
 
 // rt_status
 pub const RT_OK: c_int = 0;
@@ -77,6 +77,9 @@ extern "C" {
     pub fn rt_device_count() -> c_int;
     pub fn rt_scene_create(desc: *const rt_scene_desc, device: c_int, out: *mut *mut rt_scene) -> c_int;
     pub fn rt_scene_destroy(scene: *mut rt_scene);
+    pub fn rt_scene_create_multi(desc: *const rt_scene_desc, n_devices: c_int, device_ids: *const c_int,
+        out: *mut *mut rt_scene) -> c_int;
+    pub fn rt_scene_device_count(scene: *mut rt_scene) -> c_int;
     pub fn rt_intersect_batch(scene: *mut rt_scene, rays: *const rt_ray, n: u64, t_min: f64, t_max: f64,
         mode: c_int, shape_index: *mut i32, t: *mut f64, normal: *mut rt_vec3, point: *mut rt_vec3,
         uv: *mut f64, front_face: *mut u8) -> c_int;
@@ -93,7 +96,10 @@ extern "C" {
     pub fn rt_shard_float4_count(params: *const rt_render_params, shard_index: u32) -> u64;
     pub fn rt_assemble_frame(scene: *mut rt_scene, params: *const rt_render_params, d_shards: *const *const c_void,
         d_frame: *mut rt_vec3, stream: *mut c_void) -> c_int;
+    pub fn rt_render_device_frame(scene: *mut rt_scene, d_frame: *mut *const rt_vec3, n_pixels: *mut u64) -> c_int;
     pub fn rt_tonemap_rgba8(scene: *mut rt_scene, frame: *const rt_vec3, n_pixels: u64, rgba: *mut u8) -> c_int;
+    pub fn rt_tonemap_rgba8_device(scene: *mut rt_scene, d_rgba: *mut *const u8, rgba_host: *mut u8,
+        n_pixels: *mut u64) -> c_int;
     pub fn rt_trace_pixel_samples(scene: *mut rt_scene, rays: *const rt_ray, n_rays: u32, max_depth: u32,
         seed: u64, pixel_index: u32, mean_out: *mut rt_vec3) -> c_int;
     pub fn rt_get_stats(scene: *mut rt_scene, out: *mut rt_stats) -> c_int;

@@ -31,8 +31,8 @@ def _worker(rank, world, port, width, height, tile, spp, out_path):
         p = api.render_params(width, height, spp, 8, 0, world, rank, tile=tile)
         counts = [api.shard_float4_count(p, s) for s in range(world)]
         assert len(x) == counts[rank]
-        mine = np.zeros((counts[rank], 4), dtype=np.float32)   # (sum rgb, samples); padding stays 0
-        mine[ok, :3] = (_pixel_value(x[ok], y[ok]) * spp).astype(np.float32)
+        mine = np.zeros((counts[rank], 4), dtype=np.float64)   # (sum rgb, samples); padding stays 0
+        mine[ok, :3] = (_pixel_value(x[ok], y[ok]) * spp).astype(np.float64)
         mine[ok, 3] = spp
         shards = exchange_to_rank0(dist, torch.from_numpy(mine), counts, rank, world)
         if rank == 0:
@@ -58,7 +58,7 @@ def test_two_rank_gather_and_assemble(tmp_path, width, height, tile):
     mp.spawn(_worker, args=(world, _free_port(), width, height, tile, spp, out), nprocs=world, join=True)
     frame = np.load(out)
     yy, xx = np.mgrid[0:height, 0:width]
-    want = _pixel_value(xx, yy).astype(np.float32).astype(np.float64)   # float accumulator, exact for these values
+    want = _pixel_value(xx, yy).astype(np.float64).astype(np.float64)   # f64 accumulator
     assert np.array_equal(frame, want)
 
 
@@ -84,10 +84,10 @@ def _worker_sequence(rank, world, port, width, height, tile, out_path):
         p = api.render_params(width, height, 1, 8, 0, world, rank, tile=tile)
         counts = [api.shard_float4_count(p, s) for s in range(world)]
         bufs, frames = None, []
-        mine = torch.zeros((counts[rank], 4), dtype=torch.float32)    # one accumulator, overwritten every frame
+        mine = torch.zeros((counts[rank], 4), dtype=torch.float64)    # one accumulator, overwritten every frame
         for k, spp in enumerate((4, 1, 16, 2)):
-            acc = np.zeros((counts[rank], 4), dtype=np.float32)
-            acc[ok, :3] = ((_pixel_value(x[ok], y[ok]) + k) * spp).astype(np.float32)
+            acc = np.zeros((counts[rank], 4), dtype=np.float64)
+            acc[ok, :3] = ((_pixel_value(x[ok], y[ok]) + k) * spp).astype(np.float64)
             acc[ok, 3] = spp
             mine.copy_(torch.from_numpy(acc))
             shards = exchange_to_rank0(dist, mine, counts, rank, world, bufs)
@@ -108,7 +108,7 @@ def test_consecutive_frames_through_reused_gather_buffers(tmp_path):
     frames = np.load(out)
     yy, xx = np.mgrid[0:height, 0:width]
     for k in range(4):
-        want = (_pixel_value(xx, yy) + k).astype(np.float32).astype(np.float64)
+        want = (_pixel_value(xx, yy) + k).astype(np.float64).astype(np.float64)
         assert np.array_equal(frames[k], want), k
 
 

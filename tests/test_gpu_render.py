@@ -188,8 +188,8 @@ def test_progressive_accumulation_across_start_calls():
         assert api.render_accumulated_samples(ds) == 4 * (k + 1)
         if k == 0:
             assert np.array_equal(buf, ref4)
-    # same paths; the float4 accumulator is rounded once per frame instead of once: 1e-6 relative
-    assert np.allclose(buf, ref12, rtol=2e-6, atol=1e-7)
+    # the same paths, summed in the same order into f64 sums: three frames of 4 samples ARE the frame of 12
+    assert np.array_equal(buf, ref12)
     assert not np.allclose(buf, ref4, rtol=1e-3, atol=1e-4)
     # device-side result carries the total sample count
     torch = pytest.importorskip("torch")
@@ -233,8 +233,45 @@ def test_sharded_render_assembles_to_the_unsharded_frame():
         p0 = api.render_params(w, h, spp, depth, seed, shards, 0, tile=32)
         api.assemble_frame(scenes[0].device_scene(0), p0, ptrs, frame.data_ptr())
         torch.cuda.synchronize()
-        # the float4 accumulator keeps float sums: equal to the f64 host frame up to float rounding
-        assert np.allclose(frame.cpu().numpy(), ref, rtol=3e-7, atol=1e-9)
+        # the accumulators hold the f64 sums themselves: the assembled frame IS the unsharded one
+        assert np.array_equal(frame.cpu().numpy(), ref)
+
+
+def test_one_handle_over_all_devices_renders_the_unsharded_frame():
+    """rt_scene_create_multi through GpuRenderer(devices=[...]): ONE process, ONE handle, every visible GPU (all of
+    them; twice the same box's device 0 is not allowed, so a single-GPU box checks the n = 1 path of the same entry
+    points) -- the frame equals the single-device frame bit for bit, also with changing sizes / sample counts back to
+    back, progressive accumulation and the device-side tonemap"""
+    n_dev = rt.device_count()
+    devices = list(range(n_dev))
+    w, h, depth, seed = 200, 120, 8, 5
+    sc = rt.Scene.from_file(scene_path("cornell_box.json"), random_spheres_seed=1)
+    cam = sc.camera()
+    multi = rt.GpuRenderer(sc, 12, depth, seed=seed, devices=devices)
+    ds = sc.device_scene_multi(devices) if n_dev > 1 else sc.device_scene(0)
+    assert _ffi_core().rt_scene_device_count(ds) == n_dev
+    for (ww, hh, spp) in ((w, h, 4), (w, h, 2), (96, 72, 3), (w, h, 4)):
+        ref_sc = rt.Scene.from_file(scene_path("cornell_box.json"), random_spheres_seed=1)
+        ref = gpu_frame(ref_sc, cam, ww, hh, spp, depth, seed)
+        got = multi.render(cam, ww, hh, spp)
+        assert np.array_equal(got, ref), (ww, hh, spp)
+        # the frame stays on the (first) device; the bins' tonemap runs on it without the f64 frame crossing the bus
+        rgba = api.tonemap_last_frame(ds).reshape(hh, ww, 4)
+        assert np.array_equal(rgba, rt.tonemap_rgba8(ref_sc, ref))
+    # progressive accumulation through the same handle
+    api.render_set_accumulate(ds, True)
+    buf = np.zeros((h, w, 3))
+    for k in range(3):
+        api.render_start(ds, cam, api.render_params(w, h, 2, depth, seed))
+        api.render_wait(ds, buf)
+    api.render_set_accumulate(ds, False)
+    ref_sc = rt.Scene.from_file(scene_path("cornell_box.json"), random_spheres_seed=1)
+    assert np.array_equal(buf, gpu_frame(ref_sc, cam, w, h, 6, depth, seed))
+
+
+def _ffi_core():
+    from rs_pathtracing_b200 import _ffi
+    return _ffi.core()
 
 
 def test_tonemap_matches_the_bins_formula():
@@ -272,16 +309,18 @@ def test_work_counters_match_oracle():
 @pytest.mark.parametrize("name", ["spheres.json", "cornell_box.json", "dupin.json", "detached_materials.json",
                                   "light_source.json"])
 def test_alternative_schedules_give_the_same_frame(monkeypatch, name):
-    """the marching result does not depend on how the work is scheduled: the block-local wavefront marcher
-    (RT_B200_MARCH_V2, an experiment kept off by default), the fused k_bounce (RT_B200_FUSED_BOUNCE) and
-    other k_march voting thresholds reproduce the default frame bit for bit; so do the flat list without its
+    """the marching result does not depend on how the work is scheduled: the default is the pooled marcher k_march3
+    (a pool of rays per warp, dynamic pick-up inside every variable-length loop); the one-ray-per-lane marcher k_march
+    (RT_B200_MARCH=1, also with other voting thresholds), the block-local wavefront marcher k_march2 (RT_B200_MARCH=2)
+    and the fused k_bounce (RT_B200_FUSED_BOUNCE) reproduce the default frame bit for bit; so do the flat list without its
     staged records (RT_B200_NO_FLAT_REC) and marching-bound tests deferred to k_march (RT_B200_DEFER_BOUND).
     The fused k_bounce draws random_in_unit_sphere with the sequential rejection loop and the default k_shade
     warp-cooperatively, so this also pins the cooperative sampler to the sequential one"""
     w, h, spp, depth, seed = 96, 72, 4, 8, 21
     sc = rt.Scene.from_file(scene_path(name), random_spheres_seed=1)
     ref = gpu_frame(sc, sc.camera(), w, h, spp, depth, seed)
-    for var, val in (("RT_B200_MARCH_V2", "1"), ("RT_B200_FUSED_BOUNCE", "1"), ("RT_B200_MARCH_TUNE", "2,30,3"),
+    for var, val in (("RT_B200_MARCH", "1"), ("RT_B200_MARCH", "2"), ("RT_B200_FUSED_BOUNCE", "1"),
+                     ("RT_B200_MARCH_TUNE", "2,30,3"),
                      ("RT_B200_NO_CULL_TREE", "1"), ("RT_B200_NO_MARCH_SKIP", "1"), ("RT_B200_NO_FLAT_REC", "1"),
                      ("RT_B200_DEFER_BOUND", "1")):
         monkeypatch.setenv(var, val)

@@ -20,12 +20,14 @@ for r in rows:
     elif cur is not None and len(r) > 8:
         cur["rows"].append(r)
 sel = [b for b in blocks if want in b["name"]]
-# one block per (launch, file); group by launch = order of appearance of the rt_core.cu block
+# one block per (launch, file): a launch's blocks list every file once, so a file that repeats starts the next launch
 launches = collections.OrderedDict()
-k = -1
+k, seen = -1, set()
 for b in sel:
-    if b["file"].endswith("rt_core.cu"):
+    if k < 0 or b["file"] in seen:
         k += 1
+        seen = set()
+    seen.add(b["file"])
     launches.setdefault(k, []).append(b)
 tot = collections.Counter(); thr = collections.Counter(); smp = collections.Counter(); text = {}
 for b in launches[which]:
