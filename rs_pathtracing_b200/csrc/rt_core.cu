@@ -328,22 +328,68 @@ k_bounce(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
 #ifndef RT_EXTEND_MIN_BLOCKS
 #define RT_EXTEND_MIN_BLOCKS 3
 #endif
-template <bool COUNT>
+// RAYGEN (bounce level 0 of a frame): the primary rays are GENERATED here instead of being read back from the
+// queue a separate k_raygen pass wrote (that pass was a pure HBM round trip: 76 B written and 48 B re-read per path,
+// 3 % of the step) -- MultisamplerRayCaster::next, src/camera/ray_caster.rs:100-118, same draws, same arithmetic.
+// Path i of the batch takes queue slot i (no compaction); the slots of a clipped border tile's padding pixels are
+// marked dead (index -2) and k_shade skips them.
+struct RaygenArgs {
+    RayCasterDev rc;
+    ShardMap map;
+    unsigned long long first_owned;
+    uint32_t n_paths, spp, k0, k1, sample_base;
+    float4* radiance;
+    uint32_t* count_out;   // receives n_paths: the live count of level 0 that k_march / k_shade read
+};
+#define RT_HIT_DEAD (-2)
+template <bool COUNT, bool RAYGEN>
 __global__ void __launch_bounds__(256, RT_EXTEND_MIN_BLOCKS)
 k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ count_in, HitQueue hq,
          uint32_t* march_count, uint32_t* replay_count, DevCounters* g_counters, bool any_hit_suffices,
-         bool defer_bound) {
+         bool defer_bound, RaygenArgs rg) {
     Staged st = stage_scene(S, use_smem);
     DevCounters c = {};
-    const uint32_t n = *count_in;
+    const uint32_t n = RAYGEN ? rg.n_paths : *count_in;
+    if (RAYGEN && blockIdx.x == 0 && threadIdx.x == 0) *rg.count_out = n;
     const uint32_t n_round = (n + 31u) & ~31u;
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
         uint32_t mask = 0;
         bool degenerate = false;
-        if (i < n) {
-            D3 ro = mk(in.ox[i], in.oy[i], in.oz[i]);
-            D3 rd = mk(in.dx[i], in.dy[i], in.dz[i]);
+        bool live = i < n;
+        D3 ro = mk(0.0, 0.0, 0.0), rd = mk(0.0, 0.0, 0.0);
+        if (RAYGEN && live) {
+            const uint32_t pl = i / rg.spp, s = i - pl * rg.spp;
+            uint32_t x, y;
+            if (rg.map.pixel_of(rg.first_owned + pl, x, y)) {
+                PathRng rng;
+                rng.k0 = rg.k0; rng.k1 = rg.k1;
+                rng.pixel = x + y * rg.map.width;
+                rng.sample = rg.sample_base + s;  // (samples of earlier frames of a progressive accumulation come first)
+                rng.begin_event(0);
+                const double u = rng.next();   // ray_caster.rs:106-107
+                const double v = rng.next();
+                // :109-112
+                const D3 d = rg.rc.left_top + (rg.rc.pixel_resolution * ((double)x + u)) * rg.rc.camera_right -
+                             (rg.rc.pixel_resolution * ((double)y + v)) * rg.rc.camera_up;
+                ro = rg.rc.camera_position;
+                rd = normalize(d - rg.rc.camera_position);  // Ray::new
+                hq.key[i] = make_uint2(rng.pixel, rng.sample);
+                in.ox[i] = ro.x; in.oy[i] = ro.y; in.oz[i] = ro.z;
+                in.dx[i] = rd.x; in.dy[i] = rd.y; in.dz[i] = rd.z;
+                in.bx[i] = 1.0; in.by[i] = 1.0; in.bz[i] = 1.0;
+                in.pid[i] = i;
+            } else {
+                rg.radiance[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                hq.index[i] = RT_HIT_DEAD;
+                live = false;
+            }
+        }
+        if (live) {
+            if (!RAYGEN) {
+                ro = mk(in.ox[i], in.oy[i], in.oz[i]);
+                rd = mk(in.dx[i], in.dy[i], in.dz[i]);
+            }
             double best;
             int winner;
             const CullRay cr = make_cull_ray(ro.x, ro.y, ro.z, rd.x, rd.y, rd.z);
@@ -411,7 +457,7 @@ k_shade(DevScene S, PathQueue in, const uint32_t* __restrict__ count_in, HitQueu
     __shared__ uint4 s_ball_id[256];
     uint4* const s_id = s_ball_id + (threadIdx.x & ~31u);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        bool alive = false, shading = false, need_ball = false;
+        bool alive = false, shading = false, need_ball = false, dead = false;
         D3 no = mk(0, 0, 0), nd = mk(0, 0, 0), nb = mk(0, 0, 0);
         D3 rd = mk(0, 0, 0), beta = mk(0, 0, 0), L = mk(0.0, 0.0, 0.0);
         uint32_t pid = 0;
@@ -425,7 +471,9 @@ k_shade(DevScene S, PathQueue in, const uint32_t* __restrict__ count_in, HitQueu
             beta = mk(in.bx[i], in.by[i], in.bz[i]);
             pid = in.pid[i];
             const int bi = hq.index[i];
-            if (bi < 0) {
+            if (bi == RT_HIT_DEAD) {
+                dead = true;   // padding pixel of a clipped border tile (k_extend, RAYGEN): no path
+            } else if (bi < 0) {
                 L = hadamard(beta, sky(rd));  // renderer/mod.rs:41-43
             } else if (level == max_depth) {
                 // depth == 0: black (:26-27)
@@ -452,7 +500,7 @@ k_shade(DevScene S, PathQueue in, const uint32_t* __restrict__ count_in, HitQueu
                 L = hadamard(beta, atten);  // :34-36
             }
         }
-        if (i < n && !alive) radiance[pid] = make_float4((float)L.x, (float)L.y, (float)L.z, 1.0f);
+        if (i < n && !alive && !dead) radiance[pid] = make_float4((float)L.x, (float)L.y, (float)L.z, 1.0f);
         uint32_t slot = queue_append(alive, count_out);
         if (alive) {
             out.ox[slot] = no.x; out.oy[slot] = no.y; out.oz[slot] = no.z;
@@ -624,8 +672,8 @@ struct rt_scene {
     int grid_march2 = 0, grid_march3 = 0;
     size_t smem_march3 = 0;
     bool defer_bound = false;                    // k_extend queues every ray whose line touches a marching bound's ball; k_march sorts out the rest (RT_B200_DEFER_BOUND=1)
-    int march_version = 3;                       // 3: pooled rays per warp (k_march3, rt_march3.cu); RT_B200_MARCH=1: one ray per lane
-                                                 // (k_march); =2: block-local wavefront (k_march2, experiment)
+    int march_version = 1;                       // 1: one ray per lane (k_march); RT_B200_MARCH=3: pool of rays per SM + per-phase queues
+                                                 // (k_march3, rt_march3.cu: correct but slower, see profiles/); =2: block-local wavefront (k_march2)
     int3 march_tune = make_int3(8, 8, 8);        // k_march scheduling thresholds (RT_B200_MARCH_TUNE=a,b,c)
     int march_grid_scale = 100;                  // percent of the occupancy grid
     bool wavefront = true;         // extend/march/shade; false = fused k_bounce (more than 32 marched shapes)
@@ -855,8 +903,10 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
         cudaFuncSetAttribute(k_intersect_batch<false, RT_ISECT_VERIFY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
         cudaFuncSetAttribute(k_bounce<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
         cudaFuncSetAttribute(k_bounce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
-        cudaFuncSetAttribute(k_extend<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
-        cudaFuncSetAttribute(k_extend<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+        cudaFuncSetAttribute(k_extend<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+        cudaFuncSetAttribute(k_extend<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+        cudaFuncSetAttribute(k_extend<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
+        cudaFuncSetAttribute(k_extend<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc->smem_bytes);
     }
     // persistent grid: a whole number of CTAs per SM
     int per_sm = 0;
@@ -868,7 +918,7 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, threads, smem);
         return sc->n_sm * std::max(b, 1);
     };
-    sc->grid_extend = occ_grid(k_extend<false>, 256, sc->smem_bytes);
+    sc->grid_extend = occ_grid(k_extend<false, true>, 256, sc->smem_bytes);
     if (const char* tv = getenv("RT_B200_MARCH_TUNE")) {
         int a = 8, b = 8, c2 = 8, g = 0;
         if (sscanf(tv, "%d,%d,%d,%d", &a, &b, &c2, &g) >= 3) sc->march_tune = make_int3(std::max(a, 1), std::max(b, 1), std::max(c2, 1));
@@ -1169,7 +1219,8 @@ static int alloc_queue(rt_scene* sc, PathQueue& q, uint64_t cap) {
 
 
 // enqueue the bounce loop for paths already in q[0] (count in d_counts[0]); no host sync
-static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long first_owned, uint32_t spp, uint64_t seed) {
+static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long first_owned, uint32_t spp, uint64_t seed,
+                           const RaygenArgs* raygen = nullptr) {
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
     for (uint32_t level = 0; level <= max_depth; level++) {
         PathQueue& in = sc->q[level & 1];
@@ -1192,10 +1243,19 @@ static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long 
         }
         {
             KernelSpan span(sc, RT_KCLASS_EXTEND);
-            if (sc->counters_on)
-                k_extend<true><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, rcount, sc->d_counters, level == max_depth, sc->defer_bound);
-            else
-                k_extend<false><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, rcount, sc->d_counters, level == max_depth, sc->defer_bound);
+            const bool gen = level == 0 && raygen != nullptr;   // the frame's primary rays are generated in place
+            RaygenArgs rg{};
+            if (gen) rg = *raygen;
+#define RT_LAUNCH_EXTEND(C_, G_)                                                                                        \
+    k_extend<C_, G_><<<sc->grid_extend, 256, sc->smem_bytes, sc->stream>>>(sc->ds, sc->use_smem, in, cnt_in, sc->hq, mcount, \
+                                                                           rcount, sc->d_counters, level == max_depth,     \
+                                                                           sc->defer_bound, rg)
+            if (sc->counters_on) {
+                if (gen) RT_LAUNCH_EXTEND(true, true); else RT_LAUNCH_EXTEND(true, false);
+            } else {
+                if (gen) RT_LAUNCH_EXTEND(false, true); else RT_LAUNCH_EXTEND(false, false);
+            }
+#undef RT_LAUNCH_EXTEND
         }
         if (sc->ds.n_march > 0) {
             KernelSpan span(sc, RT_KCLASS_MARCH);
@@ -1338,11 +1398,18 @@ static int render_start_single(rt_scene* sc, const rt_camera* cam, const rt_rend
             bind_lane(sc, (int)(batch_no % (uint64_t)lanes_used));
             uint32_t npx = (uint32_t)std::min<uint64_t>(px_per_batch, sc->owned_pixels - first);
             CU(cudaMemsetAsync(sc->d_counts, 0, RT_CNT_WORDS * sizeof(uint32_t), sc->stream));
-            {
-                KernelSpan span(sc, RT_KCLASS_RAYGEN);
-                k_raygen<<<sc->grid, 256, 0, sc->stream>>>(rcd, sc->map, first, npx, spp, k0, k1, sc->q[0], sc->d_counts, sc->d_radiance, sc->hq.key, sample_base);
+            if (sc->wavefront) {   // primary rays are generated inside the level-0 k_extend
+                RaygenArgs rg;
+                rg.rc = rcd; rg.map = sc->map; rg.first_owned = first; rg.n_paths = npx * spp; rg.spp = spp;
+                rg.k0 = k0; rg.k1 = k1; rg.sample_base = sample_base; rg.radiance = sc->d_radiance; rg.count_out = sc->d_counts;
+                launch_bounces(sc, p->max_depth, first, spp, p->seed, &rg);
+            } else {
+                {
+                    KernelSpan span(sc, RT_KCLASS_RAYGEN);
+                    k_raygen<<<sc->grid, 256, 0, sc->stream>>>(rcd, sc->map, first, npx, spp, k0, k1, sc->q[0], sc->d_counts, sc->d_radiance, sc->hq.key, sample_base);
+                }
+                launch_bounces(sc, p->max_depth, first, spp, p->seed);
             }
-            launch_bounces(sc, p->max_depth, first, spp, p->seed);
             {
                 KernelSpan span(sc, RT_KCLASS_RESOLVE);
                 k_resolve<<<(npx + 255) / 256, 256, 0, sc->stream>>>(sc->d_radiance, npx, spp, first, sc->d_accum, sc->d_frame, sample_base != 0);

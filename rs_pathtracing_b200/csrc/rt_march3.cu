@@ -1,4 +1,5 @@
-// rt_march3.cu -- K3 of the wavefront renderer, third generation: exact-skip marching with a POOL OF RAYS PER WARP.
+// rt_march3.cu -- K3 of the wavefront renderer, third generation: exact-skip marching with a POOL OF RAYS PER SM
+// and a work queue per phase.
 //
 // What the profiles of k_march (one ray per lane, rt_march_kernels.cu) say (profiles/r2b_*): 7-13 of 32 lanes
 // active.  Half of its warp instructions are the exact advance of a jump (advance_exact: an accumulator that
@@ -6,20 +7,29 @@
 // at ~6 lanes: the lanes of a warp sit in different phases of their rays, and inside a phase the trip counts of
 // the loops differ by an order of magnitude -- a warp executes the union of all of it.
 //
-// Here a ray is not tied to a lane.  Each warp owns RT_M3_R ray RECORDS in shared memory (35 doubles each: the
-// reference loop's state, the ray's polynomial model, the planned jump) and its 32 lanes are workers: the warp
-// repeatedly picks the phase most of its rays are waiting for and runs that phase's SERVICE over the list of those
-// rays,
+// Here a ray is not tied to a lane, nor to a warp.  One persistent CTA per SM (16 warps) owns RT_M3_R ray RECORDS
+// in shared memory (37 doubles each: the reference loop's state, the ray's polynomial model, the planned jump) and
+// one QUEUE per phase a ray can wait for,
 //     TRANS    finish a marched shape (candidate t against the path's best), start the next one (bound, first
 //              sample, polynomial expansion along the ray) or retire the record and write the path's result
 //     PLAN     how many iterations can provably be skipped (Marcher::plan_*: the hop loop)
-//     ADV      the exact advance of t, p.x, p.y, p.z by that many steps (advance_iter), 4 tasks per ray
+//     ADV      the exact advance of t, p.x, p.y, p.z by that many steps (advance_iter): 4 tasks per ray
 //     LAND     the reference's `r = next` at the landing sample + the model self-check
 //     LIT      the reference's literal steps
-// and the services whose work per ray varies (PLAN: hops, ADV: binades, LIT: steps) hand a lane the NEXT ray of
-// the list the moment it finishes one (dynamic pick-up, one ballot per trip), so that a trip of the loop always
-// runs with as many lanes as there are rays left.  Everything is warp-private: no block barrier, no atomics
-// except the one on the global queue head, no inter-warp waiting.
+// plus the queue of FREE records.  Every warp loops: take the fullest queue and run that phase's SERVICE -- 32 lanes
+// work on 32 queue entries, and in the services whose work per entry varies (PLAN: hops, ADV: binades, LIT: steps)
+// a lane that finishes its entry pops the next one at once (dynamic pick-up), so that a trip of the service loop
+// runs with (nearly) all lanes as long as the queue has entries; a finished entry is pushed to the queue of its
+// next phase, where any warp may pick it up.  A first version with one pool PER WARP (32-96 records) was measured at
+// 7 lanes per instruction in the services: the lists were shorter than the warp (profiles/r2f_*); with ~670
+// records per SM each queue holds hundreds.
+//
+// Synchronisation: the queues are rings in shared memory with atomic head / tail counters; an entry is the record
+// number + 1, 0 = empty slot, written after a __threadfence_block() that orders the record's fields before it and
+// cleared by the consumer.  No block barrier after start-up, no lock; the only waits are for a ring slot that a
+// peer is in the middle of filling or clearing (a handful of instructions), each bounded by a spin limit that
+// raises an error state (reported through rt_stats.verify_false_culls, which every test requires to be 0)
+// instead of hanging.
 //
 // The arithmetic per ray is Marcher's (rt_march.cuh), unchanged: the t this kernel returns is the reference
 // loop's, bit for bit (tests/test_gpu_intersect.py, test_gpu_render.py::test_alternative_schedules_give_the_same_frame
@@ -35,23 +45,21 @@
 #include "rt_queues.cuh"
 
 #ifndef RT_M3_R
-#define RT_M3_R 48          // ray records per warp
+#define RT_M3_R 672         // ray records per CTA (one CTA per SM): 672 x 296 B = 194 KB of the SM's 227 KB
 #endif
-#define RT_M3_RS 35         // doubles per record (odd: consecutive records start in different banks)
-#ifndef RT_M3_WARPS
-#define RT_M3_WARPS 4
+#define RT_M3_RS 37         // doubles per record (odd: consecutive records start in different banks)
+#ifndef RT_M3_THREADS
+#define RT_M3_THREADS 512
 #endif
-#ifndef RT_M3_MIN_BLOCKS
-#define RT_M3_MIN_BLOCKS 4
-#endif
+#define RT_M3_QCAP 1024     // ring capacity of the record queues (power of two >= RT_M3_R)
+#define RT_M3_ACAP 4096     // ring capacity of the ADV task queue (power of two >= 4 RT_M3_R)
 #ifndef RT_M3_LIT_CAP
-#define RT_M3_LIT_CAP 24    // literal steps per LIT service call (a ray that needs thousands must not hold the warp)
+#define RT_M3_LIT_CAP 24    // literal steps per pick-up (a ray that needs thousands goes back to the end of the queue)
 #endif
-#ifndef RT_M3_REFILL_MIN
-#define RT_M3_REFILL_MIN 12 // refill when this many records are free (or nothing is live)
-#endif
+#define RT_M3_SPIN_LIMIT (1 << 22)
+static_assert(RT_M3_R <= RT_M3_QCAP && 4 * RT_M3_R <= RT_M3_ACAP && 4 * RT_M3_R < 65535, "queue capacities");
 
-enum { M3_FREE = 0, M3_TRANS = 1, M3_PLAN = 2, M3_ADV = 3, M3_LAND = 4, M3_LIT = 5, M3_NPH = 6 };
+enum { Q_FREE = 0, Q_TRANS = 1, Q_PLAN = 2, Q_LAND = 3, Q_LIT = 4, Q_ADV = 5, Q_COUNT = 6 };
 
 // record layout (doubles)
 enum {
@@ -59,32 +67,148 @@ enum {
     F_STATE = 12,   // (it | cooldown << 8 | backoff << 16 | flags << 24, evaluations)
     F_PATH = 13,    // (path slot, march-queue entry)
     F_MASK = 14,    // (remaining shape mask, winner)
-    F_SHAPE = 15,   // (march-list index k or 0xffffffff, shape index)
+    F_SHAPE = 15,   // (march-list index k | depth << 8, or 0xffffffff before the first shape; shape index)
     F_C = 16,       // P.c[0..6]
     F_P0 = 23,      // P.p0
     F_ERR0 = 26, F_DRIFT1 = 27,
     F_M = 28, F_MJ = 29,      // the planned jump: uncertainty band, number of iterations
-    F_NT = 30, F_NP = 31,     // its landing sample (34 = one spare)
+    F_NT = 30, F_NP = 31,     // its landing sample
+    F_STEP0 = 34, F_G = 35,   // the shape's step and gradient bound (so that no service starts with a global load)
+    F_SPARE = 36,
 };
 #define M3_FLAG_SKIP_OK 1u
 #define M3_FLAG_MORE 2u
 
-__device__ __forceinline__ uint2 m3_u2(const double* rec, int f) { return *reinterpret_cast<const uint2*>(rec + f); }
-__device__ __forceinline__ void m3_set_u2(double* rec, int f, uint32_t x, uint32_t y) {
-    *reinterpret_cast<uint2*>(rec + f) = make_uint2(x, y);
+// shared memory map (bytes from rt_smem_raw)
+#define M3_OFF_RING16 (RT_M3_R * RT_M3_RS * 8)                       // 5 rings of RT_M3_QCAP uint16
+#define M3_OFF_RINGA (M3_OFF_RING16 + 5 * RT_M3_QCAP * 2)            // ADV ring, RT_M3_ACAP uint16
+#define M3_OFF_CTRL (M3_OFF_RINGA + RT_M3_ACAP * 2)                  // head[6], tail[6], live, exhausted, error, pad
+#define M3_OFF_ADVCNT (M3_OFF_CTRL + 16 * 4)                         // int per record: ADV tasks still running
+#define M3_SMEM_BYTES (M3_OFF_ADVCNT + RT_M3_R * 4)
+
+// Everything in shared memory is addressed THROUGH THE EXTERN ARRAY ITSELF (not through derived pointers), so that
+// the compiler keeps the address space and emits LDS / STS / ATOMS.
+struct Rec {
+    int base;   // index of the record's first double
+    __device__ __forceinline__ double& operator[](int f) const { return reinterpret_cast<double*>(rt_smem_raw)[base + f]; }
+    __device__ __forceinline__ uint2& u2(int f) const { return reinterpret_cast<uint2*>(rt_smem_raw)[base + f]; }
+    __device__ __forceinline__ long long& i64(int f) const { return reinterpret_cast<long long*>(rt_smem_raw)[base + f]; }
+};
+#define REC(slot_) (Rec{(int)(slot_) * RT_M3_RS})
+#define M3_CTRL(i_) (reinterpret_cast<unsigned*>(rt_smem_raw + M3_OFF_CTRL)[i_])
+#define M3_VCTRL(i_) (reinterpret_cast<volatile unsigned*>(rt_smem_raw + M3_OFF_CTRL)[i_])
+#define M3_HEAD(q_) (q_)
+#define M3_TAIL(q_) (6 + (q_))
+#define M3_LIVE 12
+#define M3_EXHAUSTED 13
+#define M3_ERROR 14
+#define M3_ADVCNT(slot_) (reinterpret_cast<int*>(rt_smem_raw + M3_OFF_ADVCNT)[slot_])
+
+__device__ __forceinline__ volatile unsigned short* m3_ring(int q) {
+    return reinterpret_cast<volatile unsigned short*>(rt_smem_raw + (q == Q_ADV ? M3_OFF_RINGA : M3_OFF_RING16 + q * RT_M3_QCAP * 2));
 }
-__device__ __forceinline__ uint8_t m3_phase_of(int ph) {
-    return ph == RT_PHASE_ATTEMPT ? M3_PLAN : ph == RT_PHASE_LITERAL ? M3_LIT : M3_TRANS;
+__device__ __forceinline__ unsigned m3_ring_mask(int q) { return q == Q_ADV ? RT_M3_ACAP - 1 : RT_M3_QCAP - 1; }
+__device__ __forceinline__ int m3_queue_size(int q) { return (int)(M3_VCTRL(M3_TAIL(q)) - M3_VCTRL(M3_HEAD(q))); }
+
+// Warp-collective: the lanes with `wants` try to take one entry each from queue q.  Returns true for the lanes that
+// got one (in `id`).  Never waits for entries that are not there.
+__device__ __forceinline__ bool m3_pop(int q, bool wants, unsigned& id) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned need = __ballot_sync(FULL, wants);
+    if (need == 0) return false;
+    unsigned h = 0;
+    int n = 0;
+    if (lane == 0) {
+        const int want_n = __popc(need);
+        for (int tries = 0; tries < 4; tries++) {
+            const unsigned hh = M3_VCTRL(M3_HEAD(q)), tt = M3_VCTRL(M3_TAIL(q));
+            const int avail = (int)(tt - hh);
+            if (avail <= 0) break;
+            const int k = min(want_n, avail);
+            if (atomicCAS(&M3_CTRL(M3_HEAD(q)), hh, hh + (unsigned)k) == hh) {
+                h = hh;
+                n = k;
+                break;
+            }
+        }
+    }
+    n = __shfl_sync(FULL, n, 0);
+    if (n == 0) return false;
+    h = __shfl_sync(FULL, h, 0);
+    const int rank = __popc(need & ((1u << lane) - 1u));
+    const bool got = wants && rank < n;
+    if (got) {
+        volatile unsigned short* ring = m3_ring(q);
+        const unsigned idx = (h + (unsigned)rank) & m3_ring_mask(q);
+        unsigned v = ring[idx];
+        for (int spin = 0; v == 0 && spin < RT_M3_SPIN_LIMIT; spin++) v = ring[idx];   // the producer is writing it
+        if (v == 0) M3_VCTRL(M3_ERROR) = 1;
+        ring[idx] = 0;
+        id = v - 1u;
+    }
+    __threadfence_block();   // (acquire: the record's fields were written before the entry)
+    return got;
+}
+
+// Warp-collective: the lanes with `valid` append `id` to queue q.
+__device__ __forceinline__ void m3_push(int q, bool valid, unsigned id) {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned m = __ballot_sync(FULL, valid);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    __threadfence_block();   // (release: this lane's writes to the record before the entry)
+    const int leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(&M3_CTRL(M3_TAIL(q)), (unsigned)__popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    if (valid) {
+        volatile unsigned short* ring = m3_ring(q);
+        const unsigned idx = (base + (unsigned)__popc(m & ((1u << lane) - 1u))) & m3_ring_mask(q);
+        int spin = 0;
+        while (ring[idx] != 0 && spin < RT_M3_SPIN_LIMIT) spin++;   // a consumer is still clearing the slot's last entry
+        if (spin >= RT_M3_SPIN_LIMIT) M3_VCTRL(M3_ERROR) = 1;
+        ring[idx] = (unsigned short)(id + 1u);
+    }
+}
+// a ray that goes to ADV: its 4 tasks (record * 4 + component)
+__device__ __forceinline__ void m3_push_adv(bool valid, unsigned slot) {
+    const unsigned FULL = 0xffffffffu;
+    const unsigned m = __ballot_sync(FULL, valid);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    if (valid) M3_ADVCNT(slot) = 4;
+    __threadfence_block();
+    const int leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(&M3_CTRL(M3_TAIL(Q_ADV)), 4u * (unsigned)__popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    if (valid) {
+        volatile unsigned short* ring = m3_ring(Q_ADV);
+        const unsigned first = base + 4u * (unsigned)__popc(m & ((1u << lane) - 1u));
+#pragma unroll
+        for (unsigned c = 0; c < 4; c++) {
+            const unsigned idx = (first + c) & (RT_M3_ACAP - 1);
+            int spin = 0;
+            while (ring[idx] != 0 && spin < RT_M3_SPIN_LIMIT) spin++;
+            if (spin >= RT_M3_SPIN_LIMIT) M3_VCTRL(M3_ERROR) = 1;
+            ring[idx] = (unsigned short)(slot * 4u + c + 1u);
+        }
+    }
+}
+
+__device__ __forceinline__ int m3_queue_of(int ph) {   // Marcher::phase() -> the queue of the service that continues
+    return ph == RT_PHASE_ATTEMPT ? Q_PLAN : ph == RT_PHASE_LITERAL ? Q_LIT : Q_TRANS;
 }
 
 // the loop state literal() / phase() / land touch
 template <int KIND, bool COUNT>
-__device__ __forceinline__ void m3_load_core(const DevScene& S, const double* rec, Marcher<KIND, COUNT>& m, bool& more) {
+__device__ __forceinline__ void m3_load_core(const DevScene& S, Rec rec, Marcher<KIND, COUNT>& m, bool& more) {
     m.t = rec[F_T]; m.r = rec[F_R]; m.step = rec[F_STEP];
     m.p = mk(rec[F_P], rec[F_P + 1], rec[F_P + 2]);
     m.d = mk(rec[F_D], rec[F_D + 1], rec[F_D + 2]);
     m.start = rec[F_START]; m.end = rec[F_END];
-    const uint2 w = m3_u2(rec, F_STATE), ks = m3_u2(rec, F_SHAPE);
+    const uint2 w = rec.u2(F_STATE), ks = rec.u2(F_SHAPE);
     m.it = (int)(w.x & 0xffu);
     m.cooldown = (int)((w.x >> 8) & 0xffu);
     m.backoff = (int)((w.x >> 16) & 0xffu);
@@ -93,24 +217,25 @@ __device__ __forceinline__ void m3_load_core(const DevScene& S, const double* re
     m.have_poly = true;   // (expanded when the shape is started; only read when skip_ok)
     m.n = w.y;
     m.q = S.params + RT_SHAPE_PARAMS * (int)ks.y;
-    m.step0 = m.q[1];
-    m.depth = (int)m.q[2];
+    m.step0 = rec[F_STEP0];
+    m.depth = (int)((ks.x >> 8) & 0xffu);
+    m.G = rec[F_G];
     m.sd = m.step * m.d;
     if (COUNT) m.prof[0] = m.prof[1] = m.prof[2] = m.prof[3] = 0;
 }
 template <int KIND, bool COUNT>
-__device__ __forceinline__ void m3_store_state(double* rec, const Marcher<KIND, COUNT>& m, bool more) {
+__device__ __forceinline__ void m3_store_state(Rec rec, const Marcher<KIND, COUNT>& m, bool more) {
     const uint32_t flags = (m.skip_ok ? M3_FLAG_SKIP_OK : 0u) | (more ? M3_FLAG_MORE : 0u);
     const uint32_t nn = m.n > 0xffffffffull ? 0xffffffffu : (uint32_t)m.n;
-    m3_set_u2(rec, F_STATE, (uint32_t)m.it | ((uint32_t)m.cooldown << 8) | ((uint32_t)m.backoff << 16) | (flags << 24), nn);
+    rec.u2(F_STATE) = make_uint2((uint32_t)m.it | ((uint32_t)m.cooldown << 8) | ((uint32_t)m.backoff << 16) | (flags << 24), nn);
 }
 template <int KIND, bool COUNT>
-__device__ __forceinline__ void m3_store_sample(double* rec, const Marcher<KIND, COUNT>& m) {
+__device__ __forceinline__ void m3_store_sample(Rec rec, const Marcher<KIND, COUNT>& m) {
     rec[F_T] = m.t; rec[F_R] = m.r; rec[F_STEP] = m.step;
     rec[F_P] = m.p.x; rec[F_P + 1] = m.p.y; rec[F_P + 2] = m.p.z;
 }
 template <int KIND, bool COUNT>
-__device__ __forceinline__ void m3_load_poly(const double* rec, Marcher<KIND, COUNT>& m) {
+__device__ __forceinline__ void m3_load_poly(Rec rec, Marcher<KIND, COUNT>& m) {
     constexpr int DEG = Marcher<KIND, COUNT>::DEG;
 #pragma unroll
     for (int i = 0; i <= DEG; i++) m.P.c[i] = rec[F_C + i];
@@ -127,116 +252,113 @@ __device__ __forceinline__ void m3_add_prof(DevCounters& c, const Marcher<KIND, 
     }
 }
 
-// the list of the records in phase `want` (this warp's), in slot order; returns its length
-__device__ __forceinline__ int m3_build_list(const uint8_t* s_ph, uint8_t* s_list, int want, int lane) {
-    int len = 0;
-#pragma unroll
-    for (int row = 0; row < (RT_M3_R + 31) / 32; row++) {
-        const int slot = row * 32 + lane;
-        const bool hit = slot < RT_M3_R && s_ph[slot] == want;
-        const unsigned mask = __ballot_sync(0xffffffffu, hit);
-        if (hit) s_list[len + __popc(mask & ((1u << lane) - 1u))] = (uint8_t)slot;
-        len += __popc(mask);
-    }
-    __syncwarp();
-    return len;
-}
-
 template <int KIND, bool COUNT>
-__global__ void __launch_bounds__(32 * RT_M3_WARPS, RT_M3_MIN_BLOCKS)
+__global__ void __launch_bounds__(RT_M3_THREADS, 1)
 k_march3(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32_t* __restrict__ march_count,
          uint32_t* head, DevCounters* g_counters) {
     typedef Marcher<KIND, COUNT> M;
     constexpr int DEG = M::DEG;
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned lt = (1u << lane) - 1u;
-    double* const recs = reinterpret_cast<double*>(rt_smem_raw) + (size_t)warp * RT_M3_R * RT_M3_RS;
-    uint8_t* const bytes = rt_smem_raw + (size_t)RT_M3_WARPS * RT_M3_R * RT_M3_RS * sizeof(double);
-    uint8_t* const s_ph = bytes + warp * (2 * RT_M3_R);
-    uint8_t* const s_list = s_ph + RT_M3_R;
+    const int lane = threadIdx.x & 31;
     DevCounters c = {};
     const uint32_t n = *march_count;
-    bool exhausted = n == 0;
-    for (int i = lane; i < RT_M3_R; i += 32) s_ph[i] = M3_FREE;
-    __syncwarp();
+    // ---- start-up: every record is free ----------------------------------------------------------------------
+    for (int i = threadIdx.x; i < 5 * RT_M3_QCAP; i += RT_M3_THREADS)
+        reinterpret_cast<unsigned short*>(rt_smem_raw + M3_OFF_RING16)[i] = i < RT_M3_R ? (unsigned short)(i + 1) : 0;
+    for (int i = threadIdx.x; i < RT_M3_ACAP; i += RT_M3_THREADS) reinterpret_cast<unsigned short*>(rt_smem_raw + M3_OFF_RINGA)[i] = 0;
+    if (threadIdx.x < 16) M3_CTRL(threadIdx.x) = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        M3_CTRL(M3_TAIL(Q_FREE)) = RT_M3_R;
+        M3_CTRL(M3_EXHAUSTED) = n == 0 ? 1u : 0u;
+    }
+    __syncthreads();
 
+    unsigned idle_rounds = 0;
     for (;;) {
-        // ---- how many records wait for what (scalar counters: no dynamically indexed local array) ------------
-        int n_free = 0, want = M3_TRANS, want_cnt = 0;
-        unsigned free_mask[(RT_M3_R + 31) / 32];
-        {
-            int ph_row[(RT_M3_R + 31) / 32];
+        // ---- the fullest queue (lane q reads queue q's length) -----------------------------------------------
+        int my_size = lane < Q_COUNT ? m3_queue_size(lane) : 0;
+        if (lane == Q_ADV) my_size = (my_size + 3) >> 2;          // tasks -> rays
+        const int n_free = __shfl_sync(FULL, my_size, Q_FREE);
+        const bool exhausted = M3_VCTRL(M3_EXHAUSTED) != 0;
+        int want = Q_TRANS, want_size = __shfl_sync(FULL, my_size, Q_TRANS);
 #pragma unroll
-            for (int row = 0; row < (RT_M3_R + 31) / 32; row++) {
-                const int slot = row * 32 + lane;
-                ph_row[row] = slot < RT_M3_R ? (int)s_ph[slot] : -1;
-                free_mask[row] = __ballot_sync(FULL, ph_row[row] == M3_FREE);
-                n_free += __popc(free_mask[row]);
-            }
-#pragma unroll
-            for (int k = M3_TRANS; k < M3_NPH; k++) {
-                int ck = 0;
-#pragma unroll
-                for (int row = 0; row < (RT_M3_R + 31) / 32; row++) ck += __popc(__ballot_sync(FULL, ph_row[row] == k));
-                if (ck > want_cnt) {   // the phase most records wait for (ties: the earlier phase)
-                    want_cnt = ck;
-                    want = k;
-                }
+        for (int q = Q_PLAN; q < Q_COUNT; q++) {
+            const int sz = __shfl_sync(FULL, my_size, q);
+            if (sz > want_size) {
+                want_size = sz;
+                want = q;
             }
         }
-        const int live = RT_M3_R - n_free;
-        // ---- refill the free records from the march queue --------------------------------------------------
-        if (!exhausted && n_free > 0 && (live == 0 || n_free >= RT_M3_REFILL_MIN)) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(head, (uint32_t)n_free);
-            base = __shfl_sync(FULL, base, 0);
-            int before = 0;
-#pragma unroll
-            for (int row = 0; row < (RT_M3_R + 31) / 32; row++) {
-                const int slot = row * 32 + lane;
-                if ((free_mask[row] >> lane) & 1u) {
-                    const uint32_t j = base + (uint32_t)(before + __popc(free_mask[row] & lt));
+        // ---- refill free records from the march queue: whenever a warp's worth is free, or nothing else to do ---
+        if (!exhausted && n_free > 0 && (n_free >= 32 || want_size == 0)) {
+            unsigned slot = 0;
+            const bool got = m3_pop(Q_FREE, true, slot);
+            const unsigned gm = __ballot_sync(FULL, got);
+            if (gm != 0) {
+                const int k = __popc(gm);
+                uint32_t base = 0;
+                if (lane == 0) {
+                    atomicAdd(&M3_CTRL(M3_LIVE), (unsigned)k);
+                    base = atomicAdd(head, (uint32_t)k);
+                }
+                base = __shfl_sync(FULL, base, 0);
+                bool filled = false;
+                if (got) {
+                    const uint32_t j = base + (uint32_t)__popc(gm & ((1u << lane) - 1u));
                     if (j < n) {
                         const uint32_t mask = hq.mq_mask[j] & kind_mask;
                         if (mask != 0) {
                             const uint32_t pslot = hq.mq_slot[j];
-                            double* rec = recs + slot * RT_M3_RS;
+                            const Rec rec = REC(slot);
                             rec[F_BEST] = hq.t[pslot];
-                            m3_set_u2(rec, F_PATH, pslot, j);
-                            m3_set_u2(rec, F_MASK, mask, (uint32_t)hq.index[pslot]);
-                            m3_set_u2(rec, F_SHAPE, 0xffffffffu, 0u);
-                            s_ph[slot] = M3_TRANS;
+                            rec.u2(F_PATH) = make_uint2(pslot, j);
+                            rec.u2(F_MASK) = make_uint2(mask, (uint32_t)hq.index[pslot]);
+                            rec.u2(F_SHAPE) = make_uint2(0xffffffffu, 0u);
+                            filled = true;
                         }
                     }
                 }
-                before += __popc(free_mask[row]);
+                const unsigned back = __ballot_sync(FULL, got && !filled);
+                if (base + (uint32_t)k >= n && lane == 0) M3_VCTRL(M3_EXHAUSTED) = 1;
+                m3_push(Q_TRANS, filled, slot);
+                m3_push(Q_FREE, got && !filled, slot);
+                if (back != 0 && lane == 0) atomicSub(&M3_CTRL(M3_LIVE), (unsigned)__popc(back));
             }
-            if (base + (uint32_t)n_free >= n) exhausted = true;
-            __syncwarp();
+            idle_rounds = 0;
             continue;
         }
-        if (live == 0) break;   // (exhausted)
-        const int len = m3_build_list(s_ph, s_list, want, lane);
+        if (want_size == 0) {
+            if (exhausted && M3_VCTRL(M3_LIVE) == 0) break;
+            if (M3_VCTRL(M3_ERROR) != 0 || ++idle_rounds > (1u << 24)) {   // never hang: give up loudly
+                M3_VCTRL(M3_ERROR) = 1;
+                break;
+            }
+            __nanosleep(400);
+            continue;
+        }
+        idle_rounds = 0;
 
-        if (want == M3_TRANS) {
+        if (want == Q_TRANS) {
             // ---- finish a marched shape / start the next one / retire the record ---------------------------
-            for (int base = 0; base < len; base += 32) {
-                const int idx = base + lane;
-                if (idx < len) {
-                    const int slot = s_list[idx];
-                    double* rec = recs + slot * RT_M3_RS;
-                    const uint2 pe = m3_u2(rec, F_PATH), mw = m3_u2(rec, F_MASK), ks = m3_u2(rec, F_SHAPE);
+            for (;;) {
+                unsigned slot = 0;
+                const bool got = m3_pop(Q_TRANS, true, slot);
+                if (__ballot_sync(FULL, got) == 0) break;
+                int dest = -1;   // queue the record goes to next
+                if (got) {
+                    const Rec rec = REC(slot);
+                    const uint2 pe = rec.u2(F_PATH), mw = rec.u2(F_MASK), ks = rec.u2(F_SHAPE);
                     const uint32_t pslot = pe.x, entry = pe.y;
                     uint32_t mask = mw.x;
                     int winner = (int)mw.y;
                     double best = rec[F_BEST];
                     bool retired = false;
                     if (ks.x != 0xffffffffu) {   // a shape has just been marched to its end
-                        const uint2 w = m3_u2(rec, F_STATE);
+                        const uint2 w = rec.u2(F_STATE);
                         const int it = (int)(w.x & 0xffu);
                         const int shape = (int)ks.y;
-                        const int depth = (int)S.params[RT_SHAPE_PARAMS * shape + 2];
+                        const int depth = (int)((ks.x >> 8) & 0xffu);
                         const double t = rec[F_T];
                         if (COUNT) {
                             c.march_steps += w.y;
@@ -254,8 +376,7 @@ k_march3(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32
                             }
                         }
                     }
-                    bool started = false;
-                    while (!retired && mask != 0 && !started) {
+                    while (!retired && mask != 0 && dest < 0) {
                         const int k = __ffs(mask) - 1;
                         mask &= mask - 1;
                         const int shape = S.march_index[k];
@@ -279,100 +400,104 @@ k_march3(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32
                             m3_store_sample(rec, m);
                             rec[F_D] = m.d.x; rec[F_D + 1] = m.d.y; rec[F_D + 2] = m.d.z;
                             rec[F_START] = m.start; rec[F_END] = m.end;
+                            rec[F_STEP0] = m.step0; rec[F_G] = m.G;
                             m3_store_state(rec, m, false);
-                            m3_set_u2(rec, F_SHAPE, (uint32_t)k, (uint32_t)shape);
-                            s_ph[slot] = m3_phase_of(m.phase());
-                            started = true;
+                            rec.u2(F_SHAPE) = make_uint2((uint32_t)k | ((uint32_t)(m.depth & 0xff) << 8), (uint32_t)shape);
+                            dest = m3_queue_of(m.phase());
                         }
                     }
-                    if (started) {
+                    if (dest >= 0) {
                         rec[F_BEST] = best;
-                        m3_set_u2(rec, F_MASK, mask, (uint32_t)winner);
+                        rec.u2(F_MASK) = make_uint2(mask, (uint32_t)winner);
                     } else {
                         if (!retired) {
                             hq.t[pslot] = best;
                             hq.index[pslot] = winner;
                         }
-                        s_ph[slot] = M3_FREE;
+                        dest = Q_FREE;
                     }
                 }
+                const unsigned freed = __ballot_sync(FULL, dest == Q_FREE);
+                m3_push(Q_PLAN, dest == Q_PLAN, slot);
+                m3_push(Q_LIT, dest == Q_LIT, slot);
+                m3_push(Q_TRANS, dest == Q_TRANS, slot);
+                m3_push(Q_FREE, dest == Q_FREE, slot);
+                if (freed != 0 && lane == 0) atomicSub(&M3_CTRL(M3_LIVE), (unsigned)__popc(freed));
             }
-        } else if (want == M3_PLAN) {
-            // ---- jump planning: one hop per trip, a lane that finishes its ray picks up the next of the list ---
+        } else if (want == Q_PLAN) {
+            // ---- jump planning: one hop per trip; a lane that finishes its ray pops the next one --------------
             M m;
             typename M::Plan pl;
             bool has = false, more_dummy;
-            int slot = 0, next = 0;
+            unsigned slot = 0;
             for (;;) {
-                const unsigned need = __ballot_sync(FULL, !has);
-                if (next < len && need) {
-                    const int idx = next + __popc(need & lt);
-                    if (!has && idx < len) {
-                        slot = s_list[idx];
-                        const double* rec = recs + slot * RT_M3_RS;
-                        m3_load_core(S, rec, m, more_dummy);
-                        const uint2 ks = m3_u2(rec, F_SHAPE);
-                        m.G = S.march_G[ks.x];
-                        m.F = S.march_F[ks.x];
-                        m3_load_poly(rec, m);
-                        m.plan_begin(pl);
-                        has = true;
-                    }
-                    next = min(len, next + __popc(need));
+                unsigned id = 0;
+                if (m3_pop(Q_PLAN, !has, id)) {
+                    slot = id;
+                    const Rec rec = REC(slot);
+                    m3_load_core(S, rec, m, more_dummy);
+                    m3_load_poly(rec, m);
+                    m.plan_begin(pl);
+                    has = true;
                 }
                 if (__ballot_sync(FULL, has) == 0) break;
+                int dest = -1;
                 if (has && !m.plan_hop(pl)) {
                     const long long mj = m.plan_end(pl);
-                    double* rec = recs + slot * RT_M3_RS;
+                    const Rec rec = REC(slot);
                     rec[F_M] = pl.M;
-                    *reinterpret_cast<long long*>(rec + F_MJ) = mj;
+                    rec.i64(F_MJ) = mj;
                     m3_store_state(rec, m, pl.more);   // (cooldown / backoff when nothing can be skipped)
-                    s_ph[slot] = mj > 0 ? M3_ADV : m3_phase_of(m.phase());
+                    dest = mj > 0 ? Q_ADV : m3_queue_of(m.phase());
                     m3_add_prof(c, m);
                     has = false;
                 }
+                if (__ballot_sync(FULL, dest >= 0) != 0) {
+                    m3_push_adv(dest == Q_ADV, slot);
+                    m3_push(Q_LIT, dest == Q_LIT, slot);
+                    m3_push(Q_TRANS, dest == Q_TRANS, slot);
+                }
             }
-        } else if (want == M3_ADV) {
-            // ---- the exact advance: 4 tasks per ray (t, p.x, p.y, p.z), one binade per trip, dynamic pick-up ---
-            const int tasks = 4 * len;
+        } else if (want == Q_ADV) {
+            // ---- the exact advance: one task = one accumulator of one ray, one binade per trip ----------------
             double res = 0.0, s = 0.0;
             long long left = 0;
             bool has = false;
-            int slot = 0, comp = 0, next = 0;
+            unsigned slot = 0, comp = 0;
             for (;;) {
-                const unsigned need = __ballot_sync(FULL, !has);
-                if (next < tasks && need) {
-                    const int id = next + __popc(need & lt);
-                    if (!has && id < tasks) {
-                        slot = s_list[id >> 2];
-                        comp = id & 3;
-                        const double* rec = recs + slot * RT_M3_RS;
-                        const double step = rec[F_STEP];
-                        res = comp == 0 ? rec[F_T] : rec[F_P + comp - 1];
-                        s = comp == 0 ? step : rec[F_D + comp - 1] * step;   // `step * dir` (Marcher::sd)
-                        left = *reinterpret_cast<const long long*>(rec + F_MJ);
-                        has = true;
-                    }
-                    next = min(tasks, next + __popc(need));
+                unsigned id = 0;
+                if (m3_pop(Q_ADV, !has, id)) {
+                    slot = id >> 2;
+                    comp = id & 3u;
+                    const Rec rec = REC(slot);
+                    const double step = rec[F_STEP];
+                    res = comp == 0 ? rec[F_T] : rec[F_P + comp - 1];
+                    s = comp == 0 ? step : rec[F_D + comp - 1] * step;   // `step * dir` (Marcher::sd)
+                    left = rec.i64(F_MJ);
+                    has = true;
                 }
                 if (__ballot_sync(FULL, has) == 0) break;
+                bool last = false;
                 if (has) {
                     advance_iter(res, s, left);
                     if (left <= 0) {
-                        recs[slot * RT_M3_RS + F_NT + comp] = res;
+                        REC(slot)[F_NT + comp] = res;
+                        __threadfence_block();
+                        last = atomicSub(&M3_ADVCNT(slot), 1) == 1;   // the ray's fourth accumulator has arrived
                         has = false;
                     }
                 }
+                m3_push(Q_LAND, last, slot);
             }
-            __syncwarp();
-            for (int idx = lane; idx < len; idx += 32) s_ph[s_list[idx]] = M3_LAND;
-        } else if (want == M3_LAND) {
+        } else if (want == Q_LAND) {
             // ---- the reference's `r = next` at the landing sample + the model self-check --------------------
-            for (int base = 0; base < len; base += 32) {
-                const int idx = base + lane;
-                if (idx < len) {
-                    const int slot = s_list[idx];
-                    double* rec = recs + slot * RT_M3_RS;
+            for (;;) {
+                unsigned slot = 0;
+                const bool got = m3_pop(Q_LAND, true, slot);
+                if (__ballot_sync(FULL, got) == 0) break;
+                int dest = -1;
+                if (got) {
+                    const Rec rec = REC(slot);
                     M m;
                     bool more;
                     m3_load_core(S, rec, m, more);
@@ -398,80 +523,78 @@ k_march3(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32
                         m.skip_ok = false;   // the model does not describe this ray: finish it with the plain loop
                     }
                     m3_store_state(rec, m, false);
-                    s_ph[slot] = m3_phase_of(m.phase());
+                    dest = m3_queue_of(m.phase());
                 }
+                m3_push(Q_PLAN, dest == Q_PLAN, slot);
+                m3_push(Q_LIT, dest == Q_LIT, slot);
+                m3_push(Q_TRANS, dest == Q_TRANS, slot);
             }
         } else {
-            // ---- the reference's literal steps: one per trip, dynamic pick-up, at most RT_M3_LIT_CAP trips -------
+            // ---- the reference's literal steps: one per trip, at most RT_M3_LIT_CAP per pick-up ------------------
             M m;
             bool has = false, more_dummy;
-            int slot = 0, next = 0;
-            for (int trip = 0;; trip++) {
-                const unsigned need = __ballot_sync(FULL, !has);
-                if (next < len && need && trip < RT_M3_LIT_CAP) {
-                    const int idx = next + __popc(need & lt);
-                    if (!has && idx < len) {
-                        slot = s_list[idx];
-                        m3_load_core(S, recs + slot * RT_M3_RS, m, more_dummy);
-                        has = true;
-                    }
-                    next = min(len, next + __popc(need));
+            unsigned slot = 0;
+            int steps = 0;
+            for (;;) {
+                unsigned id = 0;
+                if (m3_pop(Q_LIT, !has, id)) {
+                    slot = id;
+                    m3_load_core(S, REC(slot), m, more_dummy);
+                    steps = 0;
+                    has = true;
                 }
                 if (__ballot_sync(FULL, has) == 0) break;
+                int dest = -1;
                 if (has) {
                     m.literal();
                     const int ph = m.phase();
-                    if (ph != RT_PHASE_LITERAL || trip + 1 >= RT_M3_LIT_CAP) {
-                        double* rec = recs + slot * RT_M3_RS;
+                    if (ph != RT_PHASE_LITERAL || ++steps >= RT_M3_LIT_CAP) {
+                        const Rec rec = REC(slot);
                         m3_store_sample(rec, m);
                         m3_store_state(rec, m, false);
-                        s_ph[slot] = m3_phase_of(ph);
+                        dest = m3_queue_of(ph);
                         m3_add_prof(c, m);
-                        if (COUNT) m.prof[0] = m.prof[1] = 0;
                         has = false;
                     }
                 }
-                if (trip + 1 >= RT_M3_LIT_CAP) break;
+                if (__ballot_sync(FULL, dest >= 0) != 0) {
+                    m3_push(Q_PLAN, dest == Q_PLAN, slot);
+                    m3_push(Q_TRANS, dest == Q_TRANS, slot);
+                    m3_push(Q_LIT, dest == Q_LIT, slot);
+                }
             }
         }
-        __syncwarp();
     }
+    // loud: every test requires verify_false_culls == 0
+    if (M3_VCTRL(M3_ERROR) != 0 && threadIdx.x == 0) atomicAdd(&g_counters->verify_false_culls, 1ull << 40);
     if (COUNT) flush_counters(c, g_counters);
 }
 
-static size_t march3_smem() {
-    return (size_t)RT_M3_WARPS * RT_M3_R * RT_M3_RS * sizeof(double) + (size_t)RT_M3_WARPS * 2 * RT_M3_R + 16;
-}
-
 template <int K_>
-static int occupancy3() {
-    const size_t smem = march3_smem();
-    cudaFuncSetAttribute(k_march3<K_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(k_march3<K_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    int b = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_march3<K_, false>, 32 * RT_M3_WARPS, smem);
-    return b;
+static void prepare3() {
+    cudaFuncSetAttribute(k_march3<K_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M3_SMEM_BYTES);
+    cudaFuncSetAttribute(k_march3<K_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M3_SMEM_BYTES);
 }
 
 int rt_march3_occupancy(size_t* smem3) {
-    *smem3 = march3_smem();
-    int b = occupancy3<RT_SURF_HEART>();
-    b = std::min(b, occupancy3<RT_SURF_SINE>());
-    b = std::min(b, occupancy3<RT_SURF_STAR>());
-    b = std::min(b, occupancy3<RT_SURF_DUPIN>());
-    b = std::min(b, occupancy3<RT_SURF_HUNTS>());
-    b = std::min(b, occupancy3<RT_SURF_CUSHION>());
-    return std::max(b, 1);
+    *smem3 = M3_SMEM_BYTES;
+    prepare3<RT_SURF_HEART>();
+    prepare3<RT_SURF_SINE>();
+    prepare3<RT_SURF_STAR>();
+    prepare3<RT_SURF_DUPIN>();
+    prepare3<RT_SURF_HUNTS>();
+    prepare3<RT_SURF_CUSHION>();
+    return 1;   // one persistent CTA per SM
 }
 
 template <int K_>
 static void launch3(const MarchLaunch& ml) {
     if (ml.count)
-        k_march3<K_, true><<<ml.grid3, 32 * RT_M3_WARPS, ml.smem3, ml.stream>>>(ml.ds, ml.kind_mask, ml.in, ml.hq, ml.march_count,
-                                                                               ml.head, ml.counters);
+        k_march3<K_, true><<<ml.grid3, RT_M3_THREADS, ml.smem3, ml.stream>>>(ml.ds, ml.kind_mask, ml.in, ml.hq, ml.march_count,
+                                                                            ml.head, ml.counters);
     else
-        k_march3<K_, false><<<ml.grid3, 32 * RT_M3_WARPS, ml.smem3, ml.stream>>>(ml.ds, ml.kind_mask, ml.in, ml.hq, ml.march_count,
-                                                                                ml.head, ml.counters);
+        k_march3<K_, false><<<ml.grid3, RT_M3_THREADS, ml.smem3, ml.stream>>>(ml.ds, ml.kind_mask, ml.in, ml.hq, ml.march_count,
+                                                                             ml.head, ml.counters);
 }
 
 void rt_launch_march3(const MarchLaunch& ml) {

@@ -1,4 +1,4 @@
-//! `src/renderer/gpu.rs` for the `ray_tracing` crate: the GPU drop-in for `step_by_step::ThreadPoolRenderer`
+//! `src/renderer/gpu.rs` (new file of the patch): the GPU drop-in for `step_by_step::ThreadPoolRenderer`
 //! (src/renderer/step_by_step.rs:37-121) behind `pub trait Renderer` (src/renderer/mod.rs:47-56).
 //! UNCOMPILED (no Rust toolchain in the authoring image); the tested equivalent is
 //! `renderer::GpuRenderer` in rs_pathtracing_b200/csrc/host/ray_tracing.cpp.
@@ -10,21 +10,8 @@ use crate::{
     algebra::Vector3d,
     camera::{ray_caster::ImageParams, Camera},
     renderer::Renderer,
-    world::Scene,
+    world::{flat::FlatScene, Scene},
 };
-
-/// Flat structure-of-arrays description of `Scene.world`, filled by `Describe::describe` on every shape
-/// after `add_random_spheres` (src/world/json_models.rs:44).  Rows 0..2 of
-/// `InversableTransform.{direct, inverse}` (src/algebra/transform.rs:16-23) go in verbatim.
-#[derive(Default)]
-pub struct FlatScene {
-    pub kind: Vec<u8>, pub flags: Vec<u8>,
-    pub inverse: Vec<f64>, pub direct: Vec<f64>, pub params: Vec<f64>, pub material: Vec<u32>,
-    pub materials: Vec<sys::rt_material>, pub textures: Vec<sys::rt_texture>,
-    pub images: Vec<(u32, u32, Vec<u8>)>, pub noise: Vec<sys::rt_perlin>,
-}
-/// implemented by Sphere, Cube, Rectangle, RayMarchingShape (+ each ShapeFunction), every Material and Texture
-pub trait Describe { fn describe(&self, flat: &mut FlatScene); }
 
 fn v(a: &Vector3d) -> sys::rt_vec3 { sys::rt_vec3 { x: a.x, y: a.y, z: a.z } }
 fn check(rc: i32) { if rc != sys::RT_OK { panic!("rt_b200: {}", sys::last_error()) } }  // the reference unwraps too
@@ -33,22 +20,19 @@ pub struct GpuRenderer { scene: *mut sys::rt_scene, depth: u32, seed: u64, progr
 
 impl GpuRenderer {
     /// same constructor convention as ThreadPoolRenderer::new (step_by_step.rs:37); `thread_number` is ignored
-    pub fn new(scene: Arc<RwLock<Scene>>, _thread_number: u32, depth: u32) -> Self {
+    pub fn new(scene: Arc<RwLock<Scene>>, thread_number: u32, depth: u32) -> Self {
+        Self::with_devices(scene, thread_number, depth, &[0])
+    }
+    /// the same renderer over several GPUs of the box: ONE handle (rt_scene_create_multi), frames sharded by
+    /// interleaved tiles over all of them, the assembled frame identical to the single-GPU one
+    pub fn with_devices(scene: Arc<RwLock<Scene>>, _thread_number: u32, depth: u32, devices: &[i32]) -> Self {
         let s = scene.read().unwrap();
         let f: &FlatScene = s.flat();
-        let images: Vec<sys::rt_image> = f.images.iter()
-            .map(|(w, h, px)| sys::rt_image { width: *w, height: *h, rgba: px.as_ptr() }).collect();
-        let desc = sys::rt_scene_desc {
-            n_shapes: f.kind.len() as u32, kind: f.kind.as_ptr(), flags: f.flags.as_ptr(),
-            inverse: f.inverse.as_ptr(), direct: f.direct.as_ptr(), params: f.params.as_ptr(),
-            material: f.material.as_ptr(),
-            n_materials: f.materials.len() as u32, materials: f.materials.as_ptr(),
-            n_textures: f.textures.len() as u32, textures: f.textures.as_ptr(),
-            n_images: images.len() as u32, images: images.as_ptr(),
-            n_noise: f.noise.len() as u32, noise: f.noise.as_ptr(),
-        };
+        let mut images = Vec::new();
+        let desc = f.desc(&mut images);
         let mut h = std::ptr::null_mut();
-        check(unsafe { sys::rt_scene_create(&desc, 0, &mut h) });   // copies the description
+        // (the library copies the description)
+        check(unsafe { sys::rt_scene_create_multi(&desc, devices.len() as i32, devices.as_ptr(), &mut h) });
         GpuRenderer { scene: h, depth, seed: 0, progressive: false }
     }
     /// Progressive accumulation (rt_render_set_accumulate): while on, start_rendering calls with an unchanged

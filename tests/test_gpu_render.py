@@ -309,17 +309,17 @@ def test_work_counters_match_oracle():
 @pytest.mark.parametrize("name", ["spheres.json", "cornell_box.json", "dupin.json", "detached_materials.json",
                                   "light_source.json"])
 def test_alternative_schedules_give_the_same_frame(monkeypatch, name):
-    """the marching result does not depend on how the work is scheduled: the default is the pooled marcher k_march3
-    (a pool of rays per warp, dynamic pick-up inside every variable-length loop); the one-ray-per-lane marcher k_march
-    (RT_B200_MARCH=1, also with other voting thresholds), the block-local wavefront marcher k_march2 (RT_B200_MARCH=2)
-    and the fused k_bounce (RT_B200_FUSED_BOUNCE) reproduce the default frame bit for bit; so do the flat list without its
+    """the marching result does not depend on how the work is scheduled: the default is the one-ray-per-lane marcher
+    k_march; the pooled marcher k_march3 (RT_B200_MARCH=3: a pool of ray records per SM, a queue per phase, dynamic
+    pick-up inside every variable-length loop), the block-local wavefront marcher k_march2 (RT_B200_MARCH=2), other
+    k_march voting thresholds and the fused k_bounce (RT_B200_FUSED_BOUNCE) reproduce the default frame bit for bit; so do the flat list without its
     staged records (RT_B200_NO_FLAT_REC) and marching-bound tests deferred to k_march (RT_B200_DEFER_BOUND).
     The fused k_bounce draws random_in_unit_sphere with the sequential rejection loop and the default k_shade
     warp-cooperatively, so this also pins the cooperative sampler to the sequential one"""
     w, h, spp, depth, seed = 96, 72, 4, 8, 21
     sc = rt.Scene.from_file(scene_path(name), random_spheres_seed=1)
     ref = gpu_frame(sc, sc.camera(), w, h, spp, depth, seed)
-    for var, val in (("RT_B200_MARCH", "1"), ("RT_B200_MARCH", "2"), ("RT_B200_FUSED_BOUNCE", "1"),
+    for var, val in (("RT_B200_MARCH", "3"), ("RT_B200_MARCH", "2"), ("RT_B200_FUSED_BOUNCE", "1"),
                      ("RT_B200_MARCH_TUNE", "2,30,3"),
                      ("RT_B200_NO_CULL_TREE", "1"), ("RT_B200_NO_MARCH_SKIP", "1"), ("RT_B200_NO_FLAT_REC", "1"),
                      ("RT_B200_DEFER_BOUND", "1")):
