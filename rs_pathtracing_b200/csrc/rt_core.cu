@@ -444,70 +444,146 @@ k_replay(DevScene S, PathQueue in, HitQueue hq, const uint32_t* __restrict__ rep
     }
 }
 
+// One path segment's shade step: slot i of the input queue when `valid` (all 32 lanes of a warp call this together:
+// the unit-ball sample is drawn warp-cooperatively and the survivors are appended with one atomic per warp).
+__device__ __forceinline__ void shade_slot(const DevScene& S, const PathQueue& in, const HitQueue& hq, const PathQueue& out,
+                                           uint32_t* count_out, uint32_t level, uint32_t max_depth, uint32_t k0, uint32_t k1,
+                                           float4* __restrict__ radiance, uint4* s_id, uint32_t i, bool valid) {
+    bool alive = false, shading = false, need_ball = false, dead = false;
+    D3 no = mk(0, 0, 0), nd = mk(0, 0, 0), nb = mk(0, 0, 0);
+    D3 rd = mk(0, 0, 0), beta = mk(0, 0, 0), L = mk(0.0, 0.0, 0.0);
+    uint32_t pid = 0;
+    HitRec h;
+    PathRng rng;
+    rng.k0 = k0; rng.k1 = k1;
+    rng.pixel = 0; rng.sample = 0;
+    rng.begin_event(level + 1);
+    if (valid) {
+        rd = mk(in.dx[i], in.dy[i], in.dz[i]);
+        beta = mk(in.bx[i], in.by[i], in.bz[i]);
+        pid = in.pid[i];
+        const int bi = hq.index[i];
+        if (bi == RT_HIT_DEAD) {
+            dead = true;   // padding pixel of a clipped border tile (k_extend, RAYGEN): no path
+        } else if (bi < 0) {
+            L = hadamard(beta, sky(rd));  // renderer/mod.rs:41-43
+        } else if (level == max_depth) {
+            // depth == 0: black (:26-27)
+        } else {
+            D3 ro = mk(in.ox[i], in.oy[i], in.oz[i]);
+            const rt_material mat = S.materials[S.material[bi]];
+            finalize_hit(S, bi, hq.t[i], ro, rd, h, material_reads_uv(S, mat));
+            const uint2 key = hq.key[pid];
+            rng.pixel = key.x;
+            rng.sample = key.y;
+            shading = true;
+            need_ball = material_needs_ball(mat);
+        }
+    }
+    const D3 ball = coop_random_in_unit_sphere(need_ball, rng.pixel, rng.sample, level + 1, k0, k1, s_id);
+    if (shading) {
+        D3 ndir, atten;
+        if (scatter_or_emit(S, h, rd, rng, ndir, atten, &ball)) {  // :29-32
+            alive = true;
+            no = h.point;
+            nd = ndir;
+            nb = hadamard(beta, atten);
+        } else {
+            L = hadamard(beta, atten);  // :34-36
+        }
+    }
+    if (valid && !alive && !dead) radiance[pid] = make_float4((float)L.x, (float)L.y, (float)L.z, 1.0f);
+    uint32_t slot = queue_append(alive, count_out);
+    if (alive) {
+        out.ox[slot] = no.x; out.oy[slot] = no.y; out.oz[slot] = no.z;
+        out.dx[slot] = nd.x; out.dy[slot] = nd.y; out.dz[slot] = nd.z;
+        out.bx[slot] = nb.x; out.by[slot] = nb.y; out.bz[slot] = nb.z;
+        out.pid[slot] = pid;
+    }
+}
+
+// K4.  BINNED = the SHADE QUEUE KEYED BY MATERIAL AND TEXTURE: the reference's 5-way Material dispatch
+// (src/world/material.rs:22-31) times the nested Texture::value (src/world/texture.rs:5-8) is the divergence source of
+// this kernel -- in arrival order a warp of a scene with many material kinds executes the union of their branches.
+// A block therefore takes RT_SHADE_CHUNK consecutive slots, bins them in shared memory by the winner's shade key
+// (0 = miss -> sky; 1 + S.mat_bin[material]: one bin per (material kind, root texture kind) pair present in the scene;
+// dead slots dropped) -- a counting sort with BLOCK-AGGREGATED counters: lanes with the same key are matched inside
+// the warp (__match_any_sync) and one shared-memory atomic per (warp, key) reserves their places -- and shades the
+// slots in binned order, so that all but the few warps at a bin boundary run one branch.  The paths' results do not
+// depend on the order (every random draw is keyed by the path), so the frame is bit-identical to the unbinned one.
 // (64 registers / 4 CTAs per SM was measured: spills, 1.44 -> 1.64 ms per 4 Mi paths)
-template <bool COUNT>
-__global__ void __launch_bounds__(256)
+#define RT_SHADE_CHUNK 1024
+#define RT_SHADE_MAX_BINS 32
+// 3 CTAs per SM (<= 85 registers: the kernel needed 80 before it grew the dead-slot and binning paths; at 102 it fell
+// to 2 CTAs per SM and lost 20 %)
+template <bool COUNT, bool BINNED>
+__global__ void __launch_bounds__(256, 3)
 k_shade(DevScene S, PathQueue in, const uint32_t* __restrict__ count_in, HitQueue hq, PathQueue out, uint32_t* count_out,
         uint32_t level, uint32_t max_depth, ShardMap map, unsigned long long first_owned, uint32_t spp, uint32_t k0,
         uint32_t k1, float4* __restrict__ radiance) {
     const uint32_t n = *count_in;
-    const uint32_t n_round = (n + 31u) & ~31u;
-    const uint32_t stride = gridDim.x * blockDim.x;
     // random_in_unit_sphere is drawn by the whole warp for its rejected lanes (coop_random_in_unit_sphere)
     __shared__ uint4 s_ball_id[256];
     uint4* const s_id = s_ball_id + (threadIdx.x & ~31u);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-        bool alive = false, shading = false, need_ball = false, dead = false;
-        D3 no = mk(0, 0, 0), nd = mk(0, 0, 0), nb = mk(0, 0, 0);
-        D3 rd = mk(0, 0, 0), beta = mk(0, 0, 0), L = mk(0.0, 0.0, 0.0);
-        uint32_t pid = 0;
-        HitRec h;
-        PathRng rng;
-        rng.k0 = k0; rng.k1 = k1;
-        rng.pixel = 0; rng.sample = 0;
-        rng.begin_event(level + 1);
-        if (i < n) {
-            rd = mk(in.dx[i], in.dy[i], in.dz[i]);
-            beta = mk(in.bx[i], in.by[i], in.bz[i]);
-            pid = in.pid[i];
-            const int bi = hq.index[i];
-            if (bi == RT_HIT_DEAD) {
-                dead = true;   // padding pixel of a clipped border tile (k_extend, RAYGEN): no path
-            } else if (bi < 0) {
-                L = hadamard(beta, sky(rd));  // renderer/mod.rs:41-43
-            } else if (level == max_depth) {
-                // depth == 0: black (:26-27)
-            } else {
-                D3 ro = mk(in.ox[i], in.oy[i], in.oz[i]);
-                const rt_material mat = S.materials[S.material[bi]];
-                finalize_hit(S, bi, hq.t[i], ro, rd, h, material_reads_uv(S, mat));
-                const uint2 key = hq.key[pid];
-                rng.pixel = key.x;
-                rng.sample = key.y;
-                shading = true;
-                need_ball = material_needs_ball(mat);
+    if (!BINNED) {
+        const uint32_t n_round = (n + 31u) & ~31u;
+        const uint32_t stride = gridDim.x * blockDim.x;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride)
+            shade_slot(S, in, hq, out, count_out, level, max_depth, k0, k1, radiance, s_id, i, i < n);
+        return;
+    }
+    __shared__ uint16_t s_order[RT_SHADE_CHUNK];
+    __shared__ uint32_t s_count[RT_SHADE_MAX_BINS + 1], s_cursor[RT_SHADE_MAX_BINS + 1];
+    __shared__ uint32_t s_total;
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t chunk0 = blockIdx.x * RT_SHADE_CHUNK; chunk0 < n; chunk0 += gridDim.x * RT_SHADE_CHUNK) {
+        if (threadIdx.x <= RT_SHADE_MAX_BINS) s_count[threadIdx.x] = 0;
+        __syncthreads();
+        // ---- keys + histogram: one shared atomic per (warp, key) -------------------------------------------
+        int key[RT_SHADE_CHUNK / 256];
+#pragma unroll
+        for (int r = 0; r < RT_SHADE_CHUNK / 256; r++) {
+            const uint32_t i = chunk0 + r * 256 + threadIdx.x;
+            int k = -1;
+            if (i < n) {
+                const int bi = hq.index[i];
+                if (bi != RT_HIT_DEAD) k = bi < 0 ? 0 : 1 + (int)S.mat_bin[S.material[bi]];
             }
+            key[r] = k;
+            const unsigned peers = __match_any_sync(FULL, k);
+            if (k >= 0 && lane == __ffs(peers) - 1) atomicAdd(&s_count[k], (uint32_t)__popc(peers));
         }
-        const D3 ball = coop_random_in_unit_sphere(need_ball, rng.pixel, rng.sample, level + 1, k0, k1, s_id);
-        if (shading) {
-            D3 ndir, atten;
-            if (scatter_or_emit(S, h, rd, rng, ndir, atten, &ball)) {  // :29-32
-                alive = true;
-                no = h.point;
-                nd = ndir;
-                nb = hadamard(beta, atten);
-            } else {
-                L = hadamard(beta, atten);  // :34-36
+        __syncthreads();
+        if (threadIdx.x == 0) {   // exclusive scan over at most 33 bins
+            uint32_t run = 0;
+            for (int k = 0; k <= RT_SHADE_MAX_BINS; k++) {
+                s_cursor[k] = run;
+                run += s_count[k];
             }
+            s_total = run;
         }
-        if (i < n && !alive && !dead) radiance[pid] = make_float4((float)L.x, (float)L.y, (float)L.z, 1.0f);
-        uint32_t slot = queue_append(alive, count_out);
-        if (alive) {
-            out.ox[slot] = no.x; out.oy[slot] = no.y; out.oz[slot] = no.z;
-            out.dx[slot] = nd.x; out.dy[slot] = nd.y; out.dz[slot] = nd.z;
-            out.bx[slot] = nb.x; out.by[slot] = nb.y; out.bz[slot] = nb.z;
-            out.pid[slot] = pid;
+        __syncthreads();
+        // ---- places: the same matching, the warp's leader of each key reserves a run in its bin ---------------
+#pragma unroll
+        for (int r = 0; r < RT_SHADE_CHUNK / 256; r++) {
+            const int k = key[r];
+            const unsigned peers = __match_any_sync(FULL, k);
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (k >= 0 && lane == leader) base = atomicAdd(&s_cursor[k], (uint32_t)__popc(peers));
+            base = __shfl_sync(FULL, base, leader);
+            if (k >= 0) s_order[base + __popc(peers & ((1u << lane) - 1u))] = (uint16_t)(r * 256 + threadIdx.x);
         }
+        __syncthreads();
+        // ---- shade in binned order -------------------------------------------------------------------------------
+        const uint32_t total = s_total, total_round = (total + 31u) & ~31u;
+        for (uint32_t j = threadIdx.x; j < total_round; j += 256) {
+            const bool valid = j < total;
+            const uint32_t i = chunk0 + (valid ? (uint32_t)s_order[j] : 0u);
+            shade_slot(S, in, hq, out, count_out, level, max_depth, k0, k1, radiance, s_id, i, valid);
+        }
+        __syncthreads();
     }
 }
 
@@ -677,6 +753,8 @@ struct rt_scene {
     int3 march_tune = make_int3(8, 8, 8);        // k_march scheduling thresholds (RT_B200_MARCH_TUNE=a,b,c)
     int march_grid_scale = 100;                  // percent of the occupancy grid
     bool wavefront = true;         // extend/march/shade; false = fused k_bounce (more than 32 marched shapes)
+    bool shade_binned = false;     // k_shade bins a block's slots by (material kind, texture kind) before shading them
+    int n_shade_bins = 0;
     Acc* d_accum = nullptr;        // owned order: (sum r, g, b, samples)
     rt_vec3* d_frame = nullptr;    // owned order
     uint64_t frame_capacity = 0;
@@ -822,6 +900,29 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
     if ((rc = upload(sc, d->material, (size_t)n, &sc->ds.material)) != RT_OK) return bail(rc);
     if ((rc = upload(sc, d->materials, (size_t)d->n_materials, &sc->ds.materials)) != RT_OK) return bail(rc);
     if ((rc = upload(sc, d->textures, (size_t)d->n_textures, &sc->ds.textures)) != RT_OK) return bail(rc);
+    {   // shade keys: one bin per (material kind, root texture kind) pair present in the scene (k_shade, BINNED)
+        std::vector<uint8_t> mat_bin(d->n_materials, 0);
+        std::vector<int> seen;   // pair codes in order of first appearance
+        for (uint32_t i = 0; i < d->n_materials; i++) {
+            const rt_material& m = d->materials[i];
+            const bool has_tex = m.kind == RT_MAT_LAMBERTIAN || m.kind == RT_MAT_METAL || m.kind == RT_MAT_DIFFUSE_LIGHT;
+            int code = (int)m.kind * 16 + (has_tex ? (int)d->textures[m.texture].kind : 15);
+            if (m.kind == RT_MAT_METAL && m.scalar == 0.0) code += 8;   // (a mirror draws no unit-ball sample)
+            size_t b = std::find(seen.begin(), seen.end(), code) - seen.begin();
+            if (b == seen.size()) seen.push_back(code);
+            mat_bin[i] = (uint8_t)std::min<size_t>(b, RT_SHADE_MAX_BINS - 1);
+        }
+        if ((rc = upload(sc, mat_bin.data(), mat_bin.size(), &sc->ds.mat_bin)) != RT_OK) return bail(rc);
+        // Binning pays when a warp in arrival order would see many keys: measured on the all-materials variant of
+        // detached_materials.json (8 keys; k_shade at bounce levels 1 / 2: 15 / 13 -> 28 / 28 of 32 lanes, 332 / 142 ->
+        // 188 / 83 us, frame + 8 %) against cornell_box.json (4 keys, nearly every hit Lambertian: - 0.6 %).  So: on
+        // by default when the shapes of the scene reference at least 5 different keys; RT_B200_SHADE_BINNED=0 / 1 overrides.
+        std::vector<char> used(seen.size(), 0);
+        for (uint32_t i = 0; i < n; i++) used[std::min<size_t>(mat_bin[d->material[i]], used.size() - 1)] = 1;
+        sc->n_shade_bins = (int)std::count(used.begin(), used.end(), 1);
+        const char* sb = getenv("RT_B200_SHADE_BINNED");
+        sc->shade_binned = sb ? atoi(sb) != 0 : sc->n_shade_bins >= 5;
+    }
     std::vector<DevImage> imgs(d->n_images);
     for (uint32_t i = 0; i < d->n_images; i++) {
         imgs[i].width = d->images[i].width;
@@ -934,7 +1035,7 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
     if (const char* mv = getenv("RT_B200_MARCH")) sc->march_version = std::min(std::max(atoi(mv), 1), 3);
     if (getenv("RT_B200_MARCH_V2")) sc->march_version = 2;
     if (const char* db = getenv("RT_B200_DEFER_BOUND")) sc->defer_bound = atoi(db) != 0;
-    sc->grid_shade = occ_grid(k_shade<false>, 256, 0);
+    sc->grid_shade = occ_grid(k_shade<false, true>, 256, 0);
     sc->wavefront = sc->ds.n_march <= 32 && !getenv("RT_B200_FUSED_BOUNCE");
 
     if (cudaMalloc(&sc->d_counters, sizeof(DevCounters)) != cudaSuccess) return bail(fail(RT_ERR_NOMEM, "cudaMalloc failed"));
@@ -1278,12 +1379,18 @@ static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long 
         }
         {
             KernelSpan span(sc, RT_KCLASS_SHADE);
-            if (sc->counters_on)
-                k_shade<true><<<sc->grid_shade, 256, 0, sc->stream>>>(sc->ds, in, cnt_in, sc->hq, out, cnt_out, level, max_depth, sc->map,
-                                                                      first_owned, spp, k0, k1, sc->d_radiance);
-            else
-                k_shade<false><<<sc->grid_shade, 256, 0, sc->stream>>>(sc->ds, in, cnt_in, sc->hq, out, cnt_out, level, max_depth, sc->map,
-                                                                       first_owned, spp, k0, k1, sc->d_radiance);
+            // the binned variant only where it has something to sort: several shade keys in the scene, and not at the
+            // last level (any hit is black there)
+            const bool binned = sc->shade_binned && level < max_depth;
+#define RT_LAUNCH_SHADE(C_, B_)                                                                                              \
+    k_shade<C_, B_><<<sc->grid_shade, 256, 0, sc->stream>>>(sc->ds, in, cnt_in, sc->hq, out, cnt_out, level, max_depth, sc->map, \
+                                                            first_owned, spp, k0, k1, sc->d_radiance)
+            if (sc->counters_on) {
+                if (binned) RT_LAUNCH_SHADE(true, true); else RT_LAUNCH_SHADE(true, false);
+            } else {
+                if (binned) RT_LAUNCH_SHADE(false, true); else RT_LAUNCH_SHADE(false, false);
+            }
+#undef RT_LAUNCH_SHADE
         }
     }
 }

@@ -23,6 +23,7 @@ struct DevScene {
     const uint8_t* flags;
     const uint32_t* material;
     const rt_material* materials;
+    const uint8_t* mat_bin;     // [n_materials] shade key of a material: its (kind, root texture kind) bin (k_shade)
     const rt_texture* textures;
     const DevImage* images;
     const rt_perlin* noise;

@@ -322,12 +322,27 @@ def test_alternative_schedules_give_the_same_frame(monkeypatch, name):
     for var, val in (("RT_B200_MARCH", "3"), ("RT_B200_MARCH", "2"), ("RT_B200_FUSED_BOUNCE", "1"),
                      ("RT_B200_MARCH_TUNE", "2,30,3"),
                      ("RT_B200_NO_CULL_TREE", "1"), ("RT_B200_NO_MARCH_SKIP", "1"), ("RT_B200_NO_FLAT_REC", "1"),
-                     ("RT_B200_DEFER_BOUND", "1")):
+                     ("RT_B200_DEFER_BOUND", "1"), ("RT_B200_SHADE_BINNED", "1"), ("RT_B200_SHADE_BINNED", "0")):
         monkeypatch.setenv(var, val)
         alt = rt.Scene.from_file(scene_path(name), random_spheres_seed=1)
         got = gpu_frame(alt, alt.camera(), w, h, spp, depth, seed)
         monkeypatch.delenv(var)
         assert np.array_equal(got, ref), var
+
+
+def test_binned_shade_queue_gives_the_same_frame_on_all_material_and_texture_branches(monkeypatch):
+    """config 4b (every material / texture kind live): k_shade with its slots binned by (material kind, texture kind)
+    -- the shade queue keyed by material -- against the arrival-order k_shade, bit for bit, at a size where a block's
+    chunk of 1024 slots holds many keys"""
+    frames = {}
+    for binned in ("0", "1"):
+        monkeypatch.setenv("RT_B200_SHADE_BINNED", binned)
+        sc = rt.Scene.from_file(scene_path("detached_materials.json"), random_spheres_seed=1)
+        cam = _variant_4b(sc)
+        frames[binned] = gpu_frame(sc, cam, 320, 180, 8, 8, seed=17)
+        monkeypatch.delenv("RT_B200_SHADE_BINNED")
+    assert np.array_equal(frames["0"], frames["1"])
+    assert frames["1"].mean() > 0.05
 
 
 def test_distributed_renderer_frames_follow_their_parameters():
