@@ -135,6 +135,9 @@ __device__ __noinline__ unsigned long long count_false_culls(const DevScene& S, 
         bool reached = cull_pass(cr, S.cull[i]);
         if (g >= 0)
             reached = reached && cull_pass_node(cr, S.ctab[g / RT_CULL_ROOT_FANOUT]) && cull_pass_node(cr, S.ctab[S.n_roots + g]);
+        if (g >= 0)
+            for (int l = 1; l <= S.n_upper; l++)   // every ancestor above the root
+                reached = reached && cull_pass_node(cr, S.cupper[S.upper_off[l] + ((g / RT_CULL_ROOT_FANOUT) >> (5 * l))]);
         if (reached) continue;
         double best = INFINITY;
         int winner = -1;
@@ -331,8 +334,8 @@ k_bounce(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
 // RAYGEN (bounce level 0 of a frame): the primary rays are GENERATED here instead of being read back from the
 // queue a separate k_raygen pass wrote (that pass was a pure HBM round trip: 76 B written and 48 B re-read per path,
 // 3 % of the step) -- MultisamplerRayCaster::next, src/camera/ray_caster.rs:100-118, same draws, same arithmetic.
-// Path i of the batch takes queue slot i (no compaction); the slots of a clipped border tile's padding pixels are
-// marked dead (index -2) and k_shade skips them.
+// Path i of the batch takes queue slot i (no compaction); the slots of a clipped border tile's padding pixels
+// become misses with zero throughput.
 struct RaygenArgs {
     RayCasterDev rc;
     ShardMap map;
@@ -341,7 +344,6 @@ struct RaygenArgs {
     float4* radiance;
     uint32_t* count_out;   // receives n_paths: the live count of level 0 that k_march / k_shade read
 };
-#define RT_HIT_DEAD (-2)
 template <bool COUNT, bool RAYGEN>
 __global__ void __launch_bounds__(256, RT_EXTEND_MIN_BLOCKS)
 k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ count_in, HitQueue hq,
@@ -380,8 +382,12 @@ k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
                 in.bx[i] = 1.0; in.by[i] = 1.0; in.bz[i] = 1.0;
                 in.pid[i] = i;
             } else {
-                rg.radiance[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                hq.index[i] = RT_HIT_DEAD;
+                // padding pixel of a clipped border tile: no path.  Its slot becomes a miss with zero throughput, so
+                // that k_shade needs no special case (it writes radiance 0; nobody reads a padding pixel's sum)
+                in.dx[i] = 0.0; in.dy[i] = 1.0; in.dz[i] = 0.0;
+                in.bx[i] = 0.0; in.by[i] = 0.0; in.bz[i] = 0.0;
+                in.pid[i] = i;
+                hq.index[i] = -1;
                 live = false;
             }
         }
@@ -449,7 +455,7 @@ k_replay(DevScene S, PathQueue in, HitQueue hq, const uint32_t* __restrict__ rep
 __device__ __forceinline__ void shade_slot(const DevScene& S, const PathQueue& in, const HitQueue& hq, const PathQueue& out,
                                            uint32_t* count_out, uint32_t level, uint32_t max_depth, uint32_t k0, uint32_t k1,
                                            float4* __restrict__ radiance, uint4* s_id, uint32_t i, bool valid) {
-    bool alive = false, shading = false, need_ball = false, dead = false;
+    bool alive = false, shading = false, need_ball = false;
     D3 no = mk(0, 0, 0), nd = mk(0, 0, 0), nb = mk(0, 0, 0);
     D3 rd = mk(0, 0, 0), beta = mk(0, 0, 0), L = mk(0.0, 0.0, 0.0);
     uint32_t pid = 0;
@@ -463,9 +469,7 @@ __device__ __forceinline__ void shade_slot(const DevScene& S, const PathQueue& i
         beta = mk(in.bx[i], in.by[i], in.bz[i]);
         pid = in.pid[i];
         const int bi = hq.index[i];
-        if (bi == RT_HIT_DEAD) {
-            dead = true;   // padding pixel of a clipped border tile (k_extend, RAYGEN): no path
-        } else if (bi < 0) {
+        if (bi < 0) {
             L = hadamard(beta, sky(rd));  // renderer/mod.rs:41-43
         } else if (level == max_depth) {
             // depth == 0: black (:26-27)
@@ -492,7 +496,7 @@ __device__ __forceinline__ void shade_slot(const DevScene& S, const PathQueue& i
             L = hadamard(beta, atten);  // :34-36
         }
     }
-    if (valid && !alive && !dead) radiance[pid] = make_float4((float)L.x, (float)L.y, (float)L.z, 1.0f);
+    if (valid && !alive) radiance[pid] = make_float4((float)L.x, (float)L.y, (float)L.z, 1.0f);
     uint32_t slot = queue_append(alive, count_out);
     if (alive) {
         out.ox[slot] = no.x; out.oy[slot] = no.y; out.oz[slot] = no.z;
@@ -507,7 +511,7 @@ __device__ __forceinline__ void shade_slot(const DevScene& S, const PathQueue& i
 // this kernel -- in arrival order a warp of a scene with many material kinds executes the union of their branches.
 // A block therefore takes RT_SHADE_CHUNK consecutive slots, bins them in shared memory by the winner's shade key
 // (0 = miss -> sky; 1 + S.mat_bin[material]: one bin per (material kind, root texture kind) pair present in the scene;
-// dead slots dropped) -- a counting sort with BLOCK-AGGREGATED counters: lanes with the same key are matched inside
+// slots past the queue's end dropped) -- a counting sort with BLOCK-AGGREGATED counters: lanes with the same key are matched inside
 // the warp (__match_any_sync) and one shared-memory atomic per (warp, key) reserves their places -- and shades the
 // slots in binned order, so that all but the few warps at a bin boundary run one branch.  The paths' results do not
 // depend on the order (every random draw is keyed by the path), so the frame is bit-identical to the unbinned one.
@@ -548,7 +552,7 @@ k_shade(DevScene S, PathQueue in, const uint32_t* __restrict__ count_in, HitQueu
             int k = -1;
             if (i < n) {
                 const int bi = hq.index[i];
-                if (bi != RT_HIT_DEAD) k = bi < 0 ? 0 : 1 + (int)S.mat_bin[S.material[bi]];
+                k = bi < 0 ? 0 : 1 + (int)S.mat_bin[S.material[bi]];
             }
             key[r] = k;
             const unsigned peers = __match_any_sync(FULL, k);
@@ -966,6 +970,9 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
         CullTree ct = cull_build(d->inverse, d->kind, (int)n, getenv("RT_B200_NO_CULL") != nullptr,
                                  getenv("RT_B200_NO_CULL_TREE") != nullptr || getenv("RT_B200_NO_CULL") != nullptr);
         sc->ds.n_roots = ct.n_roots;
+        sc->ds.n_upper = ct.n_upper;
+        for (int l = 0; l <= RT_CULL_UPPER_MAX; l++) sc->ds.upper_off[l] = ct.upper_off[l];
+        if ((rc = upload(sc, ct.upper.data(), ct.upper.size(), &sc->ds.cupper)) != RT_OK) return bail(rc);
         sc->ds.n_groups = ct.n_groups;
         sc->ds.n_flat = ct.n_flat;
         sc->ds.n_flat_real = ct.n_flat_real;
@@ -2034,6 +2041,24 @@ int rt_cull_tree_check(const rt_scene_desc* d, uint32_t* n_roots, uint32_t* n_gr
         const double fx = c[0] - rt_.x, fy = c[1] - rt_.y, fz = c[2] - rt_.z;
         w = fmax(w, (sqrt(fx * fx + fy * fy + fz * fz) + r - rr) / rr);
     }
+    // levels above the roots: every node encloses the nodes it covers (FP64 balls of the build)
+    {
+        std::vector<CullBall> below = ct.root_ball;
+        size_t at = 0;
+        for (int l = 1; l <= ct.n_upper; l++) {
+            std::vector<CullBall> here(ct.upper_ball.begin() + at, ct.upper_ball.begin() + at + ct.upper_count[l]);
+            at += ct.upper_count[l];
+            for (int i = 0; i < ct.upper_count[l]; i++) {
+                const double nr = node_radius(ct.upper[ct.upper_off[l] + i]);
+                for (int k = 32 * i; k < std::min(32 * i + 32, (int)below.size()); k++) {
+                    if (below[k].r < 0.0) continue;
+                    const double dx = below[k].c[0] - here[i].c[0], dy = below[k].c[1] - here[i].c[1], dz = below[k].c[2] - here[i].c[2];
+                    w = fmax(w, (sqrt(dx * dx + dy * dy + dz * dz) + below[k].r - nr) / nr);
+                }
+            }
+            below = here;
+        }
+    }
     *n_tree = in_tree;
     *worst = in_tree ? w : 0.0;
     return RT_OK;
@@ -2068,6 +2093,10 @@ int rt_cull_reached(const rt_scene_desc* d, const rt_ray* rays, uint64_t n_rays,
         for (int j = 0; j < ct.n_flat; j++)
             if (flat_ids[j] >= 0 && cull_pass(cr, flat[j])) out[flat_ids[j]] = 1;
         for (int rt_i = 0; rt_i < ct.n_roots; rt_i++) {
+            bool above = true;   // the upper levels (the device skips a rejected node's whole range: same decisions)
+            for (int l = 1; l <= ct.n_upper && above; l++)
+                above = cull_pass_node(cr, ct.upper[ct.upper_off[l] + (rt_i >> (5 * l))]);
+            if (!above) continue;
             if (!cull_pass_node(cr, roots[rt_i])) continue;
             const int g0 = RT_CULL_ROOT_FANOUT * rt_i, g1 = std::min(g0 + RT_CULL_ROOT_FANOUT, ct.n_groups);
             for (int g = g0; g < g1; g++) {

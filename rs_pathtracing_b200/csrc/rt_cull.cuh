@@ -131,6 +131,12 @@ inline float4 cull_entry_march_bound(const double* m, const double radius[3]) {
 #define RT_CULL_GROUP 16        // leaves per group
 #define RT_CULL_ROOT_FANOUT 32  // groups per root
 #define RT_CULL_NODE_RAY 101.0  // node tests use rhs = An + 101 * 3B |o|^2
+#define RT_CULL_UPPER_MAX 4     // levels above the roots: each node covers 32 nodes of the level below
+#define RT_CULL_TOP_TARGET 8    // levels are added until the top one has at most this many nodes
+
+struct CullBall {
+    double c[3], r;
+};
 
 struct CullTree {
     // table = [roots: n_roots][groups: n_groups (multiple of 8)][leaves: 16 * n_groups][flat: n_flat (multiple of 8)]
@@ -140,12 +146,17 @@ struct CullTree {
     std::vector<float4> leaf;   // [n_shapes] the shape's own entry (RT_ISECT_VERIFY)
     int n_roots = 0, n_groups = 0, n_flat = 0, n_flat_real = 0;
     std::vector<double> group_radius;  // [groups built] the FP64 radius each group entry was made from (rt_cull_tree_check)
+    // ARBITRARY DEPTH: levels above the roots.  Level l (1-based) node i is a ball around the level l-1 nodes
+    // [32 i, 32 i + 32) (level 0 = the roots), hence around every leaf ball below it -- the one property the
+    // rejection proof above uses -- and is tested with the same node test.  upper = the levels' entries back to
+    // back, level l at upper[upper_off[l]] with upper_count[l] entries; n_upper levels (0 for a scene of <= 8 roots,
+    // i.e. up to ~4 000 shapes; 1 up to ~130 000; ...).  The walk tests a node when it reaches the first root of its
+    // range and skips the whole range on rejection, so the roots tested per ray grow like log(n), not n / 512.
+    int n_upper = 0, upper_off[RT_CULL_UPPER_MAX + 1] = {0, 0, 0, 0, 0}, upper_count[RT_CULL_UPPER_MAX + 1] = {0, 0, 0, 0, 0};
+    std::vector<float4> upper;
+    std::vector<CullBall> upper_ball;  // the FP64 balls the entries were made from (rt_cull_tree_check)
+    std::vector<CullBall> root_ball;
 };
-
-struct CullBall {
-    double c[3], r;
-};
-
 
 // ball around member balls, FP32-representable centre
 inline CullBall cull_enclose(const std::vector<CullBall>& m) {
@@ -268,11 +279,42 @@ inline CullTree cull_build(const double* inverse, const uint8_t* kind, int n, bo
         grp[g] = cull_node_entry(gball[g]);
         t.group_radius.push_back(gball[g].r);
     }
+    t.root_ball.assign(t.n_roots, CullBall{{0.0, 0.0, 0.0}, -1.0});
     for (int r = 0; r < t.n_roots; r++) {
         std::vector<CullBall> m;
         for (size_t g = (size_t)r * RT_CULL_ROOT_FANOUT; g < std::min(groups.size(), (size_t)(r + 1) * RT_CULL_ROOT_FANOUT); g++)
             m.push_back(gball[g]);
-        roots[r] = m.empty() ? pad : cull_node_entry(cull_enclose(m));
+        if (m.empty()) {
+            roots[r] = pad;
+            continue;
+        }
+        t.root_ball[r] = cull_enclose(m);
+        roots[r] = cull_node_entry(t.root_ball[r]);
+    }
+    // levels above the roots (consecutive roots are spatial neighbours: the groups come out of the median splits in
+    // order), until the top level is short
+    {
+        std::vector<CullBall> below = t.root_ball;
+        while ((int)below.size() > RT_CULL_TOP_TARGET && t.n_upper < RT_CULL_UPPER_MAX) {
+            const int lv = ++t.n_upper;
+            const int count = ((int)below.size() + 31) / 32;
+            t.upper_off[lv] = (int)t.upper.size();
+            t.upper_count[lv] = count;
+            std::vector<CullBall> here(count, CullBall{{0.0, 0.0, 0.0}, -1.0});
+            for (int i = 0; i < count; i++) {
+                std::vector<CullBall> m;
+                for (int k = 32 * i; k < std::min(32 * i + 32, (int)below.size()); k++)
+                    if (below[k].r >= 0.0) m.push_back(below[k]);
+                if (m.empty()) {
+                    t.upper.push_back(pad);
+                } else {
+                    here[i] = cull_enclose(m);
+                    t.upper.push_back(cull_node_entry(here[i]));
+                }
+                t.upper_ball.push_back(here[i]);
+            }
+            below = here;
+        }
     }
     for (size_t k = 0; k < flat.size(); k++) {
         fl[k] = t.leaf[flat[k]];

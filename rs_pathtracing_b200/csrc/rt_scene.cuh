@@ -38,6 +38,9 @@ struct DevScene {
     // cids = shape index of every leaf / flat slot (-1 = padding)
     int n_roots, n_groups, n_flat, n_flat_real;
     const float4* ctab;
+    // levels above the roots (CullTree::upper): level l at cupper[upper_off[l]], l = 1 .. n_upper
+    int n_upper, upper_off[RT_CULL_UPPER_MAX + 1];
+    const float4* cupper;
     const int* cids;
     // per shape (RT_ISECT_VERIFY): its own leaf entry and its group (-1 flat list, -2 not analytic)
     const float4* cull;
@@ -294,8 +297,24 @@ __device__ __forceinline__ bool analytic_nearest_impl(const DevScene& S, const C
             if (id >= 0) analytic_test<COUNT>(S, id, ro, rd, min_t, best, winner, degenerate, c);
         }
     }
-    if (COUNT) c.cull_tests += S.n_flat_real + S.n_roots;
+    if (COUNT) c.cull_tests += S.n_flat_real;
     for (int r = 0; r < S.n_roots; r++) {
+        if (S.n_upper > 0) {
+            // arbitrary depth: entering the range of an upper node (32^l roots, aligned), test it -- top level first --
+            // and skip the whole range when the line misses its ball
+            bool skipped = false;
+            for (int l = S.n_upper; l >= 1 && !skipped; l--) {
+                const int span = 1 << (5 * l);
+                if ((r & (span - 1)) != 0) continue;
+                if (COUNT) c.cull_tests++;
+                if (!cull_pass_node(cr, __ldg(S.cupper + S.upper_off[l] + (r >> (5 * l))))) {
+                    r += span - 1;   // (the loop's r++ completes the skip)
+                    skipped = true;
+                }
+            }
+            if (skipped) continue;
+        }
+        if (COUNT) c.cull_tests++;
         if (!cull_pass_node(cr, roots[r])) continue;
         const int g0 = RT_CULL_ROOT_FANOUT * r;
         const int ng = min(RT_CULL_ROOT_FANOUT, S.n_groups - g0);  // a multiple of 8

@@ -92,3 +92,46 @@ def test_tangent_rays_reach_their_sphere():
     idx = np.repeat(np.arange(80), 12)
     assert got[np.arange(len(rays)), idx].all()
     check(sc, rays)
+
+
+def big_scene(n_shapes, seed, extent):
+    """a generated scene of n_shapes small Spheres / Cubes in a box of half-width `extent` plus a few Rectangles
+    (flat list: never culled) and one large ground sphere -- the arbitrary-depth case of the cull tree"""
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-extent, extent, (n_shapes, 3))
+    r = rng.uniform(0.05, 0.4, n_shapes)
+    rot = rng.uniform(-90, 90, (n_shapes, 3))
+    shapes = [{"type": "Cube" if k % 5 == 0 else "Sphere", "name": "s", "material": "M",
+               "transform": {"translate": c[k].tolist(), "rotate": rot[k].tolist() if k % 5 == 0 else [0, 0, 0],
+                             "scale": [float(r[k])] * 3}} for k in range(n_shapes)]
+    for k in range(6):
+        shapes.append({"type": "Rectangle", "x0": -1.0, "y0": -1.0, "x1": 1.0, "y1": 1.0, "material": "M",
+                       "transform": {"translate": rng.uniform(-extent, extent, 3).tolist(),
+                                     "rotate": rng.uniform(-90, 90, 3).tolist(), "scale": [extent / 4] * 3}})
+    shapes.append({"type": "Sphere", "name": "ground", "material": "M",
+                   "transform": {"translate": [0, -extent - 1000.0, 0], "rotate": [0, 0, 0], "scale": [1000.0] * 3}})
+    scene = dict(TRIO)
+    scene["shapes"] = shapes
+    return rt.Scene.from_json(json.dumps(scene), add_random_spheres=False)
+
+
+def box_rays(n, seed, extent):
+    rng = np.random.default_rng(seed)
+    o = rng.uniform(-1.5 * extent, 1.5 * extent, (n, 3))
+    tgt = rng.uniform(-extent, extent, (n, 3))
+    return rt.make_rays(o, tgt - o)
+
+
+def test_arbitrary_depth_tree_is_conservative_and_encloses():
+    """20 000 shapes: 40 roots under two upper-level nodes.  Enclosure of every node (rt_cull_tree_check, FP64) and
+    "oracle hits => reached" pair by pair (rt_cull_reached walks the levels like the device)"""
+    sc = big_scene(20000, seed=3, extent=30.0)
+    d = sc.desc()
+    out = [C.c_uint32() for _ in range(4)]
+    worst = C.c_double()
+    assert _ffi.core().rt_cull_tree_check(C.byref(d), *[C.byref(x) for x in out], C.byref(worst)) == 0
+    n_roots, n_groups, n_tree, n_flat = (x.value for x in out)
+    assert n_tree == 20000 and n_flat == 7 and n_roots == (n_groups + 31) // 32 and n_roots > 32
+    assert worst.value <= 1e-7, worst.value
+    got, hits = check(sc, box_rays(160, seed=4, extent=30.0), min_hit_fraction=0.5)
+    assert got.sum(axis=1).mean() < 0.01 * sc.shape_count      # a ray looks at < 1 % of the shapes

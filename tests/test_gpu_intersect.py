@@ -373,3 +373,33 @@ def test_cull_tree_sizes(n_spheres, spread, offset):
     sc.closest_hit(rays, mode=rt.RT_ISECT_VERIFY, want=("index",))
     st = sc.stats()
     assert st.verify_rays == 0 and st.verify_false_culls == 0
+
+
+@pytest.mark.parametrize("n_shapes,extent,n_rays", [(10000, 24.0, 8192), (100000, 52.0, 4096)])
+def test_arbitrary_depth_cull_tree_on_generated_scenes(n_shapes, extent, n_rays):
+    """the cull tree generalised to arbitrary depth (levels of bounding balls above the roots, walked with
+    range skipping) on generated scenes of 10^4 and 10^5 shapes (+ Rectangles on the flat list + a large ground
+    sphere): FAST == BRUTE == oracle bit for bit, RT_ISECT_VERIFY clean at every level, and the work per ray grows
+    like log n (counters), not like n"""
+    from test_cull_cpu import big_scene, box_rays
+    sc = big_scene(n_shapes, seed=n_shapes, extent=extent)
+    rays = box_rays(n_rays, seed=7, extent=extent)
+    odd = np.array([[0, 0, 0, math.nan, 0, 1], [1, 2, 3, 0, 0, 0], [0, 0, 0, math.inf, 0, 0]], dtype=np.float64)
+    rays = np.concatenate([rays, odd])
+    want = check_parity(sc, rays)
+    assert (want["index"] >= 0).mean() > 0.5
+    sub = rays[:512]
+    sc.reset_stats()
+    sc.closest_hit(sub, mode=rt.RT_ISECT_VERIFY, want=("index",))
+    st = sc.stats()
+    assert st.verify_rays == 0 and st.verify_false_culls == 0
+    sc.set_counters(True)
+    sc.reset_stats()
+    sc.closest_hit(rays[:n_rays], mode=rt.RT_ISECT_FAST, want=("index",))   # (without the NaN / inf rays: nothing culls those)
+    st = sc.stats()
+    sc.set_counters(False)
+    per_ray_cull, per_ray_exact = st.cull_tests / n_rays, st.shape_tests / n_rays
+    # 10^4 shapes: 20 roots under 1 upper node; 10^5: 196 roots under 7.  Measured (profiles/r2k_big_scenes.md):
+    # 684 / 1986 ball tests and 8.3 / 9.6 exact tests per ray -- a ray through a box this dense crosses a few dozen
+    # groups of 16 -- against 10 007 / 100 007 exact tests of the literal loop
+    assert per_ray_cull < 0.05 * n_shapes + 600 and per_ray_exact < 25, (per_ray_cull, per_ray_exact)
