@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 4
+#define RT_B200_ABI_VERSION 5
 
 typedef enum rt_status {
     RT_OK = 0,
@@ -69,7 +69,13 @@ enum {
     RT_SHAPE_SPHERE = 0,     /* unit sphere, flag bit0 = inverse_normal                         */
     RT_SHAPE_CUBE = 1,       /* unit box [-1,1]^3                                               */
     RT_SHAPE_RECTANGLE = 2,  /* z = 0 plane clipped to [x0,x1]x[y0,y1]; params = x0,y0,x1,y1    */
-    RT_SHAPE_MARCH = 3       /* RayMarchingShape; params below                                  */
+    RT_SHAPE_MARCH = 3,      /* RayMarchingShape; params below                                  */
+    RT_SHAPE_TORUS = 4       /* Torus (src/world/shapes/mod.rs:403-494): params = radius, tube_radius; quartic via
+                                the reference's complex Ferrari solver (src/algebra/equation.rs:17-67).  A root
+                                counts as real when |im| < 1e-15, which depends on the last ulp of libm's
+                                hypot / atan2 / cos / sin / cbrt: t agrees with the oracle to ~1e-12 relative where
+                                both accept the root, the accept / reject decision itself is not bit-reproducible
+                                across math libraries (neither is it between two builds of the reference)          */
 };
 #define RT_SHAPE_FLAG_INVERSE_NORMAL 1u
 
@@ -326,8 +332,9 @@ typedef struct rt_stats {
     double ms_raygen, ms_extend, ms_march, ms_shade, ms_resolve;
     uint64_t launches_extend, launches_march, launches_shade;
     /* k_march work breakdown (with counters on): literal steps at level 0, literal steps at the
-     * refinement levels, exact multi-step jumps, hops of the skip bound */
-    uint64_t march_prof[4];
+     * refinement levels, exact multi-step jumps, hops of the skip bound, rays proven to miss by the Bernstein hull
+     * of the surface polynomial / by the hop loop (no marching at all), 2 reserved.  8 entries since ABI 5 (4 before) */
+    uint64_t march_prof[8];
 } rt_stats;
 int rt_get_stats(rt_scene* scene, rt_stats* out);
 int rt_reset_stats(rt_scene* scene);

@@ -464,6 +464,127 @@ static bool march_intersect(const Shape& s, const Ray& ray, double min_t, double
     return true;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Torus -- shapes/mod.rs:403-494, on solve_quantic_equation -- algebra/equation.rs:17-67.
+// The solver runs on num::Complex<f64> (crate `num ^0.4`, Cargo.toml:21 -> num-complex 0.4.x; not vendored).  Its
+// arithmetic is restated here from that crate's published source: +, -, scalar * and / componentwise; complex *
+// (re re' - im im', re im' + im re'); complex / via norm_sqr = re'^2 + im'^2; sqrt / cbrt by cases (im == 0, re == 0,
+// else polar form hypot / atan2 -> root of r, angle / n -> r cos, r sin), signs of zero respected.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Cx {
+    double re, im;
+};
+inline Cx cx(double re) { return Cx{re, 0.0}; }                       // f64::into()
+inline Cx operator+(Cx a, Cx b) { return Cx{a.re + b.re, a.im + b.im}; }
+inline Cx operator-(Cx a, Cx b) { return Cx{a.re - b.re, a.im - b.im}; }
+inline Cx operator-(Cx a) { return Cx{-a.re, -a.im}; }
+inline Cx operator*(Cx a, Cx b) { return Cx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+inline Cx operator/(Cx a, Cx b) {
+    double norm_sqr = b.re * b.re + b.im * b.im;
+    double re = a.re * b.re + a.im * b.im;
+    double im = a.im * b.re - a.re * b.im;
+    return Cx{re / norm_sqr, im / norm_sqr};
+}
+inline Cx operator*(double k, Cx a) { return Cx{k * a.re, k * a.im}; }   // impl Mul<Complex<f64>> for f64
+inline Cx operator/(Cx a, double k) { return Cx{a.re / k, a.im / k}; }
+inline Cx operator+(double k, Cx a) { return Cx{k + a.re, a.im}; }
+inline Cx cx_from_polar(double r, double theta) { return Cx{r * std::cos(theta), r * std::sin(theta)}; }
+inline Cx cx_sqrt(Cx z) {
+    if (z.im == 0.0) {
+        if (!std::signbit(z.re)) return Cx{std::sqrt(z.re), z.im};
+        double im = std::sqrt(-z.re);                                   // sqrt(r e^(i pi)) = i sqrt(r)
+        return !std::signbit(z.im) ? Cx{0.0, im} : Cx{0.0, -im};
+    }
+    if (z.re == 0.0) {
+        double x = std::sqrt(std::fabs(z.im) / 2.0);                    // sqrt(r e^(i pi/2)) = sqrt(r/2)(1 + i)
+        return !std::signbit(z.im) ? Cx{x, x} : Cx{x, -x};
+    }
+    return cx_from_polar(std::sqrt(std::hypot(z.re, z.im)), std::atan2(z.im, z.re) / 2.0);
+}
+inline Cx cx_cbrt(Cx z) {
+    if (z.im == 0.0) {
+        if (!std::signbit(z.re)) return Cx{std::cbrt(z.re), z.im};
+        double re = std::cbrt(-z.re) / 2.0;                             // cbrt(r e^(i pi)) = cbrt(r) e^(i pi/3)
+        double im = std::sqrt(3.0) * re;
+        return !std::signbit(z.im) ? Cx{re, im} : Cx{re, -im};
+    }
+    if (z.re == 0.0) {
+        double im = std::cbrt(std::fabs(z.im)) / 2.0;                   // cbrt(r e^(i pi/2)) = cbrt(r) e^(i pi/6)
+        double re = std::sqrt(3.0) * im;
+        return !std::signbit(z.im) ? Cx{re, im} : Cx{re, -im};
+    }
+    return cx_from_polar(std::cbrt(std::hypot(z.re, z.im)), std::atan2(z.im, z.re) / 3.0);
+}
+}  // namespace
+
+// equation.rs:17-67
+void solve_quantic_equation(double a_, double b_, double c_, double d_, double e_, double re_out[4], double im_out[4]) {
+    Cx a = cx(a_), b = cx(b_) / a, c = cx(c_) / a, d = cx(d_) / a, e = cx(e_) / a;
+    Cx b2 = b * b;
+    Cx alpha = c - (3.0 / 8.0) * b2;
+    Cx beta = (b2 * b) / 8.0 - (b * c) / 2.0 + d;
+    Cx gamma = (-3.0 / 256.0) * b2 * b2 + b2 * c / 16.0 - b * d / 4.0 + e;
+    Cx alpha2 = alpha * alpha;
+    Cx t = -b / 4.0;
+    Cx roots[4];
+    if (approx_equal(beta.re, 0.0) && approx_equal(beta.im, 0.0)) {
+        Cx r = cx_sqrt(alpha2 - 4.0 * gamma);
+        Cx r1 = cx_sqrt((-alpha + r) / 2.0);
+        Cx r2 = cx_sqrt((-alpha - r) / 2.0);
+        roots[0] = t + r1; roots[1] = t - r1; roots[2] = t + r2; roots[3] = t - r2;
+    } else {
+        Cx p = -(alpha2 / 12.0 + gamma);
+        Cx q = -alpha2 * alpha / 108.0 + alpha * gamma / 3.0 - beta * beta / 8.0;
+        Cx r = -q / 2.0 + cx_sqrt(q * q / 4.0 + p * p * p / 27.0);
+        Cx u = cx_cbrt(r);
+        Cx y = (-5.0 / 6.0) * alpha + u;
+        if (approx_equal(u.re, 0.0) && approx_equal(u.im, 0.0)) y = y - cx_cbrt(q);
+        else y = y - p / (3.0 * u);
+        Cx w = cx_sqrt(alpha + 2.0 * y);
+        Cx r1 = cx_sqrt(-(3.0 * alpha + 2.0 * y + 2.0 * beta / w));
+        Cx r2 = cx_sqrt(-(3.0 * alpha + 2.0 * y - 2.0 * beta / w));
+        roots[0] = t + (w - r1) / 2.0; roots[1] = t + (w + r1) / 2.0;
+        roots[2] = t + (-w - r2) / 2.0; roots[3] = t + (-w + r2) / 2.0;
+    }
+    for (int k = 0; k < 4; k++) { re_out[k] = roots[k].re; im_out[k] = roots[k].im; }
+}
+
+static bool torus_intersect(const Shape& s, const Ray& ray, double min_t, double max_t, ObjHit* h) {
+    // shapes/mod.rs:429-476
+    const double PI = 3.14159265358979323846264338327950288;
+    V3 origin = ray.origin, dir = ray.direction;
+    double radius = s.p[0], tube_radius = s.p[1];
+    double t = 4.0 * radius * radius;
+    double g = t * (dir.x * dir.x + dir.y * dir.y);
+    double hh = 2.0 * t * (origin.x * dir.x + origin.y * dir.y);
+    double i = t * (origin.x * origin.x + origin.y * origin.y);
+    double j = dot(dir, dir);
+    double k = 2.0 * dot(origin, dir);
+    double l = dot(origin, origin) + radius * radius - tube_radius * tube_radius;
+    double a = j * j;
+    double b = 2.0 * j * k;
+    double c = 2.0 * j * l + k * k - g;
+    double d = 2.0 * k * l - hh;
+    double e = l * l - i;
+    double re[4], im[4];
+    solve_quantic_equation(a, b, c, d, e, re, im);
+    double min_root = INFINITY;
+    for (int r = 0; r < 4; r++)
+        if (approx_equal(im[r], 0.0) && re[r] < min_root) min_root = re[r];
+    if (std::isinf(min_root) || min_root < min_t || min_root > max_t) return false;
+    V3 p = origin + min_root * dir;
+    h->p = p;
+    h->n = p - normalize(v3(p.x, p.y, 0.0)) * radius;
+    double theta = std::asin(p.z / tube_radius);
+    double phi = std::acos(p.z / (radius + tube_radius * std::cos(theta))) + PI;
+    h->u = phi / (2.0 * PI);
+    h->v = theta / PI;
+    h->t = min_root;
+    return true;
+}
+
 // Shape::ray_hit_transformed (shapes/mod.rs:112-124) around RayHit::new / set_normal (ray.rs:32-64)
 bool shape_ray_hit(const Shape& s, int index, const Ray& ray, double min_t, double max_t, Hit* hit,
                    Counters* c) {
@@ -478,6 +599,7 @@ bool shape_ray_hit(const Shape& s, int index, const Ray& ray, double min_t, doub
         case RT_SHAPE_CUBE: ok = cube_intersect(s, local, min_t, max_t, &oh); break;
         case RT_SHAPE_RECTANGLE: ok = rectangle_intersect(s, local, min_t, max_t, &oh); break;
         case RT_SHAPE_MARCH: ok = march_intersect(s, local, min_t, max_t, &oh, c); break;
+        case RT_SHAPE_TORUS: ok = torus_intersect(s, local, min_t, max_t, &oh); break;
     }
     if (!ok) return false;
     V3 n_obj = normalize(oh.n);                        // RayHit::new, ray.rs:42-45
@@ -528,6 +650,12 @@ void shape_bounding_box(const Shape& s, V3* mn, V3* mx) {
             }
             lo = -hi;
             break;
+        case RT_SHAPE_TORUS: {  // :486-493
+            double a = s.p[0] + s.p[1];
+            lo = v3(-a, -a, -s.p[1]);
+            hi = v3(a, a, s.p[1]);
+            break;
+        }
         default:  // Sphere :384-398, Cube :295-301
             lo = v3(-1.0, -1.0, -1.0);
             hi = v3(1.0, 1.0, 1.0);

@@ -156,6 +156,8 @@ bool bvh_ray_hit(const Scene& sc, const Ray& ray, double min_t, double max_t, Hi
 
 // ShapeFunction::intersect_bound of a ray-marched shape on an object-space ray (ray_marching.rs:135-145, 213-225)
 bool march_intersect_bound(const Shape& s, const Ray& local, double* start, double* end);
+// solve_quantic_equation (src/algebra/equation.rs:17-67): the four complex roots of a x^4 + b x^3 + c x^2 + d x + e
+void solve_quantic_equation(double a, double b, double c, double d, double e, double re_out[4], double im_out[4]);
 
 // Perlin::noise / turb — src/algebra/noise.rs:43-86
 double perlin_noise(const rt_perlin& pn, V3 p);

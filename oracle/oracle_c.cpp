@@ -244,6 +244,10 @@ void orc_shape_hits(const Scene* sc, const rt_ray* ray, double min_t, uint8_t* h
     }
 }
 
+void orc_solve_quartic(double a, double b, double c, double d, double e, double* re4, double* im4) {
+    solve_quantic_equation(a, b, c, d, e, re4, im4);
+}
+
 // ---- Perlin noise (src/algebra/noise.rs) ---------------------------------------------------------
 double orc_perlin_noise(const rt_perlin* pn, rt_vec3 p) { return perlin_noise(*pn, fr(p)); }
 double orc_perlin_turb(const rt_perlin* pn, rt_vec3 p, int depth) { return perlin_turb(*pn, fr(p), depth); }

@@ -85,6 +85,7 @@ def lib() -> C.CDLL:
                                           C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_void_p]
     L.orc_hardware_threads.restype = C.c_uint32
     L.orc_shape_hits.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
+    L.orc_solve_quartic.argtypes = [C.c_double] * 5 + [d16, d16]
     L.orc_perlin_noise.argtypes = [C.c_void_p, Vec3]
     L.orc_perlin_noise.restype = C.c_double
     L.orc_perlin_turb.argtypes = [C.c_void_p, Vec3, C.c_int]
@@ -162,6 +163,13 @@ def philox_stream(seed, pixel, sample, event, n) -> np.ndarray:
     out = np.empty(n)
     lib().orc_philox_stream(seed, pixel, sample, event, n, _p(out))
     return out
+
+
+def solve_quartic(a, b, c, d, e) -> np.ndarray:
+    """solve_quantic_equation (src/algebra/equation.rs:17-67): the four complex roots"""
+    re, im = np.empty(4), np.empty(4)
+    lib().orc_solve_quartic(a, b, c, d, e, _p(re), _p(im))
+    return re + 1j * im
 
 
 def perlin_noise(table, p) -> float:

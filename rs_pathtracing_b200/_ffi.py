@@ -13,7 +13,7 @@ HOST_SO = os.path.join(HERE, "librt_b200_host.so")
 RT_OK = 0
 RT_ERR_INVALID, RT_ERR_NO_DEVICE, RT_ERR_CUDA, RT_ERR_STATE, RT_ERR_NOMEM = -1, -2, -3, -4, -5
 RT_ISECT_BRUTE, RT_ISECT_FAST, RT_ISECT_VERIFY = 0, 1, 2
-RT_SHAPE_SPHERE, RT_SHAPE_CUBE, RT_SHAPE_RECTANGLE, RT_SHAPE_MARCH = 0, 1, 2, 3
+RT_SHAPE_SPHERE, RT_SHAPE_CUBE, RT_SHAPE_RECTANGLE, RT_SHAPE_MARCH, RT_SHAPE_TORUS = 0, 1, 2, 3, 4
 RT_SURF_HEART, RT_SURF_SINE, RT_SURF_STAR, RT_SURF_DUPIN, RT_SURF_HUNTS, RT_SURF_CUSHION = range(6)
 RT_MAT_LAMBERTIAN, RT_MAT_METAL, RT_MAT_DIELECTRIC, RT_MAT_DIFFUSE_LIGHT, RT_MAT_EMPTY = range(5)
 RT_TEX_SOLID, RT_TEX_CHECKER, RT_TEX_UV_CHECKER, RT_TEX_IMAGE, RT_TEX_NOISE = range(5)
@@ -117,7 +117,7 @@ class Stats(C.Structure):
         ("launches_extend", C.c_uint64),
         ("launches_march", C.c_uint64),
         ("launches_shade", C.c_uint64),
-        ("march_prof", C.c_uint64 * 4),
+        ("march_prof", C.c_uint64 * 8),
     ]
 
 

@@ -467,8 +467,11 @@ struct Builder {
                 throw std::runtime_error("BruteForsableShape.depth: expected u8");
             p[2] = depth;
             push_shape(RT_SHAPE_MARCH, 0, parse_transform(v.at("transform")), p, material_index(v), name);
-        } else if (type == "Torus") {
-            throw std::runtime_error("Torus is outside the accelerated hot path (SURVEY §8f)");
+        } else if (type == "Torus") {  // shapes/mod.rs:766-789
+            (void)v.at("name");
+            p[0] = v.at("radius").as_number();
+            p[1] = v.at("tube_radius").as_number();
+            push_shape(RT_SHAPE_TORUS, 0, parse_transform(v.at("transform")), p, material_index(v), name);
         } else {
             throw std::runtime_error("unknown variant `" + type + "` for ShapeJson");
         }

@@ -143,6 +143,11 @@ __device__ __noinline__ unsigned long long count_false_culls(const DevScene& S, 
         int winner = -1;
         bool degenerate = false;
         DevCounters cc = {};
+        if (S.kind[i] == RT_SHAPE_TORUS) {   // (analytic_test only marks a reached torus for the replay: test it exactly here)
+            double t;
+            if (shape_candidate<false>(S, i, RT_SHAPE_TORUS, S.inv + 12 * i, ro, rd, min_t, INFINITY, t, cc)) bad++;
+            continue;
+        }
         analytic_test<false>(S, i, ro, rd, min_t, best, winner, degenerate, cc);
         if (winner >= 0 || degenerate) bad++;
     }
@@ -833,7 +838,7 @@ static int validate_desc(const rt_scene_desc* d) {
     if ((d->n_materials && !d->materials) || (d->n_textures && !d->textures) || (d->n_images && !d->images))
         return fail(RT_ERR_INVALID, "scene description: null table");
     for (uint32_t i = 0; i < d->n_shapes; i++) {
-        if (d->kind[i] > RT_SHAPE_MARCH) return fail(RT_ERR_INVALID, "scene description: unknown shape kind");
+        if (d->kind[i] > RT_SHAPE_TORUS) return fail(RT_ERR_INVALID, "scene description: unknown shape kind");
         if (d->material[i] >= d->n_materials) return fail(RT_ERR_INVALID, "scene description: material index out of range");
         if (d->kind[i] == RT_SHAPE_MARCH) {
             double sk = d->params[(size_t)i * RT_SHAPE_PARAMS];
@@ -968,7 +973,7 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
     // conservative cull tree (rt_cull.cuh)
     {
         CullTree ct = cull_build(d->inverse, d->kind, (int)n, getenv("RT_B200_NO_CULL") != nullptr,
-                                 getenv("RT_B200_NO_CULL_TREE") != nullptr || getenv("RT_B200_NO_CULL") != nullptr);
+                                 getenv("RT_B200_NO_CULL_TREE") != nullptr || getenv("RT_B200_NO_CULL") != nullptr, d->params);
         sc->ds.n_roots = ct.n_roots;
         sc->ds.n_upper = ct.n_upper;
         for (int l = 0; l <= RT_CULL_UPPER_MAX; l++) sc->ds.upper_off[l] = ct.upper_off[l];
@@ -1946,7 +1951,7 @@ int rt_get_stats(rt_scene* sc, rt_stats* out) {
     out->last_intersect_ms = sc->last_intersect_ms;
     out->verify_rays = c.verify_rays;
     out->verify_false_culls = c.verify_false_culls;
-    for (int k = 0; k < 4; k++) out->march_prof[k] = c.march_prof[k];
+    for (int k = 0; k < 8; k++) out->march_prof[k] = c.march_prof[k];
     out->ms_raygen = sc->ms_cls[RT_KCLASS_RAYGEN];
     out->ms_extend = sc->ms_cls[RT_KCLASS_EXTEND];
     out->ms_march = sc->ms_cls[RT_KCLASS_MARCH];
@@ -2003,7 +2008,7 @@ int rt_cull_tree_check(const rt_scene_desc* d, uint32_t* n_roots, uint32_t* n_gr
     if (rc != RT_OK) return rc;
     if (!n_roots || !n_groups || !n_tree || !n_flat || !worst) return fail(RT_ERR_INVALID, "null argument");
     const int n = (int)d->n_shapes;
-    CullTree ct = cull_build(d->inverse, d->kind, n, false, false);
+    CullTree ct = cull_build(d->inverse, d->kind, n, false, false, d->params);
     *n_roots = (uint32_t)ct.n_roots;
     *n_groups = (uint32_t)ct.n_groups;
     *n_flat = (uint32_t)ct.n_flat_real;
@@ -2025,7 +2030,8 @@ int rt_cull_tree_check(const rt_scene_desc* d, uint32_t* n_roots, uint32_t* n_gr
         if (g >= ct.n_groups || !isfinite(grp[g].w)) return fail(RT_ERR_STATE, "cull tree: shape in a padding group");
         // the shape's true world ball, from its own transform (not from the table entry)
         double r;
-        const float4 leaf = cull_entry(d->inverse + (size_t)12 * i, d->kind[i], &r);
+        const double* qi = d->params + (size_t)RT_SHAPE_PARAMS * i;
+        const float4 leaf = cull_entry(d->inverse + (size_t)12 * i, d->kind[i], &r, fabs(qi[0]) + fabs(qi[1]));
         const double* m = d->direct + (size_t)12 * i;   // centre = direct * origin
         const double c[3] = {m[3], m[7], m[11]};
         (void)leaf;
@@ -2069,7 +2075,7 @@ int rt_cull_reached(const rt_scene_desc* d, const rt_ray* rays, uint64_t n_rays,
     if (rc != RT_OK) return rc;
     if ((n_rays && !rays) || !reached) return fail(RT_ERR_INVALID, "null argument");
     const int n = (int)d->n_shapes;
-    const CullTree ct = cull_build(d->inverse, d->kind, n, false, false);
+    const CullTree ct = cull_build(d->inverse, d->kind, n, false, false, d->params);
     std::vector<std::pair<int, float4>> march;  // (shape, ball around its marching bound), like rt_scene_create
     for (int i = 0; i < n; i++) {
         if (d->kind[i] != RT_SHAPE_MARCH) continue;

@@ -67,12 +67,14 @@ namespace rt {
 // ---- host: one table entry per shape --------------------------------------------------------------
 // (cx, cy, cz, A): A = 1.1 R^2 + 3B|C|^2 rounded up; A = +inf: never culled; A = -inf: never tested
 // (padding and ray-marched shapes, masked out by the chunk's valid bits anyway).
-inline float4 cull_entry(const double* m, int kind, double* radius_out = nullptr) {
+// `ext`: object-space radius of the shape's bounding ball where the kind alone does not tell (Torus: radius + tube_radius).
+inline float4 cull_entry(const double* m, int kind, double* radius_out = nullptr, double ext = 0.0) {
     if (radius_out) *radius_out = INFINITY;
     const float INF = INFINITY;
     float4 never = make_float4(0.f, 0.f, 0.f, INF);
     if (kind == RT_SHAPE_MARCH) return make_float4(0.f, 0.f, 0.f, -INF);
-    if (kind != RT_SHAPE_SPHERE && kind != RT_SHAPE_CUBE) return never;
+    if (kind == RT_SHAPE_TORUS && !(ext > 0.0 && ext < 1e150)) return never;
+    if (kind != RT_SHAPE_SPHERE && kind != RT_SHAPE_CUBE && kind != RT_SHAPE_TORUS) return never;
     const double a[3][3] = {{m[0], m[1], m[2]}, {m[4], m[5], m[6]}, {m[8], m[9], m[10]}};
     const double tv[3] = {m[3], m[7], m[11]};
     double c[3][3];  // cofactors
@@ -104,7 +106,10 @@ inline float4 cull_entry(const double* m, int kind, double* radius_out = nullptr
     if (!(kappa <= RT_CULL_MAX_KAPPA)) return never;
     double C[3];
     for (int r = 0; r < 3; r++) C[r] = -(inv[r][0] * tv[0] + inv[r][1] * tv[1] + inv[r][2] * tv[2]);
-    const double ext2 = kind == RT_SHAPE_CUBE ? 3.0 : 1.0;
+    // Torus (shapes/mod.rs:429-452): a line whose distance from the centre exceeds radius + tube_radius has no real
+    // intersection; the quartic's roots are then complex with imaginary parts of the order of the miss distance,
+    // nowhere near the 1e-15 the reference accepts as real.  The ball test runs on the line like the Sphere's.
+    const double ext2 = kind == RT_SHAPE_CUBE ? 3.0 : kind == RT_SHAPE_TORUS ? ext * ext : 1.0;
     const double R2 = ext2 * n_inv * (1.0 + 1e-9);
     const double cc = C[0] * C[0] + C[1] * C[1] + C[2] * C[2];
     const double A = 1.1 * R2 + 3.0 * RT_CULL_B * cc;
@@ -190,7 +195,9 @@ inline float4 cull_node_entry(const CullBall& n) {
 
 // `inverse`: [n][12] inverse rows, `kind`: [n].  no_cull: every analytic shape goes to the flat list with
 // A = +inf (debug switch RT_B200_NO_CULL); no_tree: flat list only (RT_B200_NO_CULL_TREE).
-inline CullTree cull_build(const double* inverse, const uint8_t* kind, int n, bool no_cull, bool no_tree) {
+// `params`: [n][RT_SHAPE_PARAMS] (may be null: Torus shapes are then never culled).
+inline CullTree cull_build(const double* inverse, const uint8_t* kind, int n, bool no_cull, bool no_tree,
+                           const double* params = nullptr) {
     const float4 pad = make_float4(0.f, 0.f, 0.f, -INFINITY);
     CullTree t;
     t.group_of.assign(n, -2);
@@ -201,7 +208,9 @@ inline CullTree cull_build(const double* inverse, const uint8_t* kind, int n, bo
     for (int i = 0; i < n; i++) {
         if (kind[i] == RT_SHAPE_MARCH) continue;
         double r;
-        t.leaf[i] = cull_entry(inverse + (size_t)12 * i, kind[i], &r);
+        const double ext = (kind[i] == RT_SHAPE_TORUS && params)
+                               ? fabs(params[(size_t)RT_SHAPE_PARAMS * i]) + fabs(params[(size_t)RT_SHAPE_PARAMS * i + 1]) : 0.0;
+        t.leaf[i] = cull_entry(inverse + (size_t)12 * i, kind[i], &r, ext);
         if (no_cull) t.leaf[i].w = INFINITY;
         ball[i] = CullBall{{(double)t.leaf[i].x, (double)t.leaf[i].y, (double)t.leaf[i].z}, r};
         // the leaf entry's centre is the FP32-rounded one; the enclosing balls must contain the true ball:

@@ -215,13 +215,14 @@ __device__ __forceinline__ void m3_load_core(const DevScene& S, Rec rec, Marcher
     m.skip_ok = ((w.x >> 24) & M3_FLAG_SKIP_OK) != 0;
     more = ((w.x >> 24) & M3_FLAG_MORE) != 0;
     m.have_poly = true;   // (expanded when the shape is started; only read when skip_ok)
+    m.plan_miss_ok = false;   // t lives in the record: only begin()'s hull proof declares misses here
     m.n = w.y;
     m.q = S.params + RT_SHAPE_PARAMS * (int)ks.y;
     m.step0 = rec[F_STEP0];
     m.depth = (int)((ks.x >> 8) & 0xffu);
     m.G = rec[F_G];
     m.sd = m.step * m.d;
-    if (COUNT) m.prof[0] = m.prof[1] = m.prof[2] = m.prof[3] = 0;
+    if (COUNT) m.prof[0] = m.prof[1] = m.prof[2] = m.prof[3] = m.prof[4] = m.prof[5] = 0;
 }
 template <int KIND, bool COUNT>
 __device__ __forceinline__ void m3_store_state(Rec rec, const Marcher<KIND, COUNT>& m, bool more) {
@@ -248,7 +249,7 @@ template <int KIND, bool COUNT>
 __device__ __forceinline__ void m3_add_prof(DevCounters& c, const Marcher<KIND, COUNT>& m) {
     if (COUNT) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) c.march_prof[k] += m.prof[k];
+        for (int k = 0; k < 6; k++) c.march_prof[k] += m.prof[k];
     }
 }
 
@@ -389,9 +390,7 @@ k_march3(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32
                             M m;
                             m.begin(q, o, d, start, end_c, S.march_G[k], S.march_F[k]);
                             if (COUNT) c.march_rays++;
-                            if (m.skip_ok) {   // the model along the ray, once per (ray, shape): plan_begin's expansion
-                                expand_ray<KIND>(q, m.p, m.d, m.t, m.end, (m.end - m.t) + 4.0 * m.step0, m.G, m.F, m.P);
-                                m.n += 2;
+                            if (m.skip_ok) {   // the model along the ray, once per (ray, shape): expanded by begin()
 #pragma unroll
                                 for (int i = 0; i <= DEG; i++) rec[F_C + i] = m.P.c[i];
                                 rec[F_P0] = m.P.p0.x; rec[F_P0 + 1] = m.P.p0.y; rec[F_P0 + 2] = m.P.p0.z;

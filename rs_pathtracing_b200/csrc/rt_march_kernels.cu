@@ -5,6 +5,7 @@
 // (RT_B200_MARCH=1 / 2) as bit-identity cross-checks (tests/test_gpu_render.py) and as the baseline the profiles
 // compare against.  Compile with -fmad=false (see rt_math.cuh).
 #include <cuda_runtime.h>
+#include <cstdio>
 
 #include <algorithm>
 
@@ -44,9 +45,18 @@ __device__ __forceinline__ void coop_advance(unsigned jumping, long long mj, dou
         long long left = active ? mm : 0;
         // one binade (or one stretch of the near-zero walk) per trip; the lanes whose task is finished -- or
         // that never had one -- do their co-work (literal steps of their own rays) instead of idling
+#ifdef RT_MARCH_WATCHDOG
+        unsigned long long wd_adv = 0;
+#endif
         while (__any_sync(FULL, left > 0)) {
             if (left > 0) advance_iter(res, s, left);
             co_work();
+#ifdef RT_MARCH_WATCHDOG
+            if (++wd_adv == 5000000ull) {
+                if (RT_MARCH_WATCHDOG == 1) printf("WD-ADV blk %d lane %d: left %lld res %.17g s %.17g mm %lld comp %d\n", blockIdx.x, threadIdx.x, left, res, s, mm, comp);
+                left = 0;
+            }
+#endif
         }
 #pragma unroll
         for (int c = 0; c < 4; c++) {
@@ -87,80 +97,108 @@ k_march(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32_
     int shape = -1, winner = -1;
     double best = 0.0;
     Marcher<KIND, COUNT> m;
-    for (;;) {
-        // ---- refill ------------------------------------------------------------------------------
-        const unsigned idle = __ballot_sync(FULL, !have && !exhausted);
-        const unsigned busy = __ballot_sync(FULL, have);
-        if (idle && (busy == 0 || __popc(idle) >= RT_MARCH_REFILL_MIN)) {
-            uint32_t base = 0;
-            const int leader = __ffs(idle) - 1;
-            if (lane == leader) base = atomicAdd(head, (uint32_t)__popc(idle));
-            base = __shfl_sync(FULL, base, leader);
-            if (!have && !exhausted) {
-                const uint32_t j = base + __popc(idle & ((1u << lane) - 1u));
-                if (j < n) {
-                    entry = j;
-                    slot = hq.mq_slot[j];
-                    mask = hq.mq_mask[j] & kind_mask;
-                    best = hq.t[slot];
-                    winner = hq.index[slot];
-                    have = mask != 0;
-                    marching = false;
-                } else {
-                    exhausted = true;
-                }
-            }
+    // the shape a lane marched is over (phase() == RT_PHASE_END): take its candidate
+    auto finish_shape = [&]() {
+        marching = false;
+        if (COUNT) {
+            c.march_steps += m.n;
+            for (int k = 0; k < 6; k++) c.march_prof[k] += m.prof[k];
+            if (m.n > 2048) c.march_long_rays++;
+            if (m.n > c.march_max_evals) c.march_max_evals = m.n;
         }
-        if (__ballot_sync(FULL, have) == 0) {
-            if (__ballot_sync(FULL, !exhausted) == 0) break;
-            continue;
-        }
-        // ---- start the next marched shape of this lane's entry (batched like the refill) -------------
-        const unsigned need_start = __ballot_sync(FULL, have && !marching);
-        const unsigned marching_any = __ballot_sync(FULL, marching);
-        if (have && !marching && (marching_any == 0 || __popc(need_start) >= RT_MARCH_REFILL_MIN)) {
-            if (mask == 0) {
-                hq.t[slot] = best;
-                hq.index[slot] = winner;
+        if (m.finish() == RT_MARCH_DONE && !(m.t < 0.001)) {  // ray_marching.rs:55 with max_t = +inf
+            const double t = m.t;
+            if (t != t) {  // NaN candidate: replay now, and hide the entry from later kind passes
+                replay_brute(S, in, hq, slot);
+                hq.mq_mask[entry] = 0;
                 have = false;
-            } else {
-                const int k = __ffs(mask) - 1;
-                mask &= mask - 1;
-                shape = S.march_index[k];
-                const double* q = S.params + RT_SHAPE_PARAMS * shape;
-                D3 ro = mk(in.ox[slot], in.oy[slot], in.oz[slot]);
-                D3 rd = mk(in.dx[slot], in.dy[slot], in.dz[slot]);
-                D3 o, d;
-                double start, end_c;
-                if (march_needed(S, S.inv + 12 * shape, q, ro, rd, best, o, d, start, end_c)) {
-                    m.begin(q, o, d, start, end_c, S.march_G[k], S.march_F[k]);
-                    marching = true;
-                    if (COUNT) c.march_rays++;
-                }
+            } else if (t < best || (t == best && shape > winner)) {
+                best = t;
+                winner = shape;
             }
+        }
+    };
+#ifdef RT_MARCH_WATCHDOG
+    unsigned long long wd_iter = 0;
+#endif
+    for (;;) {
+#ifdef RT_MARCH_WATCHDOG
+        if (++wd_iter == 20000000ull || wd_iter == 20000001ull) {
+            if (RT_MARCH_WATCHDOG == 2 && lane == 0) atomicAdd(&g_counters->verify_rays, 1ull);
+            if (RT_MARCH_WATCHDOG == 1) printf("WD blk %d lane %d it %llu: have %d marching %d exh %d mask %x entry %u slot %u | ph %d it %d depth %d t %.17g start %.17g end %.17g step %.17g r %.6g cooldown %d backoff %d skip_ok %d n %llu\n",
+                   blockIdx.x, threadIdx.x, wd_iter, (int)have, (int)marching, (int)exhausted, mask, entry, slot,
+                   marching ? m.phase() : -1, m.it, m.depth, m.t, m.start, m.end, m.step, m.r, m.cooldown, m.backoff, (int)m.skip_ok, m.n);
+            if (wd_iter == 20000001ull) break;
+        }
+#endif
+        // ---- fill: lanes without a ray in flight fetch queue entries and start their shapes, again and again
+        //      (the `continue` below), until (nearly) every lane holds a ray that really has to be marched.  Most
+        //      entries never get that far -- the chord is clipped away by the best hit (march_needed), or begin()
+        //      proves the miss from the Bernstein hull -- so this is a filter that runs with many lanes at once, and
+        //      what it leaves in the lanes is the expensive minority.
+        //      (Written as part of the one outer loop on purpose: the same logic as a nested `for (;;)` with two
+        //      breaks hung k_march<Cushion> / k_march<Dupin> on the second frame of a scene -- deterministically per
+        //      binary, gone with any instrumentation; profiles/README.md, r2n.  Keep the nesting shallow.) ---------
+        {
+            const unsigned need = __ballot_sync(FULL, !marching && !exhausted);
+            const unsigned marching_any = __ballot_sync(FULL, marching);
+            if (need != 0 && (marching_any == 0 || __popc(need) >= RT_MARCH_REFILL_MIN)) {
+                if (have && !marching && mask == 0) {   // every shape of the entry is done
+                    hq.t[slot] = best;
+                    hq.index[slot] = winner;
+                    have = false;
+                }
+                const unsigned idle = __ballot_sync(FULL, !have && !exhausted);
+                if (idle) {
+                    uint32_t base = 0;
+                    const int leader = __ffs(idle) - 1;
+                    if (lane == leader) base = atomicAdd(head, (uint32_t)__popc(idle));
+                    base = __shfl_sync(FULL, base, leader);
+                    if (!have && !exhausted) {
+                        const uint32_t j = base + __popc(idle & ((1u << lane) - 1u));
+                        if (j < n) {
+                            entry = j;
+                            slot = hq.mq_slot[j];
+                            mask = hq.mq_mask[j] & kind_mask;
+                            best = hq.t[slot];
+                            winner = hq.index[slot];
+                            have = mask != 0;
+                        } else {
+                            exhausted = true;
+                        }
+                    }
+                }
+                if (have && !marching && mask != 0) {   // the entry's next marched shape
+                    const int k = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    shape = S.march_index[k];
+                    const double* q = S.params + RT_SHAPE_PARAMS * shape;
+                    D3 ro = mk(in.ox[slot], in.oy[slot], in.oz[slot]);
+                    D3 rd = mk(in.dx[slot], in.dy[slot], in.dz[slot]);
+                    D3 o, d;
+                    double start, end_c;
+                    if (march_needed(S, S.inv + 12 * shape, q, ro, rd, best, o, d, start, end_c)) {
+                        m.begin(q, o, d, start, end_c, S.march_G[k], S.march_F[k]);
+                        marching = true;
+                        if (COUNT) c.march_rays++;
+                        if (m.phase() == RT_PHASE_END) finish_shape();   // a proven miss (or an empty range)
+                    }
+                }
+                // again, as long as the filter leaves lanes empty (the votes at the top decide)
+                const unsigned still = __ballot_sync(FULL, !marching && !exhausted);
+                if (still != 0 && __popc(still) >= RT_MARCH_REFILL_MIN) continue;
+            }
+        }
+        if (__ballot_sync(FULL, marching) == 0) {
+            if (__ballot_sync(FULL, have || !exhausted) == 0) break;
+            continue;
         }
         // ---- marching: the warp votes between the expensive exact-jump attempt and the cheap literal
         //      steps, so that attempts run with many lanes at once ---------------------------------------
         int ph = marching ? m.phase() : -1;
         if (ph == RT_PHASE_END) {
-            marching = false;
-            if (COUNT) {
-                c.march_steps += m.n;
-                for (int k = 0; k < 4; k++) c.march_prof[k] += m.prof[k];
-                if (m.n > 2048) c.march_long_rays++;
-                if (m.n > c.march_max_evals) c.march_max_evals = m.n;
-            }
-            if (m.finish() == RT_MARCH_DONE && !(m.t < 0.001)) {  // ray_marching.rs:55 with max_t = +inf
-                const double t = m.t;
-                if (t != t) {  // NaN candidate: replay now, and hide the entry from later kind passes
-                    replay_brute(S, in, hq, slot);
-                    hq.mq_mask[entry] = 0;
-                    have = false;
-                } else if (t < best || (t == best && shape > winner)) {
-                    best = t;
-                    winner = shape;
-                }
-            }
+            finish_shape();
+            ph = -1;
         }
         const unsigned want_attempt = __ballot_sync(FULL, ph == RT_PHASE_ATTEMPT);
         const unsigned want_literal = __ballot_sync(FULL, ph == RT_PHASE_LITERAL);
@@ -236,6 +274,7 @@ __device__ __forceinline__ void m2_load_core(const DevScene& S, const MarchRec* 
     m.backoff = (int)((w.x >> 16) & 0xffu);
     m.skip_ok = ((w.x >> 24) & RT_M2_FLAG_SKIP_OK) != 0;
     m.have_poly = ((w.x >> 24) & RT_M2_FLAG_HAVE_POLY) != 0;
+    m.plan_miss_ok = true;   // (m2_store_core keeps the t = +inf a proven miss leaves behind)
     m.n = w.y;
     k = (int)ks.x;
     m.q = S.params + RT_SHAPE_PARAMS * (int)ks.y;
@@ -246,7 +285,7 @@ __device__ __forceinline__ void m2_load_core(const DevScene& S, const MarchRec* 
     m.sd = m.step * m.d;
     if (COUNT) {
         const uint2 p0 = m2_get_u2(rec, 30), p1 = m2_get_u2(rec, 31);
-        m.prof[0] = p0.x; m.prof[1] = p0.y; m.prof[2] = p1.x; m.prof[3] = p1.y;
+        m.prof[0] = p0.x; m.prof[1] = p0.y; m.prof[2] = p1.x; m.prof[3] = p1.y; m.prof[4] = m.prof[5] = 0;
     }
 }
 template <int KIND, bool COUNT>
@@ -442,7 +481,7 @@ k_march2(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32
                         const int shape = (int)ks.y;
                         if (COUNT) {
                             c.march_steps += m.n;
-                            for (int q = 0; q < 4; q++) c.march_prof[q] += m.prof[q];
+                            for (int q = 0; q < 6; q++) c.march_prof[q] += m.prof[q];
                             if (m.n > 2048) c.march_long_rays++;
                             if (m.n > c.march_max_evals) c.march_max_evals = m.n;
                         }
@@ -472,6 +511,7 @@ k_march2(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32
                             m.begin(q, o, d, start, end_c, S.march_G[k], S.march_F[k]);
                             if (COUNT) c.march_rays++;
                             m2_store_core(rec, m, true);
+                            if (m.have_poly) m2_store_poly(rec, m);   // begin() expands the model when skip_ok
                             m2_set_u2(rec, 29, (uint32_t)k, (uint32_t)shape);
                             s_phase[slot] = m2_phase_of(m.phase());
                             started = true;

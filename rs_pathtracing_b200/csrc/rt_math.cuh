@@ -240,6 +240,110 @@ __device__ inline D3 surface_gradient(const double* q, D3 p) {
 
 #define RT_MARCH_BUDGET 200000000ull
 
+// ---- Torus (src/world/shapes/mod.rs:403-494) on solve_quantic_equation (src/algebra/equation.rs:17-67) ----------
+// num::Complex<f64> arithmetic as the crate `num ^0.4` (num-complex 0.4.x) defines it: +, -, scalar * and /
+// componentwise; complex * = (re re' - im im', re im' + im re'); complex / through norm_sqr; sqrt / cbrt by cases
+// (im == 0, re == 0, else the polar form), signs of zero respected.  hypot / atan2 / cos / sin / cbrt are CUDA's
+// (1-2 ulp): the roots agree with a glibc build to ~1e-15 relative, the `|im| < 1e-15` acceptance test of the
+// caller does not always (Torus).
+struct Cx {
+    double re, im;
+};
+__device__ __forceinline__ Cx cxr(double re) { return Cx{re, 0.0}; }
+__device__ __forceinline__ Cx operator+(Cx a, Cx b) { return Cx{a.re + b.re, a.im + b.im}; }
+__device__ __forceinline__ Cx operator-(Cx a, Cx b) { return Cx{a.re - b.re, a.im - b.im}; }
+__device__ __forceinline__ Cx operator-(Cx a) { return Cx{-a.re, -a.im}; }
+__device__ __forceinline__ Cx operator*(Cx a, Cx b) { return Cx{a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ Cx operator/(Cx a, Cx b) {
+    const double norm_sqr = b.re * b.re + b.im * b.im;
+    const double re = a.re * b.re + a.im * b.im;
+    const double im = a.im * b.re - a.re * b.im;
+    return Cx{re / norm_sqr, im / norm_sqr};
+}
+__device__ __forceinline__ Cx operator*(double k, Cx a) { return Cx{k * a.re, k * a.im}; }
+__device__ __forceinline__ Cx operator/(Cx a, double k) { return Cx{a.re / k, a.im / k}; }
+__device__ __forceinline__ Cx cx_from_polar(double r, double theta) { return Cx{r * cos(theta), r * sin(theta)}; }
+static __device__ __noinline__ Cx cx_sqrt(Cx z) {
+    if (z.im == 0.0) {
+        if (!signbit(z.re)) return Cx{sqrt(z.re), z.im};
+        const double im = sqrt(-z.re);
+        return !signbit(z.im) ? Cx{0.0, im} : Cx{0.0, -im};
+    }
+    if (z.re == 0.0) {
+        const double x = sqrt(fabs(z.im) / 2.0);
+        return !signbit(z.im) ? Cx{x, x} : Cx{x, -x};
+    }
+    return cx_from_polar(sqrt(hypot(z.re, z.im)), atan2(z.im, z.re) / 2.0);
+}
+static __device__ __noinline__ Cx cx_cbrt(Cx z) {
+    if (z.im == 0.0) {
+        if (!signbit(z.re)) return Cx{cbrt(z.re), z.im};
+        const double re = cbrt(-z.re) / 2.0;
+        const double im = sqrt(3.0) * re;
+        return !signbit(z.im) ? Cx{re, im} : Cx{re, -im};
+    }
+    if (z.re == 0.0) {
+        const double im = cbrt(fabs(z.im)) / 2.0;
+        const double re = sqrt(3.0) * im;
+        return !signbit(z.im) ? Cx{re, im} : Cx{re, -im};
+    }
+    return cx_from_polar(cbrt(hypot(z.re, z.im)), atan2(z.im, z.re) / 3.0);
+}
+// equation.rs:17-67
+static __device__ __noinline__ void solve_quartic(double a_, double b_, double c_, double d_, double e_, Cx roots[4]) {
+    const Cx a = cxr(a_), b = cxr(b_) / a, c = cxr(c_) / a, d = cxr(d_) / a, e = cxr(e_) / a;
+    const Cx b2 = b * b;
+    const Cx alpha = c - (3.0 / 8.0) * b2;
+    const Cx beta = (b2 * b) / 8.0 - (b * c) / 2.0 + d;
+    const Cx gamma = (-3.0 / 256.0) * b2 * b2 + b2 * c / 16.0 - b * d / 4.0 + e;
+    const Cx alpha2 = alpha * alpha;
+    const Cx t = -b / 4.0;
+    if (approx_zero(beta.re) && approx_zero(beta.im)) {
+        const Cx r = cx_sqrt(alpha2 - 4.0 * gamma);
+        const Cx r1 = cx_sqrt((-alpha + r) / 2.0);
+        const Cx r2 = cx_sqrt((-alpha - r) / 2.0);
+        roots[0] = t + r1; roots[1] = t - r1; roots[2] = t + r2; roots[3] = t - r2;
+    } else {
+        const Cx p = -(alpha2 / 12.0 + gamma);
+        const Cx q = -alpha2 * alpha / 108.0 + alpha * gamma / 3.0 - beta * beta / 8.0;
+        const Cx r = -q / 2.0 + cx_sqrt(q * q / 4.0 + p * p * p / 27.0);
+        const Cx u = cx_cbrt(r);
+        Cx y = (-5.0 / 6.0) * alpha + u;
+        if (approx_zero(u.re) && approx_zero(u.im)) y = y - cx_cbrt(q);
+        else y = y - p / (3.0 * u);
+        const Cx w = cx_sqrt(alpha + 2.0 * y);
+        const Cx r1 = cx_sqrt(-(3.0 * alpha + 2.0 * y + 2.0 * beta / w));
+        const Cx r2 = cx_sqrt(-(3.0 * alpha + 2.0 * y - 2.0 * beta / w));
+        roots[0] = t + (w - r1) / 2.0; roots[1] = t + (w + r1) / 2.0;
+        roots[2] = t + (-w - r2) / 2.0; roots[3] = t + (-w + r2) / 2.0;
+    }
+}
+// Torus::ray_intersect, shapes/mod.rs:429-452: the candidate t (the smallest root accepted as real), range-checked
+static __device__ __noinline__ bool torus_candidate(const double* q, D3 origin, D3 dir, double min_t, double max_t, double& t_out) {
+    const double radius = q[0], tube_radius = q[1];
+    const double t = 4.0 * radius * radius;
+    const double g = t * (dir.x * dir.x + dir.y * dir.y);
+    const double h = 2.0 * t * (origin.x * dir.x + origin.y * dir.y);
+    const double i = t * (origin.x * origin.x + origin.y * origin.y);
+    const double j = dot(dir, dir);
+    const double k = 2.0 * dot(origin, dir);
+    const double l = dot(origin, origin) + radius * radius - tube_radius * tube_radius;
+    const double a = j * j;
+    const double b = 2.0 * j * k;
+    const double c = 2.0 * j * l + k * k - g;
+    const double d = 2.0 * k * l - h;
+    const double e = l * l - i;
+    Cx roots[4];
+    solve_quartic(a, b, c, d, e, roots);
+    double min_root = INFINITY;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+        if (approx_zero(roots[r].im) && roots[r].re < min_root) min_root = roots[r].re;
+    if (isinf(min_root) || min_root < min_t || min_root > max_t) return false;
+    t_out = min_root;
+    return true;
+}
+
 // solve_quadratic_equation, src/algebra/equation.rs:5-15
 __device__ __forceinline__ bool solve_quadratic(double a, double half_b, double c, double& x1, double& x2) {
     double d = half_b * half_b - a * c;

@@ -57,7 +57,7 @@ __device__ __forceinline__ void flush_counters(const DevCounters& c, DevCounters
     if (c.verify_rays) atomicAdd(&g->verify_rays, c.verify_rays);
     if (c.verify_false_culls) atomicAdd(&g->verify_false_culls, c.verify_false_culls);
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
+    for (int k = 0; k < 6; k++) {
         unsigned long long x = c.march_prof[k];
         for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
         if ((threadIdx.x & 31) == 0 && x) atomicAdd(&g->march_prof[k], x);

@@ -62,7 +62,7 @@ struct DevCounters {
     unsigned long long march_max_evals;  // most evaluations any single marched ray needed
     unsigned long long verify_rays;         // RT_ISECT_VERIFY: rays whose FAST result differs from BRUTE
     unsigned long long verify_false_culls;  // RT_ISECT_VERIFY: (ray, shape) pairs culled although the exact test hits
-    unsigned long long march_prof[4];       // k_march: literal steps at level 0 / deeper, exact jumps, bound hops
+    unsigned long long march_prof[8];       // k_march: literal steps at level 0 / deeper, exact jumps, bound hops, misses by hull / by hops
 };
 
 struct HitRec {  // RayHit, src/world/ray.rs:21-29
@@ -113,6 +113,16 @@ __device__ inline void finalize_hit(const DevScene& S, int i, double t, D3 ro, D
             }
             break;
         }
+        case RT_SHAPE_TORUS: {  // shapes/mod.rs:453-468
+            n = p - normalize(mk(p.x, p.y, 0.0)) * q[0];
+            if (want_uv) {
+                const double theta = asin(p.z / q[1]);
+                const double phi = acos(p.z / (q[0] + q[1] * cos(theta))) + PI;
+                u = phi / (2.0 * PI);
+                v = theta / PI;
+            }
+            break;
+        }
         default: {  // RT_SHAPE_MARCH, ray_marching.rs:59-61
             n = surface_gradient(q, p);
             int sk = (int)q[0];
@@ -143,6 +153,7 @@ __device__ __forceinline__ bool shape_candidate(const DevScene& S, int i, int ki
     if (kind == RT_SHAPE_SPHERE) return sphere_candidate(o, d, min_t, max_t, t);
     if (kind == RT_SHAPE_CUBE) return cube_candidate(o, d, min_t, max_t, t);
     if (kind == RT_SHAPE_RECTANGLE) return rect_candidate(S.params + RT_SHAPE_PARAMS * i, o, d, min_t, max_t, t);
+    if (kind == RT_SHAPE_TORUS) return torus_candidate(S.params + RT_SHAPE_PARAMS * i, o, d, min_t, max_t, t);
     unsigned long long ev = 0;
     bool ok = march_candidate(S.params + RT_SHAPE_PARAMS * i, o, d, min_t, max_t, t, ev);
     if (COUNT) {
@@ -205,6 +216,13 @@ __device__ __forceinline__ void analytic_test_at(int i, int kind, const double2*
     if (COUNT) c.shape_tests++;
     double t;
     bool ok;
+    if (kind == RT_SHAPE_TORUS) {
+        // Torus (shapes/mod.rs:429-476): the complex quartic solver stays out of this loop (its call frame cost
+        // every scene 240 B of spills in k_extend).  A ray whose line touches the torus's bounding ball is replayed
+        // through the literal loop instead (k_replay -> nearest_hit_brute -> torus_candidate), like a degenerate one.
+        degenerate = true;
+        return;
+    }
     if (kind == RT_SHAPE_RECTANGLE) {
         // Rectangle::ray_intersect (shapes/mod.rs:181-190) needs only o.z, d.z to reject most rays: row 2 of the
         // inverse first, the other rows when x = -o.z / d.z is in range (same operations, same order as

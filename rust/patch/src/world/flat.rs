@@ -20,6 +20,7 @@ use crate::algebra::transform::InversableTransform;
 /// params[8] of a shape row (RT_SHAPE_PARAMS):
 ///   Sphere, Cube       all zero
 ///   Rectangle          [x0, y0, x1, y1, 0, 0, 0, 0]
+///   Torus              [radius, tube_radius, 0, 0, 0, 0, 0, 0]
 ///   RayMarchingShape   [surface kind (RT_SURF_*), step, depth, a, b, c, d, sphere_radius]
 ///                      (Heart: a..sphere_radius = 0, its bound is the fixed ellipsoid of Heart::new;
 ///                       Sine / Star: a; DupinCyclide: a, b, c, d; Hunt / Cushion: only sphere_radius)

@@ -1,9 +1,9 @@
-//! Raw bindings to `include/rt_b200.h` (ABI version 4).  One item per declaration of the header; see
+//! Raw bindings to `include/rt_b200.h` (ABI version 5).  One item per declaration of the header; see
 //! the header for the contract of every entry point and the reference interface it replaces.
 #![allow(non_camel_case_types)]
 use std::os::raw::{c_char, c_int, c_void};
 
-pub const RT_B200_ABI_VERSION: c_int = 4;
+pub const RT_B200_ABI_VERSION: c_int = 5;
 
 // rt_status
 pub const RT_OK: c_int = 0;
@@ -18,6 +18,7 @@ pub const RT_SHAPE_SPHERE: u8 = 0;
 pub const RT_SHAPE_CUBE: u8 = 1;
 pub const RT_SHAPE_RECTANGLE: u8 = 2;
 pub const RT_SHAPE_MARCH: u8 = 3;
+pub const RT_SHAPE_TORUS: u8 = 4;
 pub const RT_SHAPE_FLAG_INVERSE_NORMAL: u8 = 1;
 pub const RT_SHAPE_PARAMS: usize = 8;
 pub const RT_SURF_HEART: u32 = 0;
@@ -67,7 +68,7 @@ pub const RT_ISECT_VERIFY: c_int = 2;
     pub march_steps: u64, pub march_rays: u64, pub march_long_rays: u64, pub march_max_evals: u64,
     pub last_frame_ms: f64, pub last_intersect_ms: f64, pub verify_rays: u64, pub verify_false_culls: u64,
     pub ms_raygen: f64, pub ms_extend: f64, pub ms_march: f64, pub ms_shade: f64, pub ms_resolve: f64,
-    pub launches_extend: u64, pub launches_march: u64, pub launches_shade: u64, pub march_prof: [u64; 4] }
+    pub launches_extend: u64, pub launches_march: u64, pub launches_shade: u64, pub march_prof: [u64; 8] }
 /// opaque: the device-resident scene + renderer state
 pub enum rt_scene {}
 

@@ -29,7 +29,7 @@ def test_core_exports_every_declared_symbol():
     assert names == set(_ffi.CORE_SYMBOLS), names ^ set(_ffi.CORE_SYMBOLS)
     for n in names:
         assert hasattr(lib, n)
-    assert lib.rt_abi_version() == 4
+    assert lib.rt_abi_version() == 5
 
 
 def test_host_exports_every_declared_symbol():

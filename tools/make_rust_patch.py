@@ -65,9 +65,15 @@ SPHERE = '''
         flat.push_shape(sys::RT_SHAPE_SPHERE, flags, &self.transform, [0.0; 8], &self.material);
     }
 '''
+TORUS = '''
+    fn describe(&self, flat: &mut FlatScene) {
+        flat.push_shape(sys::RT_SHAPE_TORUS, 0, &self.transform,
+                        [self.radius, self.tube_radius, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0], &self.material);
+    }
+'''
 UNSUPPORTED = '''
     fn describe(&self, _flat: &mut FlatScene) {
-        // quartic surfaces (solve_quantic_equation) are not part of the GPU core: no scene file instantiates them
+        // no JSON shim, no constructor: a Tooth cannot exist outside this module (and its material is a Box, not a MaterialPtr)
         unimplemented!("%s has no GPU description");
     }
 '''
@@ -195,7 +201,7 @@ def main():
         s = add_to_impl(s, "impl Shape for Rectangle {", RECT)
         s = add_to_impl(s, "impl Shape for Cube {", CUBE)
         s = add_to_impl(s, "impl Shape for Sphere {", SPHERE)
-        s = add_to_impl(s, "impl Shape for Torus {", UNSUPPORTED % "Torus")
+        s = add_to_impl(s, "impl Shape for Torus {", TORUS)
         s = add_to_impl(s, "impl Shape for Tooth {", UNSUPPORTED % "Tooth")
         s = add_to_impl(s, "impl Shape for ShapeCollection {", COLLECTION)
         s = add_to_impl(s, "impl Shape for BvhNode {", BVH)

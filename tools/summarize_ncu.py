@@ -29,6 +29,21 @@ WANT = [
     ("smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "stall branch_resolving / issue"),
     ("smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "stall barrier / issue"),
     ("smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio", "stall not_selected / issue"),
+    ("smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio", "stall no_instruction / issue"),
+    ("smsp__average_warps_issue_stalled_imc_miss_per_issue_active.ratio", "stall imc_miss / issue"),
+    ("smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio", "stall dispatch / issue"),
+    ("smsp__average_warps_issue_stalled_drain_per_issue_active.ratio", "stall drain / issue"),
+    ("smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "stall lg_throttle / issue"),
+    ("smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio", "stall mio_throttle / issue"),
+    ("smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio", "stall tex_throttle / issue"),
+    ("smsp__average_warps_issue_stalled_membar_per_issue_active.ratio", "stall membar / issue"),
+    ("smsp__average_warps_issue_stalled_sleeping_per_issue_active.ratio", "stall sleeping / issue"),
+    ("smsp__average_warps_issue_stalled_misc_per_issue_active.ratio", "stall misc / issue"),
+    ("smsp__average_warps_issue_stalled_selected_per_issue_active.ratio", "stall selected / issue"),
+    ("smsp__inst_executed_op_local_ld.sum", "local loads (warp instr)"),
+    ("smsp__inst_executed_op_local_st.sum", "local stores (warp instr)"),
+    ("sm__cycles_active.avg", "SM active cycles"),
+    ("sm__cycles_elapsed.avg", "SM elapsed cycles"),
 ]
 out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(l for l in out.splitlines() if not l.startswith("==")))
