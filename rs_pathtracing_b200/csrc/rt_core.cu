@@ -757,6 +757,7 @@ struct rt_scene {
     int grid_march2 = 0, grid_march3 = 0;
     size_t smem_march3 = 0;
     bool defer_bound = false;                    // k_extend queues every ray whose line touches a marching bound's ball; k_march sorts out the rest (RT_B200_DEFER_BOUND=1)
+    bool march_filter = true;                    // k_march_filter before the marching kernels (RT_B200_MARCH_FILTER=0: off)
     int march_version = 1;                       // 1: one ray per lane (k_march); RT_B200_MARCH=3: pool of rays per SM + per-phase queues
                                                  // (k_march3, rt_march3.cu: correct but slower, see profiles/); =2: block-local wavefront (k_march2)
     int3 march_tune = make_int3(8, 8, 8);        // k_march scheduling thresholds (RT_B200_MARCH_TUNE=a,b,c)
@@ -1046,6 +1047,7 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
     }
     if (const char* mv = getenv("RT_B200_MARCH")) sc->march_version = std::min(std::max(atoi(mv), 1), 3);
     if (getenv("RT_B200_MARCH_V2")) sc->march_version = 2;
+    if (const char* mf = getenv("RT_B200_MARCH_FILTER")) sc->march_filter = atoi(mf) != 0;
     if (const char* db = getenv("RT_B200_DEFER_BOUND")) sc->defer_bound = atoi(db) != 0;
     sc->grid_shade = occ_grid(k_shade<false, true>, 256, 0);
     sc->wavefront = sc->ds.n_march <= 32 && !getenv("RT_B200_FUSED_BOUNCE");
@@ -1372,6 +1374,13 @@ static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long 
         }
         if (sc->ds.n_march > 0) {
             KernelSpan span(sc, RT_KCLASS_MARCH);
+            if (sc->march_filter) {   // the miss proof for every queued (ray, shape) pair, with full warps
+                MarchLaunch fl;
+                fl.ds = sc->ds; fl.in = in; fl.hq = sc->hq; fl.march_count = mcount; fl.counters = sc->d_counters;
+                fl.count = sc->counters_on; fl.stream = sc->stream; fl.grid_filter = sc->n_sm * 8;
+                rt_launch_march_filter(fl);
+                sc->launches++;
+            }
             for (int kind = 0; kind < 6; kind++) {
                 if (!sc->kind_mask[kind]) continue;
                 uint32_t* head = sc->d_counts + RT_CNT_HEAD + kind * RT_MAX_LEVELS + level;
@@ -1380,6 +1389,7 @@ static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long 
                 ml.march_count = mcount; ml.head = head; ml.counters = sc->d_counters; ml.count = sc->counters_on;
                 ml.stream = sc->stream; ml.version = sc->march_version; ml.grid1 = sc->grid_march; ml.grid2 = sc->grid_march2;
                 ml.grid3 = sc->grid_march3; ml.smem3 = sc->smem_march3; ml.tune = sc->march_tune; ml.march_state = sc->d_march_state;
+                ml.prefiltered = sc->march_filter; ml.grid_filter = 0;
                 rt_launch_march(ml);
                 sc->launches++;
             }

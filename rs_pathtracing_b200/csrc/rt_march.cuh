@@ -405,8 +405,8 @@ enum { RT_PHASE_END = 0, RT_PHASE_ATTEMPT = 1, RT_PHASE_LITERAL = 2 };
 template <int KIND, bool PROF = false>
 struct Marcher {
     static constexpr int DEG = SurfDeg<KIND>::value;
-    unsigned prof[6];  // PROF only: literal steps at level 0 / at refinement levels, jumps, hops, misses proven by the
-                       // Bernstein hull / by the hop loop
+    unsigned prof[8];  // PROF only: literal steps at level 0 / at refinement levels, jumps, hops, misses proven by the
+                       // Bernstein hull / by the hop loop, plans that found nothing to skip, landings that failed the self-check
     const double* q;
     D3 d;
     double start, end, G, F;
@@ -422,8 +422,9 @@ struct Marcher {
     int cooldown, backoff;
     RayPoly<DEG> P;
 
+    // hull: try the miss proof (3) right away (off when k_march_filter has already tried it for this ray)
     __device__ __forceinline__ void begin(const double* q_, D3 o_, D3 d_, double start_, double end_, double G_,
-                                          double F_) {
+                                          double F_, bool hull = true) {
         q = q_; d = d_; start = start_; end = end_; G = G_; F = F_;
         step = q[1];
         step0 = step;
@@ -437,7 +438,7 @@ struct Marcher {
         cooldown = 0;
         backoff = 4;
         have_poly = false;
-        if (PROF) prof[0] = prof[1] = prof[2] = prof[3] = prof[4] = prof[5] = 0;
+        if (PROF) prof[0] = prof[1] = prof[2] = prof[3] = prof[4] = prof[5] = prof[6] = prof[7] = 0;
         // skipping pays when the chord holds many steps (NaN-proof comparisons)
         skip_ok = (G == G) && G < 1e300 && (F == F) && F < 1e300 && step > 0.0 && (end - start) > 64.0 * step &&
                   (end - start) < 1e300;
@@ -465,7 +466,7 @@ struct Marcher {
             }
 #else
             const double L = miss_span(t);
-            if (miss_drift_ok(L)) {
+            if (hull && miss_drift_ok(L)) {
                 const double ta = 0.5 * step0;
                 double sh[DEG + 1];
 #pragma unroll
@@ -679,6 +680,17 @@ struct Marcher {
         const double mf = reach / pl.abs_step * (1.0 - 1e-9) - 2.0;
         if (mf >= (double)RT_MARCH_MIN_JUMP) return (long long)fmin(mf, 1.0e15);
         // inside the |g| < M zone or next to a range limit: plain steps, retry later
+        if (PROF) prof[6]++;
+        if (it > 0) {
+            // A refinement level walks back over ONE step of the level before (<= ~100 steps of its own) towards a sign
+            // change that is known to lie ahead, and |g| only shrinks on the way: a plan that stopped within a few
+            // steps stopped at the band around that very crossing, and planning again before the crossing can only
+            // find the same (it used to: 2.5 empty plans per hit ray on cornell_box, backing off 4, 8, 16 ... steps
+            // through the last level, whose steps of 1e-8 are of the order of the band).  The sign change resets
+            // cooldown (literal()).
+            cooldown = 200;
+            return 0;
+        }
         cooldown = backoff;
         backoff = min(backoff * 2, 64);
         return 0;
@@ -711,6 +723,7 @@ struct Marcher {
             cooldown = pl.more ? 0 : RT_MARCH_LAND_COOLDOWN;
             return;
         }
+        if (PROF) prof[7]++;
         skip_ok = false;  // the model does not describe this ray: finish it with the plain loop
     }
     // the serial form (fused kernels, rt_intersect_batch)

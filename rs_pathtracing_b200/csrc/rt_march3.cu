@@ -222,7 +222,7 @@ __device__ __forceinline__ void m3_load_core(const DevScene& S, Rec rec, Marcher
     m.depth = (int)((ks.x >> 8) & 0xffu);
     m.G = rec[F_G];
     m.sd = m.step * m.d;
-    if (COUNT) m.prof[0] = m.prof[1] = m.prof[2] = m.prof[3] = m.prof[4] = m.prof[5] = 0;
+    if (COUNT) m.prof[0] = m.prof[1] = m.prof[2] = m.prof[3] = m.prof[4] = m.prof[5] = m.prof[6] = m.prof[7] = 0;
 }
 template <int KIND, bool COUNT>
 __device__ __forceinline__ void m3_store_state(Rec rec, const Marcher<KIND, COUNT>& m, bool more) {
@@ -249,7 +249,7 @@ template <int KIND, bool COUNT>
 __device__ __forceinline__ void m3_add_prof(DevCounters& c, const Marcher<KIND, COUNT>& m) {
     if (COUNT) {
 #pragma unroll
-        for (int k = 0; k < 6; k++) c.march_prof[k] += m.prof[k];
+        for (int k = 0; k < 8; k++) c.march_prof[k] += m.prof[k];
     }
 }
 

@@ -85,7 +85,7 @@ __device__ __forceinline__ void coop_advance(unsigned jumping, long long mj, dou
 template <int KIND, bool COUNT>
 __global__ void __launch_bounds__(128, RT_MARCH_MIN_BLOCKS)
 k_march(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32_t* __restrict__ march_count,
-        uint32_t* head, DevCounters* g_counters, int3 tune) {
+        uint32_t* head, DevCounters* g_counters, int3 tune, bool prefiltered) {
     DevCounters c = {};
     const uint32_t n = *march_count;
     const unsigned FULL = 0xffffffffu;
@@ -102,7 +102,7 @@ k_march(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32_
         marching = false;
         if (COUNT) {
             c.march_steps += m.n;
-            for (int k = 0; k < 6; k++) c.march_prof[k] += m.prof[k];
+            for (int k = 0; k < 8; k++) c.march_prof[k] += m.prof[k];
             if (m.n > 2048) c.march_long_rays++;
             if (m.n > c.march_max_evals) c.march_max_evals = m.n;
         }
@@ -178,7 +178,7 @@ k_march(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32_
                     D3 o, d;
                     double start, end_c;
                     if (march_needed(S, S.inv + 12 * shape, q, ro, rd, best, o, d, start, end_c)) {
-                        m.begin(q, o, d, start, end_c, S.march_G[k], S.march_F[k]);
+                        m.begin(q, o, d, start, end_c, S.march_G[k], S.march_F[k], !prefiltered);
                         marching = true;
                         if (COUNT) c.march_rays++;
                         if (m.phase() == RT_PHASE_END) finish_shape();   // a proven miss (or an empty range)
@@ -285,7 +285,7 @@ __device__ __forceinline__ void m2_load_core(const DevScene& S, const MarchRec* 
     m.sd = m.step * m.d;
     if (COUNT) {
         const uint2 p0 = m2_get_u2(rec, 30), p1 = m2_get_u2(rec, 31);
-        m.prof[0] = p0.x; m.prof[1] = p0.y; m.prof[2] = p1.x; m.prof[3] = p1.y; m.prof[4] = m.prof[5] = 0;
+        m.prof[0] = p0.x; m.prof[1] = p0.y; m.prof[2] = p1.x; m.prof[3] = p1.y; m.prof[4] = m.prof[5] = m.prof[6] = m.prof[7] = 0;
     }
 }
 template <int KIND, bool COUNT>
@@ -481,7 +481,7 @@ k_march2(DevScene S, uint32_t kind_mask, PathQueue in, HitQueue hq, const uint32
                         const int shape = (int)ks.y;
                         if (COUNT) {
                             c.march_steps += m.n;
-                            for (int q = 0; q < 6; q++) c.march_prof[q] += m.prof[q];
+                            for (int q = 0; q < 8; q++) c.march_prof[q] += m.prof[q];
                             if (m.n > 2048) c.march_long_rays++;
                             if (m.n > c.march_max_evals) c.march_max_evals = m.n;
                         }
@@ -557,10 +557,72 @@ static void launch_kind(const MarchLaunch& ml) {
             k_march2<K_, false><<<ml.grid2, RT_M2_THREADS, 0, ml.stream>>>(ml.ds, ml.kind_mask, ml.in, ml.hq, ml.march_count, ml.head,
                                                                           (MarchRec*)ml.march_state, ml.counters);
     } else if (ml.count) {
-        k_march<K_, true><<<ml.grid1, 128, 0, ml.stream>>>(ml.ds, ml.kind_mask, ml.in, ml.hq, ml.march_count, ml.head, ml.counters, ml.tune);
+        k_march<K_, true><<<ml.grid1, 128, 0, ml.stream>>>(ml.ds, ml.kind_mask, ml.in, ml.hq, ml.march_count, ml.head, ml.counters, ml.tune, ml.prefiltered);
     } else {
-        k_march<K_, false><<<ml.grid1, 128, 0, ml.stream>>>(ml.ds, ml.kind_mask, ml.in, ml.hq, ml.march_count, ml.head, ml.counters, ml.tune);
+        k_march<K_, false><<<ml.grid1, 128, 0, ml.stream>>>(ml.ds, ml.kind_mask, ml.in, ml.hq, ml.march_count, ml.head, ml.counters, ml.tune, ml.prefiltered);
     }
+}
+
+// K3a: the miss proof of rt_march.cuh (3) for every queued (ray, marched shape) pair, one entry per thread, before the
+// marching kernels see the queue: straight-line code (ray -> object space, bounding chord, the surface polynomial along
+// the ray, its Bernstein hull) that runs with full warps, where the same test inside the persistent marcher runs with
+// whatever lanes happen to be starting a shape.  A proven miss clears the shape's bit in the entry's mask; an entry
+// whose mask comes out empty is skipped by the marcher's refill.  (The proof is made for the chord clipped by the
+// best hit known NOW; a later kind pass can only shorten that chord.)
+template <int KIND, bool COUNT>
+__device__ __forceinline__ bool filter_proves_miss(const double* q, D3 o, D3 d, double start, double end_c, double G, double F,
+                                                   DevCounters& c) {
+    Marcher<KIND, COUNT> m;
+    m.begin(q, o, d, start, end_c, G, F);
+    if (m.phase() != RT_PHASE_END || m.finish() != RT_MARCH_MISS) return false;
+    if (COUNT) {
+        c.march_rays++;
+        c.march_steps += m.n;
+        for (int k = 0; k < 8; k++) c.march_prof[k] += m.prof[k];
+    }
+    return true;
+}
+template <bool COUNT>
+__global__ void __launch_bounds__(128)
+k_march_filter(DevScene S, PathQueue in, HitQueue hq, const uint32_t* __restrict__ march_count, DevCounters* g_counters) {
+    DevCounters c = {};
+    const uint32_t n = *march_count;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const uint32_t slot = hq.mq_slot[j];
+        const uint32_t mask0 = hq.mq_mask[j];
+        uint32_t mask = mask0, keep = 0;
+        const double best = hq.t[slot];
+        const D3 ro = mk(in.ox[slot], in.oy[slot], in.oz[slot]);
+        const D3 rd = mk(in.dx[slot], in.dy[slot], in.dz[slot]);
+        while (mask) {
+            const int k = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int shape = S.march_index[k];
+            const double* q = S.params + RT_SHAPE_PARAMS * shape;
+            D3 o, d;
+            double start, end_c;
+            if (!march_needed(S, S.inv + 12 * shape, q, ro, rd, best, o, d, start, end_c)) continue;
+            const double G = S.march_G[k], F = S.march_F[k];
+            bool miss;
+            switch ((int)q[0]) {
+                case RT_SURF_HEART: miss = filter_proves_miss<RT_SURF_HEART, COUNT>(q, o, d, start, end_c, G, F, c); break;
+                case RT_SURF_SINE: miss = filter_proves_miss<RT_SURF_SINE, COUNT>(q, o, d, start, end_c, G, F, c); break;
+                case RT_SURF_STAR: miss = filter_proves_miss<RT_SURF_STAR, COUNT>(q, o, d, start, end_c, G, F, c); break;
+                case RT_SURF_DUPIN: miss = filter_proves_miss<RT_SURF_DUPIN, COUNT>(q, o, d, start, end_c, G, F, c); break;
+                case RT_SURF_HUNTS: miss = filter_proves_miss<RT_SURF_HUNTS, COUNT>(q, o, d, start, end_c, G, F, c); break;
+                default: miss = filter_proves_miss<RT_SURF_CUSHION, COUNT>(q, o, d, start, end_c, G, F, c); break;
+            }
+            if (!miss) keep |= 1u << k;
+        }
+        if (keep != mask0) hq.mq_mask[j] = keep;
+    }
+    if (COUNT) flush_counters(c, g_counters);
+}
+
+void rt_launch_march_filter(const MarchLaunch& ml) {
+    if (ml.count) k_march_filter<true><<<ml.grid_filter, 128, 0, ml.stream>>>(ml.ds, ml.in, ml.hq, ml.march_count, ml.counters);
+    else k_march_filter<false><<<ml.grid_filter, 128, 0, ml.stream>>>(ml.ds, ml.in, ml.hq, ml.march_count, ml.counters);
 }
 
 void rt_launch_march(const MarchLaunch& ml) {

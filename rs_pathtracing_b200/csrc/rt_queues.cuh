@@ -57,7 +57,7 @@ __device__ __forceinline__ void flush_counters(const DevCounters& c, DevCounters
     if (c.verify_rays) atomicAdd(&g->verify_rays, c.verify_rays);
     if (c.verify_false_culls) atomicAdd(&g->verify_false_culls, c.verify_false_culls);
 #pragma unroll
-    for (int k = 0; k < 6; k++) {
+    for (int k = 0; k < 8; k++) {
         unsigned long long x = c.march_prof[k];
         for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
         if ((threadIdx.x & 31) == 0 && x) atomicAdd(&g->march_prof[k], x);
@@ -95,8 +95,11 @@ struct MarchLaunch {
     size_t smem3;
     int3 tune;
     void* march_state;        // k_march2's records
+    bool prefiltered;         // k_march_filter has run on this queue: k_march need not try the hull proof again
+    int grid_filter;
 };
 void rt_launch_march(const MarchLaunch& ml);
+void rt_launch_march_filter(const MarchLaunch& ml);   // once per level, before the per-kind launches
 void rt_launch_march3(const MarchLaunch& ml);
 // CTAs per SM of k_march / k_march2 / k_march3 and k_march3's dynamic shared memory per CTA
 void rt_march_occupancy(int per_sm[3], size_t* smem3);

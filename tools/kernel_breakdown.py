@@ -49,7 +49,7 @@ def config(cfg):
 
 
 print("| cfg | frame | Mpaths/s (2 lanes) | 1-lane ms: raygen | extend | march | shade | resolve | segments/path | "
-      "exact tests/seg | cull tests/seg | marched rays/path | evals/marched ray | rays > 2048 evals | max evals | lit0/lit+/jumps/hops/hull misses/hop misses per marched ray |")
+      "exact tests/seg | cull tests/seg | marched rays/path | evals/marched ray | rays > 2048 evals | max evals | lit0/lit+/jumps/hops/hull misses/hop misses/empty plans/failed landings per marched ray |")
 print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
 for cfg in a.cfg:
     sc, cam, w, h, spp = config(cfg)
@@ -76,4 +76,4 @@ for cfg in a.cfg:
           f"{t.ms_march:.2f} | {t.ms_shade:.2f} | {t.ms_resolve:.2f} | {c.segments / paths:.2f} | "
           f"{c.shape_tests / max(c.segments, 1):.2f} | {c.cull_tests / max(c.segments, 1):.1f} | "
           f"{c.march_rays / paths:.3f} | {c.march_steps / max(c.march_rays, 1):.1f} | {c.march_long_rays} | {c.march_max_evals} | "
-          f"{' / '.join(f'{c.march_prof[k] / max(c.march_rays, 1):.2f}' for k in range(6))} |", flush=True)
+          f"{' / '.join(f'{c.march_prof[k] / max(c.march_rays, 1):.2f}' for k in range(8))} |", flush=True)
