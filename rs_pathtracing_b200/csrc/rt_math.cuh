@@ -31,8 +31,11 @@ __device__ __forceinline__ D3 operator*(double s, D3 a) { return {a.x * s, a.y *
 // quotients from ONE correctly rounded reciprocal y = RN(1 / s) (Markstein: with r = a - s q computed exactly
 // by an FMA, q' = RN(q + r y) is RN(a / s) as soon as q is within one ulp of a / s; the first correction makes
 // q = RN(a y) faithful, the second one correctly rounded).  The FMAs are explicit, so -fmad=false does not
-// touch them.  Operands outside [2^-500, 2^500] (where r or q could leave the normal range) and s <= 0 take the
-// plain divisions; a zero numerator keeps its sign (s > 0).  Host build: rt_div3_exact, tests/test_div3_exact.py.
+// touch them.  Operands outside [2^-500, 2^500] (where r or q could leave the normal range) and s == 0 / non-finite s
+// take the plain divisions.  A negative divisor is handled as (-a) / |s| -- round-to-nearest is symmetric, and the
+// sign of a zero quotient comes out as IEEE's.  Host build: rt_div3_exact, tests/test_div3_exact.py.
+// div2_exact: the same for two numerators (Cube::ray_intersect divides -1 - o and 1 - o by the same d component,
+// the marching bounds o and d by the same radius: `divide` was 12 % of k_extend's instructions).
 __host__ __device__ __forceinline__ int fp_exponent_field(double v) {
 #ifdef __CUDA_ARCH__
     return (__double2hiint(v) >> 20) & 0x7ff;
@@ -55,21 +58,39 @@ __host__ __device__ __forceinline__ double quotient_by_rcp(double a, double s, d
 }
 __host__ __device__ __forceinline__ void div3_exact(double ax, double ay, double az, double s, double& qx, double& qy,
                                                     double& qz) {
-    if (s > 0.0 && (unsigned)(fp_exponent_field(s) - 523) <= 1000u && div3_operand_ok(ax) && div3_operand_ok(ay) &&
+    if ((unsigned)(fp_exponent_field(s) - 523) <= 1000u && div3_operand_ok(ax) && div3_operand_ok(ay) &&
         div3_operand_ok(az)) {
+        const double sa = fabs(s);
+        const bool neg = s < 0.0;
 #ifdef __CUDA_ARCH__
-        const double y = __drcp_rn(s);
+        const double y = __drcp_rn(sa);
 #else
-        const double y = 1.0 / s;
+        const double y = 1.0 / sa;
 #endif
-        qx = quotient_by_rcp(ax, s, y);
-        qy = quotient_by_rcp(ay, s, y);
-        qz = quotient_by_rcp(az, s, y);
+        qx = quotient_by_rcp(neg ? -ax : ax, sa, y);
+        qy = quotient_by_rcp(neg ? -ay : ay, sa, y);
+        qz = quotient_by_rcp(neg ? -az : az, sa, y);
         return;
     }
     qx = ax / s;
     qy = ay / s;
     qz = az / s;
+}
+__host__ __device__ __forceinline__ void div2_exact(double a, double b, double s, double& qa, double& qb) {
+    if ((unsigned)(fp_exponent_field(s) - 523) <= 1000u && div3_operand_ok(a) && div3_operand_ok(b)) {
+        const double sa = fabs(s);
+        const bool neg = s < 0.0;
+#ifdef __CUDA_ARCH__
+        const double y = __drcp_rn(sa);
+#else
+        const double y = 1.0 / sa;
+#endif
+        qa = quotient_by_rcp(neg ? -a : a, sa, y);
+        qb = quotient_by_rcp(neg ? -b : b, sa, y);
+        return;
+    }
+    qa = a / s;
+    qb = b / s;
 }
 __device__ __forceinline__ D3 operator/(D3 a, double s) {
     D3 q;
@@ -365,8 +386,10 @@ __device__ __forceinline__ bool march_bound(const double* q, D3 o, D3 d, double&
     if ((int)q[0] == RT_SURF_HEART) {
         const double sr = 1.45;  // Heart::new, :126-131
         D3 radius = mk(sr, sr / 2.05, sr);
-        D3 os = divide(o, radius);
-        D3 ds = divide(d, radius);
+        D3 os, ds;   // divide(o, radius), divide(d, radius): six IEEE quotients from three reciprocals
+        div2_exact(o.x, d.x, radius.x, os.x, ds.x);
+        div2_exact(o.y, d.y, radius.y, os.y, ds.y);
+        div2_exact(o.z, d.z, radius.z, os.z, ds.z);
         if (!solve_quadratic(dot(ds, ds), dot(ds, os), dot(os, os) - 1.0, x1, x2)) return false;
     } else {
         double R = q[7];
@@ -468,8 +491,11 @@ __device__ __forceinline__ bool sphere_candidate(D3 o, D3 d, double min_t, doubl
 
 // Cube::ray_intersect, :250-263
 __device__ __forceinline__ bool cube_candidate(D3 o, D3 d, double min_t, double max_t, double& t) {
-    D3 t_lower = divide(mk(-1.0, -1.0, -1.0) - o, d);
-    D3 t_upper = divide(mk(1.0, 1.0, 1.0) - o, d);
+    // divide(mk(-1, -1, -1) - o, d) and divide(mk(1, 1, 1) - o, d): six IEEE quotients from three reciprocals
+    D3 t_lower, t_upper;
+    div2_exact(-1.0 - o.x, 1.0 - o.x, d.x, t_lower.x, t_upper.x);
+    div2_exact(-1.0 - o.y, 1.0 - o.y, d.y, t_lower.y, t_upper.y);
+    div2_exact(-1.0 - o.z, 1.0 - o.z, d.z, t_lower.z, t_upper.z);
     double t_box_min = fmax(max3(fmin(t_lower.x, t_upper.x), fmin(t_lower.y, t_upper.y), fmin(t_lower.z, t_upper.z)), min_t);
     double t_box_max = fmin(min3(fmax(t_lower.x, t_upper.x), fmax(t_lower.y, t_upper.y), fmax(t_lower.z, t_upper.z)), max_t);
     if (t_box_min > t_box_max || t_box_min > max_t) return false;

@@ -93,3 +93,23 @@ def test_operands_outside_the_fast_range_take_the_plain_division():
     s = from_parts(rng.integers(0, 1 << 52, n, dtype=np.uint64), rng.integers(497, 503, n))
     check(a, s)
     check(1.0 / a, 1.0 / s)
+
+
+def test_negative_divisors_like_the_cube_slabs():
+    """Cube::ray_intersect (shapes/mod.rs:250-256) divides (-1 - o) and (1 - o) by the direction's components, of
+    either sign: the device takes |d| and flips the numerators (div2_exact shares the code path).  Signed zeros
+    included: (+0) / (-x) = -0."""
+    rng = np.random.default_rng(8)
+    n = 1_500_000
+    o = rng.uniform(-3, 3, (n, 3))
+    o[rng.random(n) < 0.05, 0] = -1.0          # the numerator -1 - o is then exactly +0 / -0
+    o[rng.random(n) < 0.05, 1] = 1.0
+    d = rng.standard_normal(n) * 10.0 ** rng.uniform(-6, 1, n)
+    num = np.stack([-1.0 - o[:, 0], 1.0 - o[:, 1], -1.0 - o[:, 2]], axis=1)
+    check(num, d)
+    check(-num, -np.abs(d))
+    ma = rng.integers(0, 1 << 52, (n, 3), dtype=np.uint64)
+    ms = rng.integers(0, 1 << 52, n, dtype=np.uint64)
+    a = from_parts(ma, rng.integers(-40, 40, (n, 3))) * rng.choice([-1.0, 1.0], (n, 3))
+    s = -from_parts(ms, rng.integers(-40, 40, n))
+    check(a, s)
