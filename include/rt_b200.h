@@ -333,8 +333,8 @@ typedef struct rt_stats {
     uint64_t launches_extend, launches_march, launches_shade;
     /* k_march work breakdown (with counters on): literal steps at level 0, literal steps at the
      * refinement levels, exact multi-step jumps, hops of the skip bound, rays proven to miss by the Bernstein hull
-     * of the surface polynomial / by the hop loop (no marching at all), plans that found nothing to skip, landings
-     * that failed the self-check.  8 entries since ABI 5 (4 before) */
+     * of the surface polynomial / by the hop loop (no marching at all), plans that found nothing to skip at level 0 /
+     * at a refinement level.  8 entries since ABI 5 (4 before) */
     uint64_t march_prof[8];
 } rt_stats;
 int rt_get_stats(rt_scene* scene, rt_stats* out);

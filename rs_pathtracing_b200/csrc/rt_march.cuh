@@ -280,6 +280,22 @@ struct RayPoly {
 
 #define RT_MARCH_SAFETY 16.0
 
+// magnitude arithmetic (march_bounds.hpp's Mag, device side): every operation returns an upper bound of the sum of the
+// absolute values of the terms it combines, so evaluating the surface polynomial's text on it bounds the
+// "absolute-value polynomial" at the given |coordinates| -- and anywhere closer to the origin, componentwise.
+struct MagD {
+    double v;
+};
+__device__ __forceinline__ MagD operator+(MagD a, MagD b) { return MagD{a.v + b.v}; }
+__device__ __forceinline__ MagD operator-(MagD a, MagD b) { return MagD{a.v + b.v}; }
+__device__ __forceinline__ MagD operator*(MagD a, MagD b) { return MagD{a.v * b.v}; }
+__device__ __forceinline__ MagD operator+(MagD a, double b) { return MagD{a.v + fabs(b)}; }
+__device__ __forceinline__ MagD operator-(MagD a, double b) { return MagD{a.v + fabs(b)}; }
+__device__ __forceinline__ MagD operator*(MagD a, double b) { return MagD{a.v * fabs(b)}; }
+__device__ __forceinline__ MagD operator+(double a, MagD b) { return MagD{fabs(a) + b.v}; }
+__device__ __forceinline__ MagD operator-(double a, MagD b) { return MagD{fabs(a) + b.v}; }
+__device__ __forceinline__ MagD operator*(double a, MagD b) { return MagD{fabs(a) * b.v}; }
+
 // expansion of f along the ray around the current sample (t, p); the model must cover tau in [0, tau_hi]
 template <int KIND>
 __device__ __forceinline__ void expand_ray(const double* q, D3 p, D3 d, double t, double t_end, double tau_hi,
@@ -406,7 +422,7 @@ template <int KIND, bool PROF = false>
 struct Marcher {
     static constexpr int DEG = SurfDeg<KIND>::value;
     unsigned prof[8];  // PROF only: literal steps at level 0 / at refinement levels, jumps, hops, misses proven by the
-                       // Bernstein hull / by the hop loop, plans that found nothing to skip, landings that failed the self-check
+                       // Bernstein hull / by the hop loop, plans that found nothing to skip at level 0 / at a refinement level
     const double* q;
     D3 d;
     double start, end, G, F;
@@ -419,6 +435,7 @@ struct Marcher {
     double step0;
     bool skip_ok, have_poly;
     bool plan_miss_ok;   // attempt_plan may declare the ray a miss (off in the kernels that keep t in a record)
+    bool local_model;    // P is the model re-expanded around the level-0 crossing (refine_model)
     int cooldown, backoff;
     RayPoly<DEG> P;
 
@@ -443,6 +460,7 @@ struct Marcher {
         skip_ok = (G == G) && G < 1e300 && (F == F) && F < 1e300 && step > 0.0 && (end - start) > 64.0 * step &&
                   (end - start) < 1e300;
         plan_miss_ok = true;
+        local_model = false;
         if (skip_ok) {
             // the model along the ray, expanded around the first sample; covers every later sample of the ray
             expand_ray<KIND>(q, p, d, t, end, (end - t) + 4.0 * step0, G, F, P);
@@ -571,6 +589,27 @@ struct Marcher {
         pl.span = span;
         pl.hop = 0;
     }
+    // The refinement levels (it > 0) never leave the last level-0 step around the first sign change, but their steps
+    // shrink to 1e-8: the band M has to be a fraction of ONE such step's change of g (~3e-10 on cornell_box's Heart)
+    // for a jump to be provable.  The model expanded at the chord's start cannot deliver that: shifting it hundreds of
+    // world units costs ~1e-16 * sum |c_k| tau^k of absolute accuracy (err0's `scale` term, 1e-9 and more), and the
+    // evaluation term uses the magnitude bound F of the whole region.  Measured: 70 % of the hit rays walked the last
+    // level literally (~50 steps) after an empty plan.  So the first plan of a refinement level re-expands f around
+    // the current sample: centre half a window back (the model line only runs forward), window = 2 x 1.02 level-0
+    // steps, F = the absolute-value polynomial at the window's largest |coordinates|.  P.p0 / P.t0 need not be
+    // samples: plan_begin measures the displacement e of the real sample from the model line, whatever it is.
+    __device__ __forceinline__ void refine_model() {
+        const double h = 1.02 * step0;
+        const D3 pc = mk(fma(-h, d.x, p.x), fma(-h, d.y, p.y), fma(-h, d.z, p.z));
+        const double w = 2.0 * h;
+        const MagD fm = surface_func_t<KIND, MagD>(q, MagD{fabs(pc.x) + w * fabs(d.x)}, MagD{fabs(pc.y) + w * fabs(d.y)},
+                                                   MagD{fabs(pc.z) + w * fabs(d.z)});
+        double f_loc = fm.v * (1.0 + 1e-9);
+        if (!(f_loc < F)) f_loc = F;   // (NaN / inf: the region's bound)
+        expand_ray<KIND>(q, pc, d, t - h, t + h, w, G, f_loc, P);
+        n += 2;
+        local_model = true;
+    }
     __device__ __forceinline__ void plan_begin(Plan& pl) {
         if (!have_poly) {   // (begin() expands when skip_ok; kept for marchers rebuilt from records)
             double tau_hi = (end - t) + 4.0 * step0;
@@ -581,7 +620,7 @@ struct Marcher {
         double(&s)[DEG + 1] = pl.s;
         const double abs_step = fabs(step);
         const double dir = step > 0.0 ? 1.0 : -1.0;
-        const double tau = t - P.t0;
+        double tau = t - P.t0;
         // Taylor shift to the current sample: g(tau + sigma) = sum s[k] sigma^k
 #pragma unroll
         for (int k = 0; k <= DEG; k++) s[k] = P.c[k];
@@ -589,6 +628,27 @@ struct Marcher {
         for (int i = 0; i < DEG; i++)
 #pragma unroll
             for (int j = DEG - 1; j >= i; j--) s[j] = fma(tau, s[j + 1], s[j]);
+#ifndef RT_MARCH_NO_LOCAL_MODEL
+        if (it > 0 && !local_model) {
+            // decided once per ray, at its first refinement plan: re-expand when the chord-wide model's own error
+            // term is worth more than two of the FINEST steps (|g'| x step x 0.01^(depth - 1)) -- otherwise the last
+            // level could never jump; a model that is already sharper than that (short chords, DupinCyclide under a
+            // scale of 2) is kept, the re-expansion would only cost
+            local_model = true;
+            double finest = step0;
+            for (int l = 1; l < depth; l++) finest *= 0.01;
+            if (P.err0 > 2.0 * fabs(s[1]) * finest) {
+                refine_model();
+                tau = t - P.t0;
+#pragma unroll
+                for (int k = 0; k <= DEG; k++) s[k] = P.c[k];
+#pragma unroll
+                for (int i = 0; i < DEG; i++)
+#pragma unroll
+                    for (int j = DEG - 1; j >= i; j--) s[j] = fma(tau, s[j + 1], s[j]);
+            }
+        }
+#endif
         // the range checks must not fire on skipped samples: stay 2 steps inside [start, end] and the model
         double tau_lim = (dir > 0.0 ? end : start) - P.t0 - dir * 2.0 * abs_step;
         tau_lim = fmin(fmax(tau_lim, 0.0), P.tau_hi);
@@ -680,7 +740,7 @@ struct Marcher {
         const double mf = reach / pl.abs_step * (1.0 - 1e-9) - 2.0;
         if (mf >= (double)RT_MARCH_MIN_JUMP) return (long long)fmin(mf, 1.0e15);
         // inside the |g| < M zone or next to a range limit: plain steps, retry later
-        if (PROF) prof[6]++;
+        if (PROF) prof[it > 0 ? 7 : 6]++;
         if (it > 0) {
             // A refinement level walks back over ONE step of the level before (<= ~100 steps of its own) towards a sign
             // change that is known to lie ahead, and |g| only shrinks on the way: a plan that stopped within a few
@@ -723,7 +783,6 @@ struct Marcher {
             cooldown = pl.more ? 0 : RT_MARCH_LAND_COOLDOWN;
             return;
         }
-        if (PROF) prof[7]++;
         skip_ok = false;  // the model does not describe this ray: finish it with the plain loop
     }
     // the serial form (fused kernels, rt_intersect_batch)

@@ -216,6 +216,7 @@ __device__ __forceinline__ void m3_load_core(const DevScene& S, Rec rec, Marcher
     more = ((w.x >> 24) & M3_FLAG_MORE) != 0;
     m.have_poly = true;   // (expanded when the shape is started; only read when skip_ok)
     m.plan_miss_ok = false;   // t lives in the record: only begin()'s hull proof declares misses here
+    m.local_model = false;    // (the record keeps the model of the chord's start: a refinement plan re-expands every time)
     m.n = w.y;
     m.q = S.params + RT_SHAPE_PARAMS * (int)ks.y;
     m.step0 = rec[F_STEP0];

@@ -275,6 +275,7 @@ __device__ __forceinline__ void m2_load_core(const DevScene& S, const MarchRec* 
     m.skip_ok = ((w.x >> 24) & RT_M2_FLAG_SKIP_OK) != 0;
     m.have_poly = ((w.x >> 24) & RT_M2_FLAG_HAVE_POLY) != 0;
     m.plan_miss_ok = true;   // (m2_store_core keeps the t = +inf a proven miss leaves behind)
+    m.local_model = false;   // (the record keeps the model of the chord's start: a refinement plan re-expands every time)
     m.n = w.y;
     k = (int)ks.x;
     m.q = S.params + RT_SHAPE_PARAMS * (int)ks.y;

@@ -49,7 +49,7 @@ def config(cfg):
 
 
 print("| cfg | frame | Mpaths/s (2 lanes) | 1-lane ms: raygen | extend | march | shade | resolve | segments/path | "
-      "exact tests/seg | cull tests/seg | marched rays/path | evals/marched ray | rays > 2048 evals | max evals | lit0/lit+/jumps/hops/hull misses/hop misses/empty plans/failed landings per marched ray |")
+      "exact tests/seg | cull tests/seg | marched rays/path | evals/marched ray | rays > 2048 evals | max evals | lit0/lit+/jumps/hops/hull misses/hop misses/empty plans at level 0/at refinement levels per marched ray |")
 print("|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|---|")
 for cfg in a.cfg:
     sc, cam, w, h, spp = config(cfg)
