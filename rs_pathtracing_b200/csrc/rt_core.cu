@@ -208,16 +208,6 @@ k_intersect_batch(DevScene S, bool use_smem, const rt_ray* __restrict__ rays, un
 // wavefront path tracer
 // ------------------------------------------------------------------------------------------------
 // warp-aggregated append: returns this lane's slot in the destination queue (valid when `alive`)
-__device__ __forceinline__ uint32_t queue_append(bool alive, uint32_t* counter) {
-    unsigned mask = __ballot_sync(0xffffffffu, alive);
-    if (mask == 0) return 0;
-    int lane = threadIdx.x & 31;
-    int leader = __ffs(mask) - 1;
-    uint32_t base = 0;
-    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    return base + __popc(mask & ((1u << lane) - 1u));
-}
 
 // K1: primary rays.  Batch = pixels [first_owned, first_owned + n_pixels) of this shard x spp samples,
 // path id = pixel_local * spp + sample.  Padding pixels of clipped tiles produce no path.
@@ -410,7 +400,7 @@ k_extend(DevScene S, bool use_smem, PathQueue in, const uint32_t* __restrict__ c
             if (!degenerate && !(any_hit_suffices && winner >= 0)) {
                 for (int k = 0; k < S.n_march; k++) {
                     if (!cull_pass(cr, S.march_cull[k])) continue;  // the line misses the marching bound
-                    if (defer_bound) {  // k_march runs march_needed anyway, with (nearly) full warps
+                    if (defer_bound) {  // k_march_filter runs march_needed, with full warps
                         mask |= 1u << k;
                         continue;
                     }
@@ -756,7 +746,7 @@ struct rt_scene {
     void* d_march_state = nullptr;               // k_march2: its records (rt_march_kernels.cu)
     int grid_march2 = 0, grid_march3 = 0;
     size_t smem_march3 = 0;
-    bool defer_bound = false;                    // k_extend queues every ray whose line touches a marching bound's ball; k_march sorts out the rest (RT_B200_DEFER_BOUND=1)
+    bool defer_bound = true;                     // k_extend queues every ray whose line touches a marching bound's ball and leaves the bounding chord (march_needed: 8 % of its instructions at 7 of 32 lanes) to k_march_filter, which runs it with full warps (RT_B200_DEFER_BOUND=0: off; off without the filter)
     bool march_filter = true;                    // k_march_filter before the marching kernels (RT_B200_MARCH_FILTER=0: off)
     int march_version = 1;                       // 1: one ray per lane (k_march); RT_B200_MARCH=3: pool of rays per SM + per-phase queues
                                                  // (k_march3, rt_march3.cu: correct but slower, see profiles/); =2: block-local wavefront (k_march2)
@@ -1048,6 +1038,7 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
     if (const char* mv = getenv("RT_B200_MARCH")) sc->march_version = std::min(std::max(atoi(mv), 1), 3);
     if (getenv("RT_B200_MARCH_V2")) sc->march_version = 2;
     if (const char* mf = getenv("RT_B200_MARCH_FILTER")) sc->march_filter = atoi(mf) != 0;
+    if (!sc->march_filter && !getenv("RT_B200_DEFER_BOUND")) sc->defer_bound = false;   // (measured a net loss without the filter)
     if (const char* db = getenv("RT_B200_DEFER_BOUND")) sc->defer_bound = atoi(db) != 0;
     sc->grid_shade = occ_grid(k_shade<false, true>, 256, 0);
     sc->wavefront = sc->ds.n_march <= 32 && !getenv("RT_B200_FUSED_BOUNCE");
@@ -1378,15 +1369,24 @@ static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long 
                 MarchLaunch fl;
                 fl.ds = sc->ds; fl.in = in; fl.hq = sc->hq; fl.march_count = mcount; fl.counters = sc->d_counters;
                 fl.count = sc->counters_on; fl.stream = sc->stream; fl.grid_filter = sc->n_sm * 8;
+                fl.filtered_count = sc->d_counts + RT_CNT_FILTERED + level;
                 rt_launch_march_filter(fl);
                 sc->launches++;
+            }
+            // the marching kernels read the compacted queue the filter wrote
+            HitQueue mhq = sc->hq;
+            const uint32_t* mq_count = mcount;
+            if (sc->march_filter) {
+                mhq.mq_slot = sc->hq.fq_slot;
+                mhq.mq_mask = sc->hq.fq_mask;
+                mq_count = sc->d_counts + RT_CNT_FILTERED + level;
             }
             for (int kind = 0; kind < 6; kind++) {
                 if (!sc->kind_mask[kind]) continue;
                 uint32_t* head = sc->d_counts + RT_CNT_HEAD + kind * RT_MAX_LEVELS + level;
                 MarchLaunch ml;
-                ml.ds = sc->ds; ml.kind = kind; ml.kind_mask = sc->kind_mask[kind]; ml.in = in; ml.hq = sc->hq;
-                ml.march_count = mcount; ml.head = head; ml.counters = sc->d_counters; ml.count = sc->counters_on;
+                ml.ds = sc->ds; ml.kind = kind; ml.kind_mask = sc->kind_mask[kind]; ml.in = in; ml.hq = mhq;
+                ml.march_count = mq_count; ml.head = head; ml.counters = sc->d_counters; ml.count = sc->counters_on;
                 ml.stream = sc->stream; ml.version = sc->march_version; ml.grid1 = sc->grid_march; ml.grid2 = sc->grid_march2;
                 ml.grid3 = sc->grid_march3; ml.smem3 = sc->smem_march3; ml.tune = sc->march_tune; ml.march_state = sc->d_march_state;
                 ml.prefiltered = sc->march_filter; ml.grid_filter = 0;
@@ -1433,6 +1433,8 @@ static int ensure_path_buffers(rt_scene* sc, uint64_t need_paths) {
         CU(cudaMalloc(&p, need_paths * sizeof(int32_t))); sc->qallocs.push_back(p); sc->hq.index = (int32_t*)p;
         CU(cudaMalloc(&p, need_paths * sizeof(uint32_t))); sc->qallocs.push_back(p); sc->hq.mq_slot = (uint32_t*)p;
         CU(cudaMalloc(&p, need_paths * sizeof(uint32_t))); sc->qallocs.push_back(p); sc->hq.mq_mask = (uint32_t*)p;
+        CU(cudaMalloc(&p, need_paths * sizeof(uint32_t))); sc->qallocs.push_back(p); sc->hq.fq_slot = (uint32_t*)p;
+        CU(cudaMalloc(&p, need_paths * sizeof(uint32_t))); sc->qallocs.push_back(p); sc->hq.fq_mask = (uint32_t*)p;
         CU(cudaMalloc(&p, need_paths * sizeof(uint32_t))); sc->qallocs.push_back(p); sc->hq.rq_slot = (uint32_t*)p;
         CU(cudaMalloc(&p, need_paths * sizeof(uint2))); sc->qallocs.push_back(p); sc->hq.key = (uint2*)p;
     }

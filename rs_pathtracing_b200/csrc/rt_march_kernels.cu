@@ -567,9 +567,10 @@ static void launch_kind(const MarchLaunch& ml) {
 // K3a: the miss proof of rt_march.cuh (3) for every queued (ray, marched shape) pair, one entry per thread, before the
 // marching kernels see the queue: straight-line code (ray -> object space, bounding chord, the surface polynomial along
 // the ray, its Bernstein hull) that runs with full warps, where the same test inside the persistent marcher runs with
-// whatever lanes happen to be starting a shape.  A proven miss clears the shape's bit in the entry's mask; an entry
-// whose mask comes out empty is skipped by the marcher's refill.  (The proof is made for the chord clipped by the
-// best hit known NOW; a later kind pass can only shorten that chord.)
+// whatever lanes happen to be starting a shape.  A proven miss clears the shape's bit in the entry's mask; the entries
+// that keep a bit are written, compacted, to the filtered queue (hq.fq_slot / fq_mask, one atomic per warp), which is
+// what the marching kernels then read.  (The proof is made for the chord clipped by the best hit known NOW; a later
+// kind pass can only shorten that chord.)
 template <int KIND, bool COUNT>
 __device__ __forceinline__ bool filter_proves_miss(const double* q, D3 o, D3 d, double start, double end_c, double G, double F,
                                                    DevCounters& c) {
@@ -585,17 +586,24 @@ __device__ __forceinline__ bool filter_proves_miss(const double* q, D3 o, D3 d, 
 }
 template <bool COUNT>
 __global__ void __launch_bounds__(128)
-k_march_filter(DevScene S, PathQueue in, HitQueue hq, const uint32_t* __restrict__ march_count, DevCounters* g_counters) {
+k_march_filter(DevScene S, PathQueue in, HitQueue hq, const uint32_t* __restrict__ march_count, uint32_t* filtered_count,
+               DevCounters* g_counters) {
     DevCounters c = {};
     const uint32_t n = *march_count;
+    const uint32_t n_round = (n + 31u) & ~31u;   // whole warps stay converged for queue_append
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const uint32_t slot = hq.mq_slot[j];
-        const uint32_t mask0 = hq.mq_mask[j];
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n_round; j += stride) {
+        const bool valid = j < n;
+        const uint32_t slot = valid ? hq.mq_slot[j] : 0u;
+        const uint32_t mask0 = valid ? hq.mq_mask[j] : 0u;
         uint32_t mask = mask0, keep = 0;
-        const double best = hq.t[slot];
-        const D3 ro = mk(in.ox[slot], in.oy[slot], in.oz[slot]);
-        const D3 rd = mk(in.dx[slot], in.dy[slot], in.dz[slot]);
+        double best = 0.0;
+        D3 ro = mk(0.0, 0.0, 0.0), rd = mk(0.0, 0.0, 0.0);
+        if (valid) {
+            best = hq.t[slot];
+            ro = mk(in.ox[slot], in.oy[slot], in.oz[slot]);
+            rd = mk(in.dx[slot], in.dy[slot], in.dz[slot]);
+        }
         while (mask) {
             const int k = __ffs(mask) - 1;
             mask &= mask - 1;
@@ -616,14 +624,20 @@ k_march_filter(DevScene S, PathQueue in, HitQueue hq, const uint32_t* __restrict
             }
             if (!miss) keep |= 1u << k;
         }
-        if (keep != mask0) hq.mq_mask[j] = keep;
+        // what is left goes to the compacted queue the marching kernels read (they would otherwise fetch and skip
+        // the emptied entries -- more than half of them on cornell_box)
+        const uint32_t at = queue_append(keep != 0, filtered_count);
+        if (keep != 0) {
+            hq.fq_slot[at] = slot;
+            hq.fq_mask[at] = keep;
+        }
     }
     if (COUNT) flush_counters(c, g_counters);
 }
 
 void rt_launch_march_filter(const MarchLaunch& ml) {
-    if (ml.count) k_march_filter<true><<<ml.grid_filter, 128, 0, ml.stream>>>(ml.ds, ml.in, ml.hq, ml.march_count, ml.counters);
-    else k_march_filter<false><<<ml.grid_filter, 128, 0, ml.stream>>>(ml.ds, ml.in, ml.hq, ml.march_count, ml.counters);
+    if (ml.count) k_march_filter<true><<<ml.grid_filter, 128, 0, ml.stream>>>(ml.ds, ml.in, ml.hq, ml.march_count, ml.filtered_count, ml.counters);
+    else k_march_filter<false><<<ml.grid_filter, 128, 0, ml.stream>>>(ml.ds, ml.in, ml.hq, ml.march_count, ml.filtered_count, ml.counters);
 }
 
 void rt_launch_march(const MarchLaunch& ml) {

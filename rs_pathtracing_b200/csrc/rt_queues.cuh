@@ -21,6 +21,8 @@ struct HitQueue {
     int32_t* index;   // winning shape, -1 = none
     uint32_t* mq_slot;  // march queue: path slot ...
     uint32_t* mq_mask;  // ... and the marched shapes (bit k = S.march_index[k]) it still has to test
+    uint32_t* fq_slot;  // the march queue after k_march_filter: the entries that still have a shape to march, compacted
+    uint32_t* fq_mask;
     uint32_t* rq_slot;  // replay queue: degenerate rays (Sphere D == 0, NaN t) that must go through the literal loop
     uint2* key;         // [path id] the path's RNG key (image pixel index, sample), written once by k_raygen /
                         // k_load_rays: k_shade reads 8 B instead of redoing six integer divisions per segment
@@ -32,7 +34,20 @@ struct HitQueue {
 #define RT_CNT_MARCH (RT_MAX_LEVELS)
 #define RT_CNT_REPLAY (2 * RT_MAX_LEVELS)
 #define RT_CNT_HEAD (3 * RT_MAX_LEVELS)              // + kind * RT_MAX_LEVELS
-#define RT_CNT_WORDS (9 * RT_MAX_LEVELS)
+#define RT_CNT_FILTERED (9 * RT_MAX_LEVELS)          // length of the filtered march queue
+#define RT_CNT_WORDS (10 * RT_MAX_LEVELS)
+
+// append to a queue: one atomic per warp (ballot + popc); must be called by all 32 lanes of a warp
+__device__ __forceinline__ uint32_t queue_append(bool alive, uint32_t* counter) {
+    unsigned mask = __ballot_sync(0xffffffffu, alive);
+    if (mask == 0) return 0;
+    int lane = threadIdx.x & 31;
+    int leader = __ffs(mask) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, (uint32_t)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(mask & ((1u << lane) - 1u));
+}
 
 __device__ __forceinline__ void flush_counters(const DevCounters& c, DevCounters* g) {
     // warp-reduce, one atomic per warp and counter
@@ -97,6 +112,7 @@ struct MarchLaunch {
     void* march_state;        // k_march2's records
     bool prefiltered;         // k_march_filter has run on this queue: k_march need not try the hull proof again
     int grid_filter;
+    uint32_t* filtered_count; // k_march_filter: length of the compacted queue it writes (hq.fq_slot / fq_mask)
 };
 void rt_launch_march(const MarchLaunch& ml);
 void rt_launch_march_filter(const MarchLaunch& ml);   // once per level, before the per-kind launches

@@ -313,7 +313,9 @@ def test_alternative_schedules_give_the_same_frame(monkeypatch, name):
     k_march; the pooled marcher k_march3 (RT_B200_MARCH=3: a pool of ray records per SM, a queue per phase, dynamic
     pick-up inside every variable-length loop), the block-local wavefront marcher k_march2 (RT_B200_MARCH=2), other
     k_march voting thresholds and the fused k_bounce (RT_B200_FUSED_BOUNCE) reproduce the default frame bit for bit; so do the flat list without its
-    staged records (RT_B200_NO_FLAT_REC) and marching-bound tests deferred to k_march (RT_B200_DEFER_BOUND).
+    staged records (RT_B200_NO_FLAT_REC), marching-bound tests done by k_extend instead of k_march_filter
+    (RT_B200_DEFER_BOUND=0) and the marcher without the filter kernel in front of it (RT_B200_MARCH_FILTER=0: the miss
+    proof then runs inside k_march).
     The fused k_bounce draws random_in_unit_sphere with the sequential rejection loop and the default k_shade
     warp-cooperatively, so this also pins the cooperative sampler to the sequential one"""
     w, h, spp, depth, seed = 96, 72, 4, 8, 21
@@ -322,7 +324,8 @@ def test_alternative_schedules_give_the_same_frame(monkeypatch, name):
     for var, val in (("RT_B200_MARCH", "3"), ("RT_B200_MARCH", "2"), ("RT_B200_FUSED_BOUNCE", "1"),
                      ("RT_B200_MARCH_TUNE", "2,30,3"),
                      ("RT_B200_NO_CULL_TREE", "1"), ("RT_B200_NO_MARCH_SKIP", "1"), ("RT_B200_NO_FLAT_REC", "1"),
-                     ("RT_B200_DEFER_BOUND", "1"), ("RT_B200_SHADE_BINNED", "1"), ("RT_B200_SHADE_BINNED", "0")):
+                     ("RT_B200_DEFER_BOUND", "0"), ("RT_B200_MARCH_FILTER", "0"), ("RT_B200_SHADE_BINNED", "1"),
+                     ("RT_B200_SHADE_BINNED", "0")):
         monkeypatch.setenv(var, val)
         alt = rt.Scene.from_file(scene_path(name), random_spheres_seed=1)
         got = gpu_frame(alt, alt.camera(), w, h, spp, depth, seed)
