@@ -332,15 +332,17 @@ __device__ __forceinline__ void expand_ray(const double* q, D3 p, D3 d, double t
 // ---- (3) a ray that provably never comes near the surface: None without marching ----------------------------
 // Two thirds of the marched rays of cornell_box cross the Heart's bounding ellipsoid without touching the Heart.
 // For them the reference executes `r = next` thousands of times and leaves through the range check; the exact
-// values of t and p never matter.  If |g| >= M with constant sign on the WHOLE stretch the samples can fall on --
-// tau in [0, (end - t0) + 3 step]: the last sample evaluated is the first one with t > end -- then no sample sees a
-// sign change or |f| < 1e-15 (the argument of (2), with the a-priori displacement bound for all m steps), and the
-// result is None.  The proof is the convex-hull property of the Bernstein form: on [0, L],
-// min_i b_i <= g <= max_i b_i, b = the Bernstein coefficients of g over [0, L]; the hull is tightened by de Casteljau
-// subdivision at the midpoint (two levels: 93 % of the misses among random chords of the Heart's bound, against 52 %
-// for the undivided hull).  Straight-line code: every lane of a warp that starts a shape runs it together.
+// values of t and p never matter.  If sigma g(tau) > M(tau) on the WHOLE stretch the samples can fall on -- tau up to
+// (end - t0) + 3 step: the last sample evaluated is the first one with t > end -- then no sample sees a sign change
+// or |f| < 1e-15 (the argument of (2), with the a-priori displacement bound of tau / step steps at the sample at
+// tau), and the result is None.  M(tau) is linear in tau, so sigma g - M is a polynomial of the same degree, and the
+// proof is the convex-hull property of its Bernstein form: on [a, b], min_i b_i <= p <= max_i b_i, b = the Bernstein
+// coefficients of p over [a, b]; the hull is tightened by de Casteljau subdivision at the midpoint (two levels: 93 %
+// of the misses among random chords of the Heart's bound, against 52 % for the undivided hull).  Marcher::begin has
+// the details (the interval starts half a step in; the value at sample 0 only lends its sign).  Straight-line code:
+// k_march_filter runs it for every queued (ray, shape) pair with full warps, before the marcher sees the queue.
 // Rounding: the conversion and each subdivision level are convex combinations / binomial sums of <= 7 terms bounded
-// by scale = sum |c_k| L^k, error <= 3e-15 scale in total, and `margin` >= err0 >= 1.6e-13 scale is added to M.
+// by scale = sum |c_k| L^k, error <= 3e-15 scale in total; err0 >= 1.6e-13 scale is subtracted once more for it.
 template <int DEG>
 __device__ __forceinline__ bool bern_hull_clear(const double (&b)[DEG + 1], double thr, bool positive) {
     bool ok = true;
@@ -475,14 +477,6 @@ struct Marcher {
             // band being linear in tau -- and that r, the value at sample 0, is not of the opposite sign.  Starting
             // half a step in matters: a ray that leaves the surface it was scattered from has |g(0)| ~ 1e-9, far
             // inside the band of a 20 000-step chord, but is 1e-4 away from zero one step later.
-#ifdef RT_MARCH_NO_TILT
-            const double L = miss_span(t);
-            const double M = P.err0 + (L / step0 + 4.0) * P.drift1;
-            if (miss_drift_ok(L) && bernstein_clear<DEG>(P.c, L, M + P.err0)) {
-                t = INFINITY;   // phase() -> RT_PHASE_END, finish() -> RT_MARCH_MISS
-                if (PROF) prof[4]++;
-            }
-#else
             const double L = miss_span(t);
             if (hull && miss_drift_ok(L)) {
                 const double ta = 0.5 * step0;
@@ -500,7 +494,7 @@ struct Marcher {
                         for (int k = 0; k <= DEG; k++) sh[k] = -sh[k];
                     }
                     // err0 twice: once for the band, once for the rounding of the shift and of the Bernstein form
-                    sh[0] -= 2.0 * P.err0 + (ta / step0 + 4.0) * P.drift1;
+                    sh[0] -= fmax(2.0 * P.err0 + (ta / step0 + 4.0) * P.drift1, 2e-15);   // (>= 2e-15: approx_equal's exit)
                     sh[1] -= P.drift1 / step0;
                     if (bernstein_clear<DEG>(sh, L - ta, 0.0)) {
                         t = INFINITY;   // phase() -> RT_PHASE_END, finish() -> RT_MARCH_MISS
@@ -508,7 +502,6 @@ struct Marcher {
                     }
                 }
             }
-#endif
 #endif
         }
     }
@@ -572,7 +565,9 @@ struct Marcher {
         const double span = fmin(remaining, (2.0 * fabs(pl.s[0]) / fabs(pl.s[1]) + 32.0 * pl.abs_step));  // fmin ignores a NaN quotient
         pl.newton_limited = span < remaining;
         const double m_max = (fabs(pl.shift) + span) / pl.abs_step + 4.0;
-        pl.M = pl.base + m_max * P.drift1;
+        // (never below 2e-15: a skipped sample must also stay clear of the reference's `approx_equal(next, 0.0)` exit,
+        // |f| < 1e-15, and for a surface of tiny magnitude the error terms alone would not guarantee that)
+        pl.M = fmax(pl.base + m_max * P.drift1, 2e-15);
         // furthest sigma in [0, span] such that the whole stretch is provably inside {|g| >= M, same sign}:
         // hops of length 2b / (|g'| + sqrt(g'^2 + 2 B2 b)), b = |g| - M, B2 >= max |g''| over the span.
         // The hop length is a lower bound, so it is computed in FP32 (rounded toward safety, shortened 1 %).

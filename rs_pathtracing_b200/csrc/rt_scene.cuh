@@ -377,7 +377,9 @@ __device__ __forceinline__ bool march_needed(const DevScene& S, const double* m,
     const double step = q[1];
     end_c = end;
     if (step > 0.0) {
-        if (!(start < best)) return false;           // every candidate lies beyond start
+        // every candidate lies at or beyond start: a chord that starts past the best hit cannot win; one that starts
+        // exactly AT it still can (t == best, later shape index wins the tie); a NaN start is dropped as before
+        if (!(start <= best)) return false;
         end_c = fmin(end, best + 2.0 * step);        // a hit found later than this cannot win
     }
     return true;

@@ -170,6 +170,25 @@ def test_later_shape_wins_ties():
     assert set(np.unique(want["index"])) <= {-1, 2}
 
 
+def test_marched_candidate_at_the_best_hit_wins_the_tie():
+    """A marched shape of depth 0 returns t = the start of its bounding chord (ray_marching.rs:27-57: no loop, then
+    the range check).  With a unit Sphere in front of a Sine surface bounded by the unit sphere the two candidates are
+    the SAME double (both solve a = d.d, half_b = d.o, c = o.o - 1), and ShapeCollection's loop lets the later shape
+    win the tie (shapes/mod.rs:573-597).  The marcher's prune `chord starts beyond the best hit` must therefore be
+    strict: start == best still has to be marched"""
+    import json
+    scene = json.loads(json.dumps(TRIO))
+    ident = {"translate": [0, 0, 0], "rotate": [0, 0, 0], "scale": [1, 1, 1]}
+    scene["shapes"] = [
+        {"type": "Sphere", "name": "s", "material": "M", "transform": ident},
+        {"type": "BruteForsableShape", "name": "m", "material": "M", "transform": ident, "step": 0.01, "depth": 0,
+         "shape": {"type": "Sine", "a": 0.7, "sphere_radius": 1.0}},
+    ]
+    sc = rt.Scene.from_json(json.dumps(scene), add_random_spheres=False)
+    want = check_parity(sc, bench_rays(2048, target_radius=0.8))
+    assert (want["index"] == 1).mean() > 0.9   # (a handful of rays: the two roots differ in the last place)
+
+
 SURFACES = {
     "Heart": {"type": "Heart"},
     "Sine": {"type": "Sine", "a": 0.7, "sphere_radius": 2.0},
