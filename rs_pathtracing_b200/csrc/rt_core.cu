@@ -751,6 +751,7 @@ struct rt_scene {
     int march_version = 1;                       // 1: one ray per lane (k_march); RT_B200_MARCH=3: pool of rays per SM + per-phase queues
                                                  // (k_march3, rt_march3.cu: correct but slower, see profiles/); =2: block-local wavefront (k_march2)
     int3 march_tune = make_int3(8, 8, 8);        // k_march scheduling thresholds (RT_B200_MARCH_TUNE=a,b,c)
+    int3 march_tune0 = make_int3(32, 8, 8);      // ... at bounce level 0 (RT_B200_MARCH_TUNE0=a,b,c): neighbouring entries are samples of one pixel, so a warp refills only when all of its lanes are done and its 32 rays stay (nearly) in step: k_march -3 % on cornell_box, -4 % on dupin
     int march_grid_scale = 100;                  // percent of the occupancy grid
     bool wavefront = true;         // extend/march/shade; false = fused k_bounce (more than 32 marched shapes)
     bool shade_binned = false;     // k_shade bins a block's slots by (material kind, texture kind) before shading them
@@ -1034,6 +1035,10 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
         sc->grid_march = std::max(sc->n_sm * per_sm[0] * sc->march_grid_scale / 100, 1);
         sc->grid_march2 = sc->n_sm * per_sm[1];
         sc->grid_march3 = std::max(sc->n_sm * per_sm[2] * sc->march_grid_scale / 100, 1);
+    }
+    if (const char* tv0 = getenv("RT_B200_MARCH_TUNE0")) {
+        int a = 0, b = 0, c2 = 0;
+        if (sscanf(tv0, "%d,%d,%d", &a, &b, &c2) == 3) sc->march_tune0 = make_int3(std::max(a, 1), std::max(b, 1), std::max(c2, 1));
     }
     if (const char* mv = getenv("RT_B200_MARCH")) sc->march_version = std::min(std::max(atoi(mv), 1), 3);
     if (getenv("RT_B200_MARCH_V2")) sc->march_version = 2;
@@ -1388,7 +1393,7 @@ static void launch_bounces(rt_scene* sc, uint32_t max_depth, unsigned long long 
                 ml.ds = sc->ds; ml.kind = kind; ml.kind_mask = sc->kind_mask[kind]; ml.in = in; ml.hq = mhq;
                 ml.march_count = mq_count; ml.head = head; ml.counters = sc->d_counters; ml.count = sc->counters_on;
                 ml.stream = sc->stream; ml.version = sc->march_version; ml.grid1 = sc->grid_march; ml.grid2 = sc->grid_march2;
-                ml.grid3 = sc->grid_march3; ml.smem3 = sc->smem_march3; ml.tune = sc->march_tune; ml.march_state = sc->d_march_state;
+                ml.grid3 = sc->grid_march3; ml.smem3 = sc->smem_march3; ml.tune = level == 0 ? sc->march_tune0 : sc->march_tune; ml.march_state = sc->d_march_state;
                 ml.prefiltered = sc->march_filter; ml.grid_filter = 0;
                 rt_launch_march(ml);
                 sc->launches++;
