@@ -94,6 +94,14 @@ class DistributedRenderer:
         self._frame = None
         self._host = None
         self._exchanged = None   # event on torch's stream: the previous frame's accumulator has been read
+        # pipelined sequences (render_jobs_device): two staging copies of the shard's accumulator, so that the NEXT
+        # frame can start rendering while this one is still being exchanged and assembled
+        self._stage = [None, None]
+        self._stage_ready = [None, None]   # event on the copy stream: the staging copy is complete
+        self._stage_free = [None, None]    # event on torch's stream: the exchange has read the staging buffer
+        self._stage_k = 0
+        self._copy_stream = None
+        self._host2 = [None, None]
 
     def _params(self, w, h, spp, shard):
         return api.render_params(w, h, spp, self.depth, self.seed, self.world, shard, tile=self.tile)
@@ -132,6 +140,111 @@ class DistributedRenderer:
                            stream=int(torch.cuda.current_stream().cuda_stream) or CUDA_STREAM_LEGACY)
         self._exchanged.record()   # rank 0's own accumulator is read by k_assemble when it is the only shard
         return self._frame
+
+    # ---- pipelined sequences: frame n's exchange and assembly overlap frame n+1's render ---------------------------
+    def _exchange_assemble(self, mine, width, height, samples_number):
+        """the exchange + rank 0's k_assemble of render_device, on torch's current stream, reading `mine`"""
+        torch, dist = self.torch, self.dist
+        p = self._params(width, height, samples_number, self.rank)
+        counts = [api.shard_float4_count(p, s) for s in range(self.world)]
+        shards = exchange_to_rank0(dist, mine, counts, self.rank, self.world, self._gather_bufs)
+        if shards is None:
+            return None
+        if self.world > 1:
+            self._gather_bufs = shards
+        if self._frame is None or tuple(self._frame.shape) != (height, width, 3):
+            self._frame = torch.empty((height, width, 3), dtype=torch.float64, device=mine.device)
+        api.assemble_frame(self.dev_scene, self._params(width, height, samples_number, 0),
+                           [int(s.data_ptr()) for s in shards], int(self._frame.data_ptr()),
+                           stream=int(torch.cuda.current_stream().cuda_stream) or CUDA_STREAM_LEGACY)
+        return self._frame
+
+    def render_jobs_device(self, jobs, on_frame=None, on_rendered=None):
+        """A SEQUENCE of frames, pipelined: jobs = [(camera, width, height, samples_number), ...].  While frame n's
+        accumulators travel to rank 0 and are assembled there, every rank already renders frame n+1: the serial tail
+        of render_device (host wait -> NCCL send/recv -> k_assemble, about 1 ms whatever the frame) disappears from
+        every step but the last.  Each frame is still a complete frame on rank 0: on_frame(i, device_frame) is called
+        there right after frame i's k_assemble has been ENQUEUED on torch's current stream (consume it on that
+        stream, or copy it: the next frame's assembly overwrites it); on_rendered(i) is called on every rank when
+        its shard of frame i has finished rendering.  Returns the last device frame (rank 0) / None.
+
+        What makes the overlap safe: the shard's accumulator is copied (device to device, a few microseconds) to one
+        of two staging buffers as soon as the shard is complete, and the host waits for THAT copy -- not for the
+        exchange -- before it starts the next frame, whose k_resolve overwrites the accumulator.  The exchange reads
+        the staging buffer; a staging buffer is rewritten two frames later, after an event says its exchange is
+        over."""
+        torch = self.torch
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        if self._exchanged is not None:     # a preceding render_device(): its send may still read the accumulator
+            self._exchanged.synchronize()
+        jobs = list(jobs)
+        frame = None
+        if jobs:
+            cam, w, h, spp = jobs[0]
+            api.render_start(self.dev_scene, cam, self._params(w, h, spp, self.rank))
+        for i, (cam, w, h, spp) in enumerate(jobs):
+            ptr, n = api.render_device_result(self.dev_scene)   # host: this shard's kernels are done
+            if on_rendered is not None:
+                on_rendered(i)
+            mine = torch.as_tensor(api.DevicePointer(ptr, (n, 4), "<f8", owner=self), device=f"cuda:{self.device}")
+            k = self._stage_k = (self._stage_k + 1) % 2
+            if self._stage[k] is None or tuple(self._stage[k].shape) != (n, 4):
+                self._stage[k] = torch.empty((n, 4), dtype=torch.float64, device=mine.device)
+            cs = self._copy_stream
+            if self._stage_free[k] is not None:
+                cs.wait_event(self._stage_free[k])
+            with torch.cuda.stream(cs):
+                self._stage[k].copy_(mine)
+                if self._stage_ready[k] is None:
+                    self._stage_ready[k] = torch.cuda.Event()
+                self._stage_ready[k].record(cs)
+            self._stage_ready[k].synchronize()                  # host: the accumulator may be overwritten now
+            if i + 1 < len(jobs):
+                ncam, nw, nh, nspp = jobs[i + 1]
+                api.render_start(self.dev_scene, ncam, self._params(nw, nh, nspp, self.rank))
+            torch.cuda.current_stream().wait_event(self._stage_ready[k])
+            frame = self._exchange_assemble(self._stage[k], w, h, spp)
+            if self._stage_free[k] is None:
+                self._stage_free[k] = torch.cuda.Event()
+            self._stage_free[k].record()
+            if frame is not None and on_frame is not None:
+                on_frame(i, frame)
+        return frame
+
+    def render_many_device(self, camera: Camera, width: int, height: int, samples_number: int, count: int,
+                           on_frame=None, on_rendered=None):
+        return self.render_jobs_device([(camera, width, height, samples_number)] * count, on_frame, on_rendered)
+
+    def render_jobs(self, jobs, keep: bool = False):
+        """render_jobs_device with every frame copied to pinned host memory inside the pipeline (two host buffers,
+        asynchronous copies on torch's stream).  Returns the list of host frames when `keep` (copies), else the last
+        frame (a view of a pinned buffer, valid until the next call); None on the other ranks."""
+        torch = self.torch
+        out, events = [], []
+
+        def to_host(i, frame):
+            b = i % 2
+            if self._host2[b] is None or tuple(self._host2[b].shape) != tuple(frame.shape):
+                self._host2[b] = torch.empty(frame.shape, dtype=frame.dtype, pin_memory=True)
+            if keep and len(events) >= 2:            # the buffer is about to be reused: take frame i-2 out first
+                events[i - 2].synchronize()
+                out.append(self._host2[b].numpy().copy())
+            self._host2[b].copy_(frame, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            events.append(ev)
+
+        jobs = list(jobs)
+        last = self.render_jobs_device(jobs, on_frame=to_host)
+        if last is None:
+            return None
+        torch.cuda.current_stream().synchronize()
+        if not keep:
+            return self._host2[(len(jobs) - 1) % 2].numpy()
+        for i in range(max(len(jobs) - 2, 0), len(jobs)):
+            out.append(self._host2[i % 2].numpy().copy())
+        return out
 
     def render(self, camera: Camera, width: int, height: int, samples_number: int) -> Optional[np.ndarray]:
         frame = self.render_device(camera, width, height, samples_number)

@@ -32,6 +32,13 @@ for name, w, h, seq in CASES:
     for i, spp in enumerate(seq):   # back to back: no barrier, no synchronisation between the frames
         f = dr.render(cam, w, h, spp)
         frames.append(None if f is None else f.copy())
+    # ... and the same sequence PIPELINED (frame n's exchange overlaps frame n+1's render): the very same frames
+    piped = dr.render_jobs([(cam, w, h, spp) for spp in seq], keep=True)
+    if rank == 0:
+        for i, f in enumerate(piped):
+            same = np.array_equal(f, frames[i])
+            failed += int(not same)
+            print(f"{name} {w}x{h} pipelined frame {i}: {'identical to the unpipelined one' if same else 'DIFFERS'}", flush=True)
     if rank == 0:
         sc2 = rt.Scene.from_file(os.path.join(ROOT, "scenes", name), random_spheres_seed=1)
         d2 = sc2.device_scene(lr)
