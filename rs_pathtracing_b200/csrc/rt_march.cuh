@@ -478,7 +478,8 @@ struct Marcher {
             // half a step in matters: a ray that leaves the surface it was scattered from has |g(0)| ~ 1e-9, far
             // inside the band of a 20 000-step chord, but is 1e-4 away from zero one step later.
             const double L = miss_span(t);
-            if (hull && miss_drift_ok(L)) {
+            // (depth 0: the reference runs no loop at all and returns the hit at t = start, whatever the surface does)
+            if (hull && depth > 0 && miss_drift_ok(L)) {
                 const double ta = 0.5 * step0;
                 double sh[DEG + 1];
 #pragma unroll

@@ -189,6 +189,20 @@ def test_marched_candidate_at_the_best_hit_wins_the_tie():
     assert (want["index"] == 1).mean() > 0.9   # (a handful of rays: the two roots differ in the last place)
 
 
+def test_depth_zero_marched_shape_is_hit_at_the_start_of_its_chord():
+    """depth 0: `for _ in 0..self.depth` runs no iteration, the candidate is t = start for EVERY ray that enters the
+    bound (ray_marching.rs:27-57) -- also for the rays whose chord never comes near the surface, which the miss proof
+    of rt_march.cuh (3) must therefore leave alone"""
+    import json
+    scene = json.loads(json.dumps(TRIO))
+    ident = {"translate": [0, 0, 0], "rotate": [0, 0, 0], "scale": [1, 1, 1]}
+    scene["shapes"] = [{"type": "BruteForsableShape", "name": "m", "material": "M", "transform": ident, "step": 0.01,
+                        "depth": 0, "shape": {"type": "Star", "a": 1.3, "sphere_radius": 2.0}}]
+    sc = rt.Scene.from_json(json.dumps(scene), add_random_spheres=False)
+    want = check_parity(sc, bench_rays(2048, target_radius=1.9))
+    assert (want["index"] == 0).mean() > 0.9
+
+
 SURFACES = {
     "Heart": {"type": "Heart"},
     "Sine": {"type": "Sine", "a": 0.7, "sphere_radius": 2.0},
