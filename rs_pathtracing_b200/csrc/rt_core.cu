@@ -464,9 +464,6 @@ __device__ __forceinline__ void shade_slot(const DevScene& S, const PathQueue& i
         beta = mk(in.bx[i], in.by[i], in.bz[i]);
         pid = in.pid[i];
         const int bi = hq.index[i];
-        // the path's RNG key is a dependent gather (pid -> key[pid], DRAM): asked for here, a few hundred instructions
-        // before the sampler needs it, instead of right in front of it (the kernel's top stall is long_scoreboard)
-        const uint2 key = hq.key[pid];
         if (bi < 0) {
             L = hadamard(beta, sky(rd));  // renderer/mod.rs:41-43
         } else if (level == max_depth) {
@@ -475,6 +472,7 @@ __device__ __forceinline__ void shade_slot(const DevScene& S, const PathQueue& i
             D3 ro = mk(in.ox[i], in.oy[i], in.oz[i]);
             const rt_material mat = S.materials[S.material[bi]];
             finalize_hit(S, bi, hq.t[i], ro, rd, h, material_reads_uv(S, mat));
+            const uint2 key = hq.key[pid];
             rng.pixel = key.x;
             rng.sample = key.y;
             shading = true;
