@@ -767,7 +767,8 @@ struct rt_scene {
     // the fields q, hq, d_radiance, d_counts, d_march_state, qallocs, path_capacity and `stream` above are
     // the BOUND lane's (bind_lane swaps them); lanes[0].stream is the main stream
     PathLane lanes[RT_MAX_LANES];
-    int n_lanes = 2, cur_lane = 0;
+    int n_lanes = 3, cur_lane = 0;
+    bool lanes_from_env = false;
     std::vector<Batch> batches;
     size_t delivered = 0;          // batches already copied to the caller
     cudaEvent_t ev_frame_start = nullptr, ev_frame_stop = nullptr;
@@ -885,7 +886,10 @@ int rt_scene_create(const rt_scene_desc* d, int device, rt_scene** out) {
             cudaEventCreateWithFlags(&sc->lanes[l].done, cudaEventDisableTiming) != cudaSuccess)
             return bail(fail(RT_ERR_CUDA, "cudaStreamCreate failed"));
     }
-    sc->n_lanes = (int)std::min<size_t>(std::max<size_t>(env_size("RT_B200_LANES", 2), 1), RT_MAX_LANES);
+    // three lanes since round 2 (the marching kernels got shorter, the thin deep levels weigh more: 944 -> 957 Mpaths/s on
+    // the bench frame); a frame of fewer than 6 batches takes two of them (4 batches on 3 lanes end with a batch alone)
+    sc->n_lanes = (int)std::min<size_t>(std::max<size_t>(env_size("RT_B200_LANES", 3), 1), RT_MAX_LANES);
+    sc->lanes_from_env = getenv("RT_B200_LANES") != nullptr;
     cudaEventCreate(&sc->ev_a);
     cudaEventCreate(&sc->ev_b);
     cudaEventCreate(&sc->ev_frame_start);
@@ -1496,6 +1500,10 @@ static int render_start_single(rt_scene* sc, const rt_camera* cam, const rt_rend
     uint64_t px_per_batch = std::max<uint64_t>(1, cap_paths / spp);
     // batches alternate between lanes (streams); per-kernel timing wants the launches back to back
     int lanes_used = sc->ktiming ? 1 : sc->n_lanes;
+    if (!sc->lanes_from_env && lanes_used > 2) {
+        const uint64_t full = (std::max<uint64_t>(sc->owned_pixels, 1) + px_per_batch - 1) / px_per_batch;
+        if (full < 6) lanes_used = 2;
+    }
     if (lanes_used > 1) {  // a frame of one batch is split when each part still fills the GPU
         uint64_t split = (std::max<uint64_t>(sc->owned_pixels, 1) + lanes_used - 1) / lanes_used;
         if (split * spp >= ((uint64_t)1 << 20)) px_per_batch = std::min(px_per_batch, split);
