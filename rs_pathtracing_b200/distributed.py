@@ -102,6 +102,7 @@ class DistributedRenderer:
         self._stage_k = 0
         self._copy_stream = None
         self._host2 = [None, None]
+        self._dev_scene_b = None           # a second rt_scene on the same device: two frames of a sequence in flight
 
     def _params(self, w, h, spp, shard):
         return api.render_params(w, h, spp, self.depth, self.seed, self.world, shard, tile=self.tile)
@@ -161,9 +162,10 @@ class DistributedRenderer:
 
     def render_jobs_device(self, jobs, on_frame=None, on_rendered=None):
         """A SEQUENCE of frames, pipelined: jobs = [(camera, width, height, samples_number), ...].  While frame n's
-        accumulators travel to rank 0 and are assembled there, every rank already renders frame n+1: the serial tail
-        of render_device (host wait -> NCCL send/recv -> k_assemble, about 1 ms whatever the frame) disappears from
-        every step but the last.  Each frame is still a complete frame on rank 0: on_frame(i, device_frame) is called
+        accumulators travel to rank 0 and are assembled there, every rank already renders frame n+1 (two frames are in
+        flight on two handles of the same device): the serial tail of render_device (host wait -> NCCL send/recv ->
+        k_assemble, about 1 ms whatever the frame) and the drain of a frame's last batches disappear from every step
+        but the last.  Each frame is still a complete frame on rank 0: on_frame(i, device_frame) is called
         there right after frame i's k_assemble has been ENQUEUED on torch's current stream (consume it on that
         stream, or copy it: the next frame's assembly overwrites it); on_rendered(i) is called on every rank when
         its shard of frame i has finished rendering.  Returns the last device frame (rank 0) / None.
@@ -179,12 +181,17 @@ class DistributedRenderer:
         if self._exchanged is not None:     # a preceding render_device(): its send may still read the accumulator
             self._exchanged.synchronize()
         jobs = list(jobs)
+        # TWO frames in flight: frame n+1 is already on the device (second handle = its own streams, queues and
+        # accumulator) when frame n completes, so the drain of a frame's last batches -- the thin deep bounce levels
+        # overlap with nothing -- and the host's turn-around between two frames are filled with the next frame's work.
+        handles = [self.dev_scene, self._second_handle()] if len(jobs) > 1 else [self.dev_scene]
         frame = None
-        if jobs:
-            cam, w, h, spp = jobs[0]
-            api.render_start(self.dev_scene, cam, self._params(w, h, spp, self.rank))
+        for i in range(min(len(handles), len(jobs))):
+            cam, w, h, spp = jobs[i]
+            api.render_start(handles[i], cam, self._params(w, h, spp, self.rank))
         for i, (cam, w, h, spp) in enumerate(jobs):
-            ptr, n = api.render_device_result(self.dev_scene)   # host: this shard's kernels are done
+            hnd = handles[i % len(handles)]
+            ptr, n = api.render_device_result(hnd)   # host: this shard's kernels are done
             if on_rendered is not None:
                 on_rendered(i)
             mine = torch.as_tensor(api.DevicePointer(ptr, (n, 4), "<f8", owner=self), device=f"cuda:{self.device}")
@@ -199,10 +206,11 @@ class DistributedRenderer:
                 if self._stage_ready[k] is None:
                     self._stage_ready[k] = torch.cuda.Event()
                 self._stage_ready[k].record(cs)
-            self._stage_ready[k].synchronize()                  # host: the accumulator may be overwritten now
-            if i + 1 < len(jobs):
-                ncam, nw, nh, nspp = jobs[i + 1]
-                api.render_start(self.dev_scene, ncam, self._params(nw, nh, nspp, self.rank))
+            self._stage_ready[k].synchronize()                  # host: this handle's accumulator may be overwritten now
+            nxt = i + len(handles)
+            if nxt < len(jobs):
+                ncam, nw, nh, nspp = jobs[nxt]
+                api.render_start(hnd, ncam, self._params(nw, nh, nspp, self.rank))
             torch.cuda.current_stream().wait_event(self._stage_ready[k])
             frame = self._exchange_assemble(self._stage[k], w, h, spp)
             if self._stage_free[k] is None:
@@ -211,6 +219,24 @@ class DistributedRenderer:
             if frame is not None and on_frame is not None:
                 on_frame(i, frame)
         return frame
+
+    def _second_handle(self):
+        if self._dev_scene_b is None:
+            from . import _ffi
+            h = C.c_void_p()
+            d = self.scene.desc()
+            api._check(_ffi.core().rt_scene_create(C.byref(d), self.device, C.byref(h)))
+            self._dev_scene_b = h
+        return self._dev_scene_b
+
+    def __del__(self):
+        try:
+            if self._dev_scene_b is not None:
+                from . import _ffi
+                _ffi.core().rt_scene_destroy(self._dev_scene_b)
+                self._dev_scene_b = None
+        except Exception:
+            pass
 
     def render_many_device(self, camera: Camera, width: int, height: int, samples_number: int, count: int,
                            on_frame=None, on_rendered=None):
