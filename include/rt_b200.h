@@ -362,6 +362,13 @@ int rt_advance_exact(double a, double s, int64_t m, double* out);
  * divisions the reference performs (Vector3d / f64, src/algebra/mod.rs:299-317).  Needs no device. */
 int rt_div3_exact(const double* a, const double* s, uint64_t n, double* q);
 
+/* Host-only build of the marcher's miss proof (csrc/rt_march.cuh (3), bernstein_clear): *clear = 1 iff the Bernstein hull
+ * of  p(x) = sum_k coefficients[k] x^k  over [0, length] -- undivided, or after one / two levels of de Casteljau
+ * subdivision at the midpoint -- shows |p| > threshold with the sign of p(0) on the whole interval.  degree = 4 or 6.
+ * A sufficient test, never a necessary one: CPU tests compare it with dense sampling (clear => really clear) and
+ * measure how often it succeeds.  Needs no device. */
+int rt_bernstein_clear(const double* coefficients, int degree, double length, double threshold, int* clear);
+
 /* Host-only self-check of the conservative cull tree k_extend walks (csrc/rt_cull.cuh): builds the tree for
  * `desc` exactly like rt_scene_create and verifies, in FP64, that every group ball encloses the balls of
  * its leaves and every root ball the balls of its groups, with the slack the proof in rt_cull.cuh needs.

@@ -2027,6 +2027,22 @@ int rt_div3_exact(const double* a, const double* s, uint64_t n, double* q) {
     return RT_OK;
 }
 
+int rt_bernstein_clear(const double* coefficients, int degree, double length, double threshold, int* clear) {
+    if (!coefficients || !clear) return fail(RT_ERR_INVALID, "null argument");
+    if (degree == 6) {
+        double c[7];
+        for (int k = 0; k <= 6; k++) c[k] = coefficients[k];
+        *clear = bernstein_clear<6>(c, length, threshold) ? 1 : 0;
+    } else if (degree == 4) {
+        double c[5];
+        for (int k = 0; k <= 4; k++) c[k] = coefficients[k];
+        *clear = bernstein_clear<4>(c, length, threshold) ? 1 : 0;
+    } else {
+        return fail(RT_ERR_INVALID, "degree must be 4 or 6 (the marched surfaces' degrees along a ray)");
+    }
+    return RT_OK;
+}
+
 int rt_cull_tree_check(const rt_scene_desc* d, uint32_t* n_roots, uint32_t* n_groups, uint32_t* n_tree,
                        uint32_t* n_flat, double* worst) {
     int rc = validate_desc(d);

@@ -344,14 +344,14 @@ __device__ __forceinline__ void expand_ray(const double* q, D3 p, D3 d, double t
 // Rounding: the conversion and each subdivision level are convex combinations / binomial sums of <= 7 terms bounded
 // by scale = sum |c_k| L^k, error <= 3e-15 scale in total; err0 >= 1.6e-13 scale is subtracted once more for it.
 template <int DEG>
-__device__ __forceinline__ bool bern_hull_clear(const double (&b)[DEG + 1], double thr, bool positive) {
+__host__ __device__ __forceinline__ bool bern_hull_clear(const double (&b)[DEG + 1], double thr, bool positive) {
     bool ok = true;
 #pragma unroll
     for (int i = 0; i <= DEG; i++) ok = ok && (positive ? b[i] > thr : b[i] < -thr);   // NaN -> false
     return ok;
 }
 template <int DEG>
-__device__ __forceinline__ void bern_split(const double (&b)[DEG + 1], double (&l)[DEG + 1], double (&r)[DEG + 1]) {
+__host__ __device__ __forceinline__ void bern_split(const double (&b)[DEG + 1], double (&l)[DEG + 1], double (&r)[DEG + 1]) {
     double w[DEG + 1];
 #pragma unroll
     for (int i = 0; i <= DEG; i++) w[i] = b[i];
@@ -365,7 +365,8 @@ __device__ __forceinline__ void bern_split(const double (&b)[DEG + 1], double (&
 }
 // true: |g(tau)| > thr with the sign of c[0] for every tau in [0, L]
 template <int DEG>
-__device__ __forceinline__ bool bernstein_clear(const double (&c)[DEG + 1], double L, double thr) {
+// (host + device: the host build backs rt_bernstein_clear, which the CPU tests compare with dense sampling)
+__host__ __device__ __forceinline__ bool bernstein_clear(const double (&c)[DEG + 1], double L, double thr) {
     static_assert(DEG == 4 || DEG == 6, "binomial table");
     double b[DEG + 1];
     double pw = 1.0;
