@@ -362,6 +362,16 @@ int rt_advance_exact(double a, double s, int64_t m, double* out);
  * divisions the reference performs (Vector3d / f64, src/algebra/mod.rs:299-317).  Needs no device. */
 int rt_div3_exact(const double* a, const double* s, uint64_t n, double* q);
 
+/* Host-only build of the WHOLE exact-skip marcher (csrc/rt_march.cuh: Marcher -- the miss proof, jump planning, the
+ * exact multi-step advance, landing self-check, literal steps, the local model of the refinement levels), the very
+ * source the kernels compile: for one ray-marched shape (params8 = its rt_scene_desc params row, inverse12 = rows 0..2
+ * of its inverse transform) and n world-space rays, the candidate RayMarchingShape::ray_intersect returns
+ * (src/world/shapes/ray_marching.rs:20-74) with the chord clipped at best + 2 steps like k_march does (best = +inf:
+ * unclipped).  hit_out[i] = 1 and t_out[i] = t, or 0.  evaluations (optional) = surface evaluations spent, the measure
+ * of what exact skipping saves.  CPU tests compare t BIT FOR BIT with the oracle's literal loop.  Needs no device. */
+int rt_march_candidates_host(const double* params8, const double* inverse12, const rt_ray* rays, uint64_t n, double t_min,
+                             double t_max, double best, double* t_out, uint8_t* hit_out, uint64_t* evaluations);
+
 /* Host-only build of the marcher's miss proof (csrc/rt_march.cuh (3), bernstein_clear): *clear = 1 iff the Bernstein hull
  * of  p(x) = sum_k coefficients[k] x^k  over [0, length] -- undivided, or after one / two levels of de Casteljau
  * subdivision at the midpoint -- shows |p| > threshold with the sign of p(0) on the whole interval.  degree = 4 or 6.

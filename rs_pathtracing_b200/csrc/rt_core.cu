@@ -2027,6 +2027,42 @@ int rt_div3_exact(const double* a, const double* s, uint64_t n, double* q) {
     return RT_OK;
 }
 
+int rt_march_candidates_host(const double* params8, const double* inverse12, const rt_ray* rays, uint64_t n, double t_min,
+                             double t_max, double best, double* t_out, uint8_t* hit_out, uint64_t* evaluations) {
+    if (!params8 || !inverse12 || (n && !rays) || !t_out || !hit_out) return fail(RT_ERR_INVALID, "null argument");
+    const int kind = (int)params8[0];
+    if (!(kind >= RT_SURF_HEART && kind <= RT_SURF_CUSHION)) return fail(RT_ERR_INVALID, "unknown surface kind");
+    double G, H;
+    bounds::region_bounds(params8, &G, &H);
+    const double F = bounds::region_magnitude(params8);
+    unsigned long long total = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        const D3 ro = mk(rays[i].origin.x, rays[i].origin.y, rays[i].origin.z);
+        const D3 rd = mk(rays[i].direction.x, rays[i].direction.y, rays[i].direction.z);
+        // march_needed (rt_scene.cuh), host side: object-space ray, bounding chord, clipped by the best hit so far
+        const D3 o = xf_point(inverse12, ro), d = xf_vector(inverse12, rd);
+        double start, end, t = 0.0;
+        bool hit = false;
+        if (march_bound(params8, o, d, start, end)) {
+            double end_c = end;
+            bool needed = true;
+            if (params8[1] > 0.0) {
+                if (!(start <= best)) needed = false;
+                end_c = fmin(end, best + 2.0 * params8[1]);
+            }
+            if (needed) {
+                unsigned long long ev = 0;
+                hit = march_candidate_skip(params8, o, d, start, end_c, t_min, t_max, G, F, t, ev);
+                total += ev;
+            }
+        }
+        hit_out[i] = hit ? 1 : 0;
+        t_out[i] = hit ? t : 0.0;
+    }
+    if (evaluations) *evaluations = total;
+    return RT_OK;
+}
+
 int rt_bernstein_clear(const double* coefficients, int degree, double length, double threshold, int* clear) {
     if (!coefficients || !clear) return fail(RT_ERR_INVALID, "null argument");
     if (degree == 6) {

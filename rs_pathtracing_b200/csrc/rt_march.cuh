@@ -280,25 +280,46 @@ struct RayPoly {
 
 #define RT_MARCH_SAFETY 16.0
 
+// double -> float rounded towards +inf / -inf (the hop lengths are lower bounds: FP32, rounded to the safe side).  The
+// host forms give the same floats, so the host build of the marcher (rt_march_candidates_host) plans the same jumps.
+__host__ __device__ __forceinline__ float d2f_ru(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2float_ru(x);
+#else
+    float f = (float)x;
+    if ((double)f < x) f = nextafterf(f, INFINITY);
+    return f;
+#endif
+}
+__host__ __device__ __forceinline__ float d2f_rd(double x) {
+#ifdef __CUDA_ARCH__
+    return __double2float_rd(x);
+#else
+    float f = (float)x;
+    if ((double)f > x) f = nextafterf(f, -INFINITY);
+    return f;
+#endif
+}
+
 // magnitude arithmetic (march_bounds.hpp's Mag, device side): every operation returns an upper bound of the sum of the
 // absolute values of the terms it combines, so evaluating the surface polynomial's text on it bounds the
 // "absolute-value polynomial" at the given |coordinates| -- and anywhere closer to the origin, componentwise.
 struct MagD {
     double v;
 };
-__device__ __forceinline__ MagD operator+(MagD a, MagD b) { return MagD{a.v + b.v}; }
-__device__ __forceinline__ MagD operator-(MagD a, MagD b) { return MagD{a.v + b.v}; }
-__device__ __forceinline__ MagD operator*(MagD a, MagD b) { return MagD{a.v * b.v}; }
-__device__ __forceinline__ MagD operator+(MagD a, double b) { return MagD{a.v + fabs(b)}; }
-__device__ __forceinline__ MagD operator-(MagD a, double b) { return MagD{a.v + fabs(b)}; }
-__device__ __forceinline__ MagD operator*(MagD a, double b) { return MagD{a.v * fabs(b)}; }
-__device__ __forceinline__ MagD operator+(double a, MagD b) { return MagD{fabs(a) + b.v}; }
-__device__ __forceinline__ MagD operator-(double a, MagD b) { return MagD{fabs(a) + b.v}; }
-__device__ __forceinline__ MagD operator*(double a, MagD b) { return MagD{fabs(a) * b.v}; }
+__host__ __device__ __forceinline__ MagD operator+(MagD a, MagD b) { return MagD{a.v + b.v}; }
+__host__ __device__ __forceinline__ MagD operator-(MagD a, MagD b) { return MagD{a.v + b.v}; }
+__host__ __device__ __forceinline__ MagD operator*(MagD a, MagD b) { return MagD{a.v * b.v}; }
+__host__ __device__ __forceinline__ MagD operator+(MagD a, double b) { return MagD{a.v + fabs(b)}; }
+__host__ __device__ __forceinline__ MagD operator-(MagD a, double b) { return MagD{a.v + fabs(b)}; }
+__host__ __device__ __forceinline__ MagD operator*(MagD a, double b) { return MagD{a.v * fabs(b)}; }
+__host__ __device__ __forceinline__ MagD operator+(double a, MagD b) { return MagD{fabs(a) + b.v}; }
+__host__ __device__ __forceinline__ MagD operator-(double a, MagD b) { return MagD{fabs(a) + b.v}; }
+__host__ __device__ __forceinline__ MagD operator*(double a, MagD b) { return MagD{fabs(a) * b.v}; }
 
 // expansion of f along the ray around the current sample (t, p); the model must cover tau in [0, tau_hi]
 template <int KIND>
-__device__ __forceinline__ void expand_ray(const double* q, D3 p, D3 d, double t, double t_end, double tau_hi,
+__host__ __device__ __forceinline__ void expand_ray(const double* q, D3 p, D3 d, double t, double t_end, double tau_hi,
                                            double G, double F, RayPoly<SurfDeg<KIND>::value>& P) {
     constexpr int DEG = SurfDeg<KIND>::value;
     auto g = surface_func_t<KIND>(q, poly_lin(p.x, d.x), poly_lin(p.y, d.y), poly_lin(p.z, d.z));
@@ -443,7 +464,7 @@ struct Marcher {
     RayPoly<DEG> P;
 
     // hull: try the miss proof (3) right away (off when k_march_filter has already tried it for this ray)
-    __device__ __forceinline__ void begin(const double* q_, D3 o_, D3 d_, double start_, double end_, double G_,
+    __host__ __device__ __forceinline__ void begin(const double* q_, D3 o_, D3 d_, double start_, double end_, double G_,
                                           double F_, bool hull = true) {
         q = q_; d = d_; start = start_; end = end_; G = G_; F = F_;
         step = q[1];
@@ -509,16 +530,16 @@ struct Marcher {
     }
     // the stretch of tau (from the sample at t_now, level 0) on which the remaining samples of the ray can fall: the
     // last one evaluated is the first with t > end, i.e. at most end + step (+ rounding); 3 steps for margin
-    __device__ __forceinline__ double miss_span(double t_now) const { return (end - t_now) + 3.0 * step0; }
+    __host__ __device__ __forceinline__ double miss_span(double t_now) const { return (end - t_now) + 3.0 * step0; }
     // the accumulated t stays within half a step of t0 + n step for all the steps of the stretch (so that "the first
     // sample with t > end" is where the model says): n roundings of at most half an ulp of the largest t
-    __device__ __forceinline__ bool miss_drift_ok(double L) const {
+    __host__ __device__ __forceinline__ bool miss_drift_ok(double L) const {
         const double tmax = fmax(fabs(start), fabs(end)) + 4.0 * step0;
         return (L / step0 + 4.0) * 1.1102230246251565e-16 * tmax < 0.25 * step0;
     }
 
     // what the next iteration starts with.  RT_PHASE_END: the loops are over (finish() tells how)
-    __device__ __forceinline__ int phase() const {
+    __host__ __device__ __forceinline__ int phase() const {
         if (it >= depth) return RT_PHASE_END;
         // n > RT_MARCH_BUDGET: t + step == t (step underflowed against t); the reference would spin
         // forever, a kernel must not: report a miss
@@ -526,7 +547,7 @@ struct Marcher {
         return (skip_ok && cooldown == 0) ? RT_PHASE_ATTEMPT : RT_PHASE_LITERAL;
     }
     // valid when phase() == RT_PHASE_END
-    __device__ __forceinline__ int finish() const { return it >= depth ? RT_MARCH_DONE : RT_MARCH_MISS; }
+    __host__ __device__ __forceinline__ int finish() const { return it >= depth ? RT_MARCH_DONE : RT_MARCH_MISS; }
 
     // Try one exact multi-step jump from the current sample.  Afterwards either the state is m
     // iterations further (the reference would have executed exactly `r = next` in each of them), or
@@ -561,7 +582,7 @@ struct Marcher {
     // advanced once, by the total.  (It used to take a landing + a fresh attempt: 2.9 attempts per ray at
     // level 0, 1.4 of them failing.)  M grows from stage to stage with the number of steps the jump may then
     // cover; the stretch proven by an earlier stage only needed the smaller M of that stage.
-    __device__ __forceinline__ void plan_stage(Plan& pl) {
+    __host__ __device__ __forceinline__ void plan_stage(Plan& pl) {
         const double remaining = fmax(pl.span_limit - fabs(pl.shift), 0.0);
         // do not look further than twice the Newton distance to the next root: the |g''| bound grows with the span
         const double span = fmin(remaining, (2.0 * fabs(pl.s[0]) / fabs(pl.s[1]) + 32.0 * pl.abs_step));  // fmin ignores a NaN quotient
@@ -579,7 +600,7 @@ struct Marcher {
             b2 += (double)(k * (k - 1)) * fabs(pl.s[k]) * pw;
             pw *= span;
         }
-        pl.B2 = __double2float_ru(b2 * (1.0 + 1e-9));
+        pl.B2 = d2f_ru(b2 * (1.0 + 1e-9));
         pl.sig = 0.0;
         pl.g = pl.s[0];
         pl.dg = pl.s[1];
@@ -595,7 +616,7 @@ struct Marcher {
     // the current sample: centre half a window back (the model line only runs forward), window = 2 x 1.02 level-0
     // steps, F = the absolute-value polynomial at the window's largest |coordinates|.  P.p0 / P.t0 need not be
     // samples: plan_begin measures the displacement e of the real sample from the model line, whatever it is.
-    __device__ __forceinline__ void refine_model() {
+    __host__ __device__ __forceinline__ void refine_model() {
         const double h = 1.02 * step0;
         const D3 pc = mk(fma(-h, d.x, p.x), fma(-h, d.y, p.y), fma(-h, d.z, p.z));
         const double w = 2.0 * h;
@@ -607,7 +628,7 @@ struct Marcher {
         n += 2;
         local_model = true;
     }
-    __device__ __forceinline__ void plan_begin(Plan& pl) {
+    __host__ __device__ __forceinline__ void plan_begin(Plan& pl) {
         if (!have_poly) {   // (begin() expands when skip_ok; kept for marchers rebuilt from records)
             double tau_hi = (end - t) + 4.0 * step0;
             expand_ray<KIND>(q, p, d, t, end, tau_hi, G, F, P);
@@ -676,7 +697,7 @@ struct Marcher {
         plan_stage(pl);
     }
     // the stage ended short of the |g| = M boundary: re-plan from the point reached, if that may help
-    __device__ __forceinline__ bool plan_next_stage(Plan& pl, bool progressed) {
+    __host__ __device__ __forceinline__ bool plan_next_stage(Plan& pl, bool progressed) {
         if (!progressed) return false;
         if (pl.stage + 1 >= RT_MARCH_MAX_STAGES) {
             pl.more = true;
@@ -693,14 +714,14 @@ struct Marcher {
         return true;
     }
     // one hop; false when the planning is over
-    __device__ __forceinline__ bool plan_hop(Plan& pl) {
+    __host__ __device__ __forceinline__ bool plan_hop(Plan& pl) {
         if (pl.hop >= 32) return plan_next_stage(pl, pl.sig > 0.0);
         pl.hop++;
         if (PROF) prof[3]++;
         const double b = fabs(pl.g) - pl.M;
         if (!(b > 0.0)) return false;  // at the boundary of the uncertainty band: the jump ends here
-        const float bf = __double2float_rd(b);
-        const float af = __double2float_ru(fabs(pl.dg));
+        const float bf = d2f_rd(b);
+        const float af = d2f_ru(fabs(pl.dg));
         const float den = af + sqrtf(fmaf(af, af, 2.0f * pl.B2 * bf));
         const double dt = (double)(0.99f * (2.0f * bf / den));
         const double ns = pl.sig + dt;
@@ -723,7 +744,7 @@ struct Marcher {
         return true;
     }
     // the number of iterations that can be skipped (0: none, cooldown is set)
-    __device__ __forceinline__ long long plan_end(const Plan& pl) {
+    __host__ __device__ __forceinline__ long long plan_end(const Plan& pl) {
         double reach = fabs(pl.shift) + pl.sig;
         if (pl.miss_possible) {
             // the last stage ran into the range limit (plan_hop: sig = span, not Newton-limited): proven to the end
@@ -749,17 +770,17 @@ struct Marcher {
             return 0;
         }
         cooldown = backoff;
-        backoff = min(backoff * 2, 64);
+        backoff = backoff * 2 < 64 ? backoff * 2 : 64;
         return 0;
     }
-    __device__ __forceinline__ long long attempt_plan(Plan& pl) {
+    __host__ __device__ __forceinline__ long long attempt_plan(Plan& pl) {
         plan_begin(pl);
         while (plan_hop(pl)) {
         }
         return plan_end(pl);
     }
     // nt / np: t and p after m more iterations (advance_exact of t by step and of p by sd)
-    __device__ __forceinline__ void attempt_land(const Plan& pl, double nt, D3 np) {
+    __host__ __device__ __forceinline__ void attempt_land(const Plan& pl, double nt, D3 np) {
         const double land = surface_func<KIND>(q, np);  // the reference's `r = next` at the landing sample
         n++;
         if (PROF) prof[2]++;
@@ -783,7 +804,7 @@ struct Marcher {
         skip_ok = false;  // the model does not describe this ray: finish it with the plain loop
     }
     // the serial form (fused kernels, rt_intersect_batch)
-    __device__ __forceinline__ void attempt() {
+    __host__ __device__ __forceinline__ void attempt() {
         Plan pl;
         const long long m = attempt_plan(pl);
         if (m <= 0) return;
@@ -796,7 +817,7 @@ struct Marcher {
     }
 
     // the reference's literal step (ray_marching.rs:37-51)
-    __device__ __forceinline__ void literal() {
+    __host__ __device__ __forceinline__ void literal() {
         if (cooldown > 0) cooldown--;
         t += step;
         p.x += sd.x;
@@ -823,7 +844,7 @@ struct Marcher {
 };
 
 template <int KIND>
-__device__ __forceinline__ bool march_loop_skip(const double* q, D3 o, D3 d, double start, double end, double min_t,
+__host__ __device__ __forceinline__ bool march_loop_skip(const double* q, D3 o, D3 d, double start, double end, double min_t,
                                                 double max_t, double G, double F, double& t_out,
                                                 unsigned long long& evals) {
     Marcher<KIND> m;
@@ -840,7 +861,7 @@ __device__ __forceinline__ bool march_loop_skip(const double* q, D3 o, D3 d, dou
     return true;
 }
 
-__device__ inline bool march_candidate_skip(const double* q, D3 o, D3 d, double start, double end, double min_t,
+__host__ __device__ inline bool march_candidate_skip(const double* q, D3 o, D3 d, double start, double end, double min_t,
                                             double max_t, double G, double F, double& t, unsigned long long& evals) {
     switch ((int)q[0]) {
         case RT_SURF_HEART: return march_loop_skip<RT_SURF_HEART>(q, o, d, start, end, min_t, max_t, G, F, t, evals);

@@ -19,12 +19,12 @@ namespace rt {
 struct D3 {
     double x, y, z;
 };
-__device__ __forceinline__ D3 mk(double x, double y, double z) { return D3{x, y, z}; }
-__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
-__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
-__device__ __forceinline__ D3 operator-(D3 a) { return {-a.x, -a.y, -a.z}; }
-__device__ __forceinline__ D3 operator*(D3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
-__device__ __forceinline__ D3 operator*(double s, D3 a) { return {a.x * s, a.y * s, a.z * s}; }
+__host__ __device__ __forceinline__ D3 mk(double x, double y, double z) { return D3{x, y, z}; }
+__host__ __device__ __forceinline__ D3 operator+(D3 a, D3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__host__ __device__ __forceinline__ D3 operator-(D3 a, D3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__host__ __device__ __forceinline__ D3 operator-(D3 a) { return {-a.x, -a.y, -a.z}; }
+__host__ __device__ __forceinline__ D3 operator*(D3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+__host__ __device__ __forceinline__ D3 operator*(double s, D3 a) { return {a.x * s, a.y * s, a.z * s}; }
 // Vector / scalar (mod.rs:299-317: three IEEE divisions by the same divisor).  nvcc's inline division takes a
 // ~100-instruction slow path whenever the numerator is zero -- two components of every axis-aligned wall normal
 // -- which made `normalize` a quarter of k_shade.  div3_exact returns the same three correctly rounded
@@ -98,12 +98,12 @@ __device__ __forceinline__ D3 operator/(D3 a, double s) {
     return q;
 }
 // `*` between vectors is the dot product: (x*x' + y*y') + z*z'   (mod.rs:319-349)
-__device__ __forceinline__ double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__host__ __device__ __forceinline__ double dot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ D3 hadamard(D3 a, D3 b) { return {a.x * b.x, a.y * b.y, a.z * b.z}; }  // product, :135-141
 __device__ __forceinline__ D3 divide(D3 a, D3 b) { return {a.x / b.x, a.y / b.y, a.z / b.z}; }    // :143-150
 __device__ __forceinline__ double length(D3 a) { return sqrt(dot(a, a)); }                       // :117-120
 __device__ __forceinline__ D3 normalize(D3 a) { return a / length(a); }                          // :107-110
-__device__ __forceinline__ bool approx_zero(double a) { return fabs(a - 0.0) < 1e-15; }          // approx_equal(a, 0.0), :14-17
+__host__ __device__ __forceinline__ bool approx_zero(double a) { return fabs(a - 0.0) < 1e-15; }          // approx_equal(a, 0.0), :14-17
 // f64::min/max ignore a NaN operand; so do fmin/fmax (:168-198)
 __device__ __forceinline__ double max3(double a, double b, double c) { return fmax(fmax(a, b), c); }
 __device__ __forceinline__ double min3(double a, double b, double c) { return fmin(fmin(a, b), c); }
@@ -121,11 +121,11 @@ __device__ __forceinline__ D3 refract(D3 v, D3 n, double ratio) {  // :127-133
 
 // Transform::transform_point / transform_vector / transform_normal on rows 0..2 of the 4x4
 // (src/algebra/transform.rs:394-425).  `m` is 12 doubles, row-major 3x4.
-__device__ __forceinline__ D3 xf_point(const double* m, D3 p) {
+__host__ __device__ __forceinline__ D3 xf_point(const double* m, D3 p) {
     return {p.x * m[0] + p.y * m[1] + p.z * m[2] + m[3], p.x * m[4] + p.y * m[5] + p.z * m[6] + m[7],
             p.x * m[8] + p.y * m[9] + p.z * m[10] + m[11]};
 }
-__device__ __forceinline__ D3 xf_vector(const double* m, D3 v) {
+__host__ __device__ __forceinline__ D3 xf_vector(const double* m, D3 v) {
     return {v.x * m[0] + v.y * m[1] + v.z * m[2], v.x * m[4] + v.y * m[5] + v.z * m[6],
             v.x * m[8] + v.y * m[9] + v.z * m[10]};
 }
@@ -186,7 +186,7 @@ __host__ __device__ __forceinline__ auto surface_func_t(const double* q, T px, T
 }
 
 template <int KIND>
-__device__ __forceinline__ double surface_func(const double* q, D3 p) {
+__host__ __device__ __forceinline__ double surface_func(const double* q, D3 p) {
     return surface_func_t<KIND, double>(q, p.x, p.y, p.z);
 }
 
@@ -366,7 +366,7 @@ static __device__ __noinline__ bool torus_candidate(const double* q, D3 origin, 
 }
 
 // solve_quadratic_equation, src/algebra/equation.rs:5-15
-__device__ __forceinline__ bool solve_quadratic(double a, double half_b, double c, double& x1, double& x2) {
+__host__ __device__ __forceinline__ bool solve_quadratic(double a, double half_b, double c, double& x1, double& x2) {
     double d = half_b * half_b - a * c;
     if (d < 0.0) return false;
     if (d == 0.0) {
@@ -381,7 +381,7 @@ __device__ __forceinline__ bool solve_quadratic(double a, double half_b, double 
 }
 
 // ShapeFunction::intersect_bound — ray_marching.rs:135-145 (Heart: ellipsoid), :213-225 (sphere)
-__device__ __forceinline__ bool march_bound(const double* q, D3 o, D3 d, double& start, double& end) {
+__host__ __device__ __forceinline__ bool march_bound(const double* q, D3 o, D3 d, double& start, double& end) {
     double x1, x2;
     if ((int)q[0] == RT_SURF_HEART) {
         const double sr = 1.45;  // Heart::new, :126-131
