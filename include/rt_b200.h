@@ -367,10 +367,11 @@ int rt_div3_exact(const double* a, const double* s, uint64_t n, double* q);
  * source the kernels compile: for one ray-marched shape (params8 = its rt_scene_desc params row, inverse12 = rows 0..2
  * of its inverse transform) and n world-space rays, the candidate RayMarchingShape::ray_intersect returns
  * (src/world/shapes/ray_marching.rs:20-74) with the chord clipped at best + 2 steps like k_march does (best = +inf:
- * unclipped).  hit_out[i] = 1 and t_out[i] = t, or 0.  evaluations (optional) = surface evaluations spent, the measure
+ * unclipped).  miss_proof != 0: with the Bernstein-hull miss proof at the start of the ray, as k_march_filter runs it
+ * (the per-lane device callers leave it out).  hit_out[i] = 1 and t_out[i] = t, or 0.  evaluations (optional) = surface evaluations spent, the measure
  * of what exact skipping saves.  CPU tests compare t BIT FOR BIT with the oracle's literal loop.  Needs no device. */
 int rt_march_candidates_host(const double* params8, const double* inverse12, const rt_ray* rays, uint64_t n, double t_min,
-                             double t_max, double best, double* t_out, uint8_t* hit_out, uint64_t* evaluations);
+                             double t_max, double best, int miss_proof, double* t_out, uint8_t* hit_out, uint64_t* evaluations);
 
 /* Host-only build of the marcher's miss proof (csrc/rt_march.cuh (3), bernstein_clear): *clear = 1 iff the Bernstein hull
  * of  p(x) = sum_k coefficients[k] x^k  over [0, length] -- undivided, or after one / two levels of de Casteljau

@@ -158,7 +158,7 @@ CORE_SYMBOLS = {
     "rt_advance_exact": (C.c_int, [C.c_double, C.c_double, C.c_int64, C.POINTER(C.c_double)]),
     "rt_div3_exact": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "rt_march_candidates_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_double,
-                                          C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
+                                          C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]),
     "rt_bernstein_clear": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.POINTER(C.c_int)]),
     "rt_cull_reached": (C.c_int, [C.POINTER(SceneDesc), C.c_void_p, C.c_uint64, C.c_void_p]),
     "rt_cull_tree_check": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),

@@ -2028,7 +2028,7 @@ int rt_div3_exact(const double* a, const double* s, uint64_t n, double* q) {
 }
 
 int rt_march_candidates_host(const double* params8, const double* inverse12, const rt_ray* rays, uint64_t n, double t_min,
-                             double t_max, double best, double* t_out, uint8_t* hit_out, uint64_t* evaluations) {
+                             double t_max, double best, int miss_proof, double* t_out, uint8_t* hit_out, uint64_t* evaluations) {
     if (!params8 || !inverse12 || (n && !rays) || !t_out || !hit_out) return fail(RT_ERR_INVALID, "null argument");
     const int kind = (int)params8[0];
     if (!(kind >= RT_SURF_HEART && kind <= RT_SURF_CUSHION)) return fail(RT_ERR_INVALID, "unknown surface kind");
@@ -2052,7 +2052,7 @@ int rt_march_candidates_host(const double* params8, const double* inverse12, con
             }
             if (needed) {
                 unsigned long long ev = 0;
-                hit = march_candidate_skip(params8, o, d, start, end_c, t_min, t_max, G, F, t, ev);
+                hit = march_candidate_skip(params8, o, d, start, end_c, t_min, t_max, G, F, t, ev, miss_proof != 0);
                 total += ev;
             }
         }

@@ -843,12 +843,15 @@ struct Marcher {
     }
 };
 
+// `hull`: try the miss proof (3) when the ray starts.  The per-lane callers (k_intersect_batch, the fused k_bounce) pass
+// false: a warp waits for its slowest lane there, which is a ray that hits, and the proof only adds to its work
+// (cfg 2 on the cornell shape list: 509 -> 542 Mrays/s without it); the wavefront runs it in k_march_filter.
 template <int KIND>
 __host__ __device__ __forceinline__ bool march_loop_skip(const double* q, D3 o, D3 d, double start, double end, double min_t,
-                                                double max_t, double G, double F, double& t_out,
-                                                unsigned long long& evals) {
+                                                         double max_t, double G, double F, double& t_out,
+                                                         unsigned long long& evals, bool hull) {
     Marcher<KIND> m;
-    m.begin(q, o, d, start, end, G, F);
+    m.begin(q, o, d, start, end, G, F, hull);
     int ph;
     while ((ph = m.phase()) != RT_PHASE_END) {
         if (ph == RT_PHASE_ATTEMPT) m.attempt();
@@ -862,14 +865,15 @@ __host__ __device__ __forceinline__ bool march_loop_skip(const double* q, D3 o, 
 }
 
 __host__ __device__ inline bool march_candidate_skip(const double* q, D3 o, D3 d, double start, double end, double min_t,
-                                            double max_t, double G, double F, double& t, unsigned long long& evals) {
+                                                     double max_t, double G, double F, double& t, unsigned long long& evals,
+                                                     bool hull = false) {
     switch ((int)q[0]) {
-        case RT_SURF_HEART: return march_loop_skip<RT_SURF_HEART>(q, o, d, start, end, min_t, max_t, G, F, t, evals);
-        case RT_SURF_SINE: return march_loop_skip<RT_SURF_SINE>(q, o, d, start, end, min_t, max_t, G, F, t, evals);
-        case RT_SURF_STAR: return march_loop_skip<RT_SURF_STAR>(q, o, d, start, end, min_t, max_t, G, F, t, evals);
-        case RT_SURF_DUPIN: return march_loop_skip<RT_SURF_DUPIN>(q, o, d, start, end, min_t, max_t, G, F, t, evals);
-        case RT_SURF_HUNTS: return march_loop_skip<RT_SURF_HUNTS>(q, o, d, start, end, min_t, max_t, G, F, t, evals);
-        default: return march_loop_skip<RT_SURF_CUSHION>(q, o, d, start, end, min_t, max_t, G, F, t, evals);
+        case RT_SURF_HEART: return march_loop_skip<RT_SURF_HEART>(q, o, d, start, end, min_t, max_t, G, F, t, evals, hull);
+        case RT_SURF_SINE: return march_loop_skip<RT_SURF_SINE>(q, o, d, start, end, min_t, max_t, G, F, t, evals, hull);
+        case RT_SURF_STAR: return march_loop_skip<RT_SURF_STAR>(q, o, d, start, end, min_t, max_t, G, F, t, evals, hull);
+        case RT_SURF_DUPIN: return march_loop_skip<RT_SURF_DUPIN>(q, o, d, start, end, min_t, max_t, G, F, t, evals, hull);
+        case RT_SURF_HUNTS: return march_loop_skip<RT_SURF_HUNTS>(q, o, d, start, end, min_t, max_t, G, F, t, evals, hull);
+        default: return march_loop_skip<RT_SURF_CUSHION>(q, o, d, start, end, min_t, max_t, G, F, t, evals, hull);
     }
 }
 

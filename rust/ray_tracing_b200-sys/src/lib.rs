@@ -111,7 +111,7 @@ extern "C" {
     pub fn rt_advance_exact(a: f64, s: f64, m: i64, out: *mut f64) -> c_int;
     pub fn rt_div3_exact(a: *const f64, s: *const f64, n: u64, q: *mut f64) -> c_int;
     pub fn rt_march_candidates_host(params8: *const f64, inverse12: *const f64, rays: *const rt_ray, n: u64, t_min: f64,
-                                    t_max: f64, best: f64, t_out: *mut f64, hit_out: *mut u8, evaluations: *mut u64) -> c_int;
+                                    t_max: f64, best: f64, miss_proof: c_int, t_out: *mut f64, hit_out: *mut u8, evaluations: *mut u64) -> c_int;
     pub fn rt_bernstein_clear(coefficients: *const f64, degree: c_int, length: f64, threshold: f64, clear: *mut c_int) -> c_int;
     pub fn rt_cull_reached(desc: *const rt_scene_desc, rays: *const rt_ray, n_rays: u64, reached: *mut u8) -> c_int;
     pub fn rt_cull_tree_check(desc: *const rt_scene_desc, n_roots: *mut u32, n_groups: *mut u32, n_tree: *mut u32,

@@ -59,7 +59,7 @@ def make_test_rays(surface, scale, n, seed):
     return np.concatenate([rays, np.array(ax)])
 
 
-def host_march(sc, rays, best=np.inf, t_min=0.001):
+def host_march(sc, rays, best=np.inf, t_min=0.001, miss_proof=True):
     d = sc.desc()
     params = np.array([d.params[k] for k in range(8)], dtype=np.float64)
     inverse = np.array([d.inverse[k] for k in range(12)], dtype=np.float64)
@@ -68,7 +68,7 @@ def host_march(sc, rays, best=np.inf, t_min=0.001):
     hit = np.zeros(len(rays), np.uint8)
     ev = C.c_uint64(0)
     rc = _ffi.core().rt_march_candidates_host(params.ctypes.data, inverse.ctypes.data, rays.ctypes.data, len(rays), t_min,
-                                              np.inf, best, t.ctypes.data, hit.ctypes.data, C.byref(ev))
+                                              np.inf, best, int(miss_proof), t.ctypes.data, hit.ctypes.data, C.byref(ev))
     assert rc == 0
     return hit.astype(bool), t, ev.value
 
@@ -85,11 +85,14 @@ def test_host_marcher_reproduces_the_literal_loop(surface, scale, rotate, step, 
     sc = one_shape_scene(surface, scale, rotate, step, depth)
     rays = make_test_rays(surface, scale, n, seed=hash(surface) % 1000 + int(scale))
     want = po.OracleScene(sc.desc()).intersect_batch(rays)
-    hit, t, evals = host_march(sc, rays)
     want_hit = want["index"] == 0
-    assert np.array_equal(hit, want_hit), f"{(hit != want_hit).sum()} rays: hit / miss differs"
     assert want_hit.mean() > 0.05, "the test rays must actually hit the surface"
-    assert np.array_equal(t[hit].view(np.uint64), want["t"][want_hit].view(np.uint64)), "t is not bit-identical"
+    evals = {}
+    for miss_proof in (True, False):    # as k_march_filter + k_march run it / as the per-lane callers do
+        hit, t, evals[miss_proof] = host_march(sc, rays, miss_proof=miss_proof)
+        assert np.array_equal(hit, want_hit), f"{(hit != want_hit).sum()} rays: hit / miss differs"
+        assert np.array_equal(t[hit].view(np.uint64), want["t"][want_hit].view(np.uint64)), "t is not bit-identical"
+    assert evals[True] <= evals[False]  # the proof only ever saves evaluations
 
 
 def test_host_marcher_clipped_chord_and_work_saved():
